@@ -1,0 +1,136 @@
+"""CPU suite: pins the C restatement (oracle/vcfc_oracle.c) against the reference.
+
+(a) SURVEY.md 8(c) known-answer vectors, typed in here by hand from the survey table;
+(b) tests/golden/ fixtures written by the unmodified reference binary;
+(c) the reference binary run live on fresh seeded inputs, when oracle/_ref is present.
+"""
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import pytest
+
+import goldenlib
+import oraclelib as O
+import vcfgen
+
+HDR = (b"##fileformat=VCFv4.1\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
+       b"#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + b"\t".join(b"S%d" % i for i in range(8)) + b"\n")
+
+
+def enc1(line: bytes) -> bytes:
+    rc, out, nl, _ = O.compress_block(line)
+    assert rc == 0 and nl == 1
+    return out
+
+
+def test_kat_survey_8c_line1():
+    req = b"1\t100\trs1\tA\tT\t100\tPASS\tAC=1\tGT\t"
+    line = req + b"0|0\t0|0\t0|0\t0|1\t0|1\t1|0\t1|1\t0|0\n"
+    assert len(req) == 31
+    assert enc1(line) == bytes.fromhex("c0000029c000001f") + req + bytes.fromhex("03a2c181010a")
+
+
+def test_kat_survey_8c_line2():
+    req = b"1\t102\trs2\tA\tT,G\t100\tPASS\tAC=1\tGT\t"
+    line = req + b"0|2\t0|0\t./.\t0/0\t0/1\t2|2\t1|1\t2|1\n"
+    tail = bytes.fromhex("e1307c320901e12e2f2e09e1302f3009e1302f3109e1327c320981e1327c310a")
+    assert enc1(line) == bytes.fromhex("c0000045c0000021") + req + tail
+
+
+def test_kat_survey_8c_line3_gtdp():
+    req = b"1\t104\trs3\tA\tT\t100\tPASS\tAC=1\tGT:DP\t"
+    s = [b"0|0:3", b"0|0:3", b"0|1:9", b"0|0:3"] * 2
+    body = b"".join(b"\xe1" + x + (b"\t" if i < 7 else b"") for i, x in enumerate(s))
+    assert enc1(req + b"\t".join(s) + b"\n") == bytes.fromhex("c000005ec0000022") + req + body + b"\n"
+
+
+def test_kat_survey_8c_line4_all_ref():
+    req = b"1\t106\trs4\tA\tT\t100\tPASS\tAC=1\tGT\t"
+    assert enc1(req + b"\t".join([b"0|0"] * 8) + b"\n") == bytes.fromhex("c0000025c000001f") + req + b"\x08\n"
+
+
+@pytest.mark.parametrize("gt,n,expect", [
+    (b"0|0", 300, "7f7f2e"), (b"0|1", 70, "bfbfa8"), (b"0|0", 127, "7f"), (b"1|1", 31, "9f"),
+    (b"1|0", 32, "dfc1"), (b"0|0", 128, "7f01"), (b"0|1", 62, "bfbf"), (b"1|1", 63, "9f9f81"),
+])
+def test_run_chunking(gt, n, expect):
+    req = b"1\t1\t.\tA\tT\t.\t.\t.\tGT\t"
+    out = enc1(req + b"\t".join([gt] * n) + b"\n")
+    assert out[8 + len(req):-1].hex() == expect
+
+
+def test_error_codes():
+    assert O.compress_block(b"1\t5\t.\tA\tC\t.\t.\t.\n")[0] == O.E_EIGHTCOLS
+    assert O.compress_block(b"1\t5\t.\tA\tC\t.\t.\n")[0] == O.E_TOOFEW
+    assert O.compress_block(b"\t\t\n")[0] == O.E_TOOFEW
+    rc, out, nl, el = O.compress_block(b"1\t5\t.\tA\tC\t.\t.\t.\tGT\t0|0\nbad\n")
+    assert rc == O.E_TOOFEW and el == 1 and nl == 1
+
+
+def test_golden_fixtures(golden):
+    assert len(golden) >= 12
+    for name, g in golden.items():
+        rc, out = O.compress_vcf(g["vcf"])
+        if g["entry"]["compress_rc"] != 0:
+            assert rc != 0, name            # the reference aborted on this input
+            continue
+        assert rc == 0, name
+        assert out == g["vcfc"], name
+        assert hashlib.sha256(out).hexdigest() == g["entry"]["vcfc_sha256"]
+        rc, txt = O.decompress_vcfc(g["vcfc"])
+        assert rc == 0, name
+        assert txt == g["rt"], name
+        assert hashlib.sha256(txt).hexdigest() == g["entry"]["rt_sha256"]
+
+
+def test_offsets_and_counts():
+    _, data = vcfgen.random_vcf_like(50, 40, seed=3)
+    rc, out, nl, _, offs = O.compress_block(data, want_offsets=True)
+    assert rc == 0 and nl == 50 and offs[0] == 0
+    for i, o in enumerate(offs):
+        ll = int.from_bytes(out[o:o + 4], "big") & 0x3FFFFFFF
+        nxt = offs[i + 1] if i + 1 < nl else len(out)
+        assert o + 4 + ll == nxt
+
+
+def test_decode_rejects_bad_input():
+    _, data = vcfgen.random_vcf_like(3, 8, seed=1)
+    rc, out, _, _ = O.compress_block(data)
+    assert O.decompress_block(out, 8)[0] == 0
+    assert O.decompress_block(out[:-1], 8)[0] == O.E_TRUNC
+    bad = bytearray(out); bad[0] = 0x40
+    assert O.decompress_block(bytes(bad), 8)[0] == O.E_FORMAT
+    assert O.decompress_block(out, 9)[0] < 0
+
+
+@pytest.mark.skipif(not O.have_ref_binary(), reason="oracle/_ref/main_release not built")
+@pytest.mark.parametrize("maker,args", [
+    (vcfgen.random_vcf_like, dict(n_lines=120, n_samples=333, seed=11)),
+    (vcfgen.random_vcf_like, dict(n_lines=30, n_samples=2504, seed=12, probs=(0.5, 0.4, 0.1))),
+    (vcfgen.kg_like, dict(n_lines=40, n_samples=1000, seed=13)),
+])
+def test_live_reference_binary(maker, args):
+    h, d = maker(**args)
+    vcf = h + d
+    with tempfile.TemporaryDirectory() as wd:
+        ip, op, rp = (os.path.join(wd, x) for x in ("a.vcf", "a.vcfc", "a.rt"))
+        open(ip, "wb").write(vcf)
+        assert subprocess.run([O.REF_BIN, "compress", ip, op]).returncode == 0
+        ref = open(op, "rb").read()
+        rc, mine = O.compress_vcf(vcf)
+        assert rc == 0 and mine == ref
+        assert subprocess.run([O.REF_BIN, "decompress", op, rp]).returncode == 0
+        rc, txt = O.decompress_vcfc(ref)
+        assert rc == 0 and txt == open(rp, "rb").read() == vcf
+
+
+def test_file_drivers(tmp_path):
+    h, d = vcfgen.random_vcf_like(20, 50, seed=2)
+    ip, op, rp = (str(tmp_path / x) for x in ("a.vcf", "a.vcfc", "a.rt"))
+    open(ip, "wb").write(h + d)
+    assert O.lib().vcfc_oracle_compress_file(ip.encode(), op.encode()) == 0
+    assert open(op, "rb").read() == O.compress_vcf(h + d)[1]
+    assert O.lib().vcfc_oracle_decompress_file(op.encode(), rp.encode()) == 0
+    assert open(rp, "rb").read() == h + d
