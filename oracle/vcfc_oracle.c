@@ -262,7 +262,10 @@ long vcfc_oracle_parse_headers(const uint8_t *in, size_t in_len, uint64_t *sampl
     int got_meta = 0, got_header = 0;
     uint64_t sc = 0;
     for (;;) {
-        if (p >= in_len) { if (!got_meta || !got_header) return VCFC_E_HEADER; break; }
+        /* compress.cpp:1136-1153: at EOF the read fails but the stale first byte is still '#', so the
+         * reference throws either way ("missing headers" / "row after already reading a header"):
+         * a file without data lines does not decode [probed, SURVEY.md 8a]. */
+        if (p >= in_len) return VCFC_E_HEADER;
         if (in[p] != '#') { if (!got_meta || !got_header) return VCFC_E_HEADER; break; }
         if (got_header) return VCFC_E_HEADER;
         if (p + 1 >= in_len) return VCFC_E_HEADER;

@@ -1,0 +1,271 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bit-exact is the bar (byte/integer work).  Sources of truth, in order:
+  tests/golden/   fixtures written by the UNMODIFIED reference binary (oracle/make_golden.py)
+  oraclelib       the C restatement, itself pinned to those fixtures by tests/test_oracle.py
+Nothing here reads /root/reference.
+"""
+import hashlib
+import importlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import goldenlib
+import oraclelib as O
+import vcfgen
+
+pytestmark = pytest.mark.gpu
+pkg = importlib.import_module("vcf-compression_b200")
+
+
+@pytest.fixture(scope="module")
+def codec():
+    c = pkg.Codec(0)          # raises if the CUDA library / device is missing: no silent fallback
+    yield c
+    c.close()
+
+
+@pytest.fixture(params=["auto", "generic"])
+def any_path(request, codec):
+    """Run a test through the default dispatch and through the generic kernels."""
+    codec.force_generic(request.param == "generic")
+    yield codec
+    codec.force_generic(False)
+
+
+def check_block(codec, data: bytes, sample_count=None, expect_path=None):
+    """encode == oracle (bytes, line count, offsets); decode(encode) == oracle decode."""
+    orc, oout, onl, oel, ooffs = O.compress_block(data, want_offsets=True)
+    rc, out, nl, el, offs = codec.compress_block(data, want_offsets=True)
+    assert rc == (-orc if orc < 0 else 0), (rc, orc)
+    assert out == oout
+    assert nl == onl
+    if orc != 0:
+        assert el == oel
+        return out
+    assert offs == ooffs
+    if expect_path is not None:
+        assert codec.last_path == expect_path
+    if sample_count is not None and out:
+        drc, txt, dnl, _ = codec.decompress_block(out, sample_count)
+        orc2, otxt, onl2, _ = O.decompress_block(oout, sample_count)
+        assert drc == (-orc2 if orc2 < 0 else 0)
+        assert txt == otxt and dnl == onl2
+    return out
+
+
+# ---- known-answer vectors, SURVEY.md 8(c) ------------------------------------------------------
+def test_kat_lines(any_path):
+    req = b"1\t100\trs1\tA\tT\t100\tPASS\tAC=1\tGT\t"
+    line = req + b"0|0\t0|0\t0|0\t0|1\t0|1\t1|0\t1|1\t0|0\n"
+    rc, out, nl, _ = any_path.compress_block(line)
+    assert rc == 0 and nl == 1
+    assert out == bytes.fromhex("c0000029c000001f") + req + bytes.fromhex("03a2c181010a")
+    req2 = b"1\t102\trs2\tA\tT,G\t100\tPASS\tAC=1\tGT\t"
+    line2 = req2 + b"0|2\t0|0\t./.\t0/0\t0/1\t2|2\t1|1\t2|1\n"
+    tail = bytes.fromhex("e1307c320901e12e2f2e09e1302f3009e1302f3109e1327c320981e1327c310a")
+    rc, out, _, _ = any_path.compress_block(line2)
+    assert rc == 0 and out == bytes.fromhex("c0000045c0000021") + req2 + tail
+    rc, txt, nl, _ = any_path.decompress_block(out, 8)
+    assert rc == 0 and txt == line2 and nl == 1
+
+
+@pytest.mark.parametrize("gt,n,expect", [
+    (b"0|0", 300, "7f7f2e"), (b"0|1", 70, "bfbfa8"), (b"0|0", 127, "7f"), (b"1|1", 31, "9f"),
+    (b"1|0", 32, "dfc1"), (b"0|0", 128, "7f01"), (b"0|1", 62, "bfbf"), (b"1|1", 63, "9f9f81"),
+])
+def test_run_chunking(any_path, gt, n, expect):
+    req = b"1\t1\t.\tA\tT\t.\t.\t.\tGT\t"
+    line = req + b"\t".join([gt] * n) + b"\n"
+    rc, out, _, _ = any_path.compress_block(line)
+    assert rc == 0 and out[8 + len(req):-1].hex() == expect
+    rc, txt, _, _ = any_path.decompress_block(out, n)
+    assert rc == 0 and txt == line
+
+
+# ---- fixtures from the reference binary ---------------------------------------------------------
+def test_golden_fixtures(any_path, golden):
+    for name, g in golden.items():
+        rc, out = any_path.compress_vcf(g["vcf"])
+        if g["entry"]["compress_rc"] != 0:
+            assert rc != 0, name
+            continue
+        assert rc == 0, name
+        assert out == g["vcfc"], name
+        assert hashlib.sha256(out).hexdigest() == g["entry"]["vcfc_sha256"]
+        rc, txt = any_path.decompress_vcfc(g["vcfc"])
+        if g["entry"].get("decompress_rc", 0) != 0:
+            assert rc != 0, name
+            continue
+        assert rc == 0, name
+        assert txt == g["rt"], name
+
+
+# ---- seeded inputs against the oracle -------------------------------------------------------------
+@pytest.mark.parametrize("maker,args", [
+    (vcfgen.random_vcf_like, dict(n_lines=200, n_samples=333, seed=11)),
+    (vcfgen.random_vcf_like, dict(n_lines=64, n_samples=2504, seed=12)),
+    (vcfgen.random_vcf_like, dict(n_lines=40, n_samples=2504, seed=13, probs=(0.5, 0.4, 0.1))),
+    (vcfgen.random_vcf_like, dict(n_lines=3000, n_samples=7, seed=14)),
+    (vcfgen.random_vcf_like, dict(n_lines=500, n_samples=1, seed=15)),
+    (vcfgen.random_vcf_like, dict(n_lines=3, n_samples=100000, seed=16, probs=(0.98, 0.02, 0.0))),
+    (vcfgen.kg_like, dict(n_lines=300, n_samples=2504, seed=17)),
+    (vcfgen.kg_like, dict(n_lines=100, n_samples=1000, seed=18)),
+])
+def test_seeded_vs_oracle(any_path, maker, args):
+    _, data = maker(**args)
+    check_block(any_path, data, sample_count=args["n_samples"])
+
+
+def test_edge_case_lines(any_path):
+    for s in (1, 3, 8, 40, 129):
+        lines = vcfgen.edge_case_lines(s)
+        check_block(any_path, b"".join(lines), sample_count=s)
+        for ln in lines:
+            check_block(any_path, ln, sample_count=s)
+
+
+def test_run_length_lines(any_path):
+    check_block(any_path, b"".join(vcfgen.run_length_lines()), sample_count=700)
+    check_block(any_path, b"".join(vcfgen.run_length_lines(lengths=(126, 127, 128, 381), n_samples=2504)), sample_count=2504)
+
+
+def test_ragged_and_empty_inputs(any_path):
+    rc, out, nl, _ = any_path.compress_block(b"")
+    assert rc == 0 and out == b"" and nl == 0
+    _, data = vcfgen.random_vcf_like(5, 9, seed=3)
+    lines = data.split(b"\n")[:-1]
+    check_block(any_path, b"\n\n" + b"\n\n\n".join(lines) + b"\n\n", sample_count=9)   # blank lines are dropped
+    check_block(any_path, data[:-1], sample_count=9)                                    # no final newline
+    check_block(any_path, data.replace(b"\n", b"\r\n"), sample_count=9)                 # CR-LF
+    check_block(any_path, b"1\t5\t.\tA\tC\t.\t.\t.\tGT\n", sample_count=0)              # 9 columns, no samples
+    check_block(any_path, lines[0] + b"\t\n" + lines[1] + b"\n")                        # trailing tab
+    check_block(any_path, lines[0].replace(b"\t0|0\t", b"\t\t", 1) + b"\n")             # empty field
+    wide = b"1\t7\t.\tA\tC\t.\t.\t" + b"X" * 70000 + b"\tGT\t" + b"\t".join([b"0|1"] * 50) + b"\n"
+    check_block(any_path, wide + lines[2] + b"\n" + wide, sample_count=None)            # a 70 kB INFO column
+
+
+def test_error_lines(any_path):
+    ok = b"1\t5\t.\tA\tC\t.\t.\t.\tGT\t0|0\n"
+    for bad, code in ((b"1\t5\t.\tA\tC\t.\t.\t.\n", pkg.E_EIGHTCOLS), (b"1\t5\t.\tA\tC\t.\t.\n", pkg.E_TOOFEW),
+                      (b"\t\t\n", pkg.E_TOOFEW), (b"bad\n", pkg.E_TOOFEW)):
+        rc, out, nl, el = any_path.compress_block(bad)
+        assert rc == code and nl == 0 and el == 0 and out == b""
+        rc, out, nl, el = any_path.compress_block(ok * 3 + bad + ok)
+        orc, oout, onl, oel = O.compress_block(ok * 3 + bad + ok)
+        assert rc == code == -orc and nl == onl == 3 and el == oel == 3 and out == oout
+    rc, out, nl, _ = any_path.compress_block(ok, out_cap=10)
+    assert rc == pkg.E_CAP
+
+
+def test_decode_rejects_bad_input(any_path):
+    _, data = vcfgen.random_vcf_like(3, 8, seed=1)
+    rc, out, _, _ = any_path.compress_block(data)
+    assert any_path.decompress_block(out, 8)[0] == 0
+    assert any_path.decompress_block(out[:-1], 8)[0] == pkg.E_TRUNC
+    bad = bytearray(out)
+    bad[0] = 0x40
+    assert any_path.decompress_block(bytes(bad), 8)[0] == pkg.E_FORMAT
+    assert any_path.decompress_block(out, 9)[0] != 0
+    assert any_path.decompress_block(out, 7)[0] != 0
+    rc, txt, nl, _ = any_path.decompress_block(out + b"\x01\x02\x03", 8)     # <8 trailing bytes = EOF
+    assert rc == 0 and txt == data and nl == 3
+    assert any_path.decompress_block(out, 8, out_cap=20)[0] == pkg.E_CAP
+
+
+def test_chunked_host_path_matches_single_call(codec, monkeypatch):
+    """The host-pointer API splits at newlines into chunks; bytes must not depend on the chunk size."""
+    _, data = vcfgen.random_vcf_like(400, 2504, seed=21)       # ~4 MB
+    ref = O.compress_block(data, want_offsets=True)
+    monkeypatch.setenv("VCFC_CHUNK_MB", "1")
+    monkeypatch.setenv("VCFC_DCHUNK_MB", "1")
+    rc, out, nl, _, offs = codec.compress_block(data, want_offsets=True)
+    assert rc == 0 and out == ref[1] and nl == ref[2] and offs == ref[4]
+    rc, txt, nl2, _ = codec.decompress_block(out, 2504)
+    assert rc == 0 and txt == data and nl2 == nl
+    bad = data[:2_000_000] + b"oops\n" + data[2_000_000:]
+    bad = bad[:bad.rfind(b"\n", 0, 2_000_000) + 1] + b"oops\n" + data[data.rfind(b"\n", 0, 2_000_000) + 1:]
+    orc, oout, onl, oel = O.compress_block(bad)
+    rc, out, nl, el = codec.compress_block(bad)
+    assert rc == -orc and out == oout and nl == onl and el == oel
+
+
+def test_device_pointer_api(codec):
+    import torch
+    _, data = vcfgen.kg_like(200, 2504, seed=5)
+    ref = O.compress_block(data)[1]
+    dev = torch.device("cuda:0")
+    d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
+    d_out = torch.empty(len(data) * 2 + 4096, dtype=torch.uint8, device=dev)
+    d_res = torch.zeros(4, dtype=torch.int64, device=dev)
+    d_offs = torch.zeros(256, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    codec.encode_dev(d_in.data_ptr(), len(data), d_out.data_ptr(), d_out.numel(), d_res.data_ptr(), st,
+                     d_offs.data_ptr(), 256)
+    r = codec.fetch_result(d_res.data_ptr(), st)
+    assert r.status == 0 and r.n_lines == 200 and r.out_len == len(ref)
+    assert bytes(d_out[:r.out_len].cpu().numpy()) == ref
+    offs = d_offs[:200].cpu().numpy()
+    assert offs[0] == 0 and all(ref[o] >> 6 == 3 for o in offs)
+    sz = codec.decode_size_dev(d_out.data_ptr(), r.out_len, 2504, st)
+    assert sz.status == 0 and sz.out_len == len(data) and sz.n_lines == 200
+    d_txt = torch.empty(len(data) + 64, dtype=torch.uint8, device=dev)
+    codec.decode_dev(d_out.data_ptr(), r.out_len, 2504, d_txt.data_ptr(), d_txt.numel(), d_res.data_ptr(), st)
+    r2 = codec.fetch_result(d_res.data_ptr(), st)
+    assert r2.status == 0 and r2.out_len == len(data)
+    assert torch.equal(d_txt[:len(data)], d_in)
+
+
+# ---- file drivers and the CLI (reference verbs) ----------------------------------------------------
+def test_file_drivers_and_cli(codec, golden, tmp_path):
+    g = golden["refgen_300x40"]
+    ip, op, rp = (str(tmp_path / x) for x in ("a.vcf", "a.vcfc", "a.rt"))
+    open(ip, "wb").write(g["vcf"])
+    assert codec.compress(ip, op) == 0
+    assert open(op, "rb").read() == g["vcfc"]
+    assert codec.decompress2_fd(op, rp) == 0
+    assert open(rp, "rb").read() == g["rt"]
+    if os.path.exists(pkg.CLI_PATH):
+        op2, rp2 = str(tmp_path / "b.vcfc"), str(tmp_path / "b.rt")
+        assert subprocess.run([pkg.CLI_PATH, "compress", ip, op2]).returncode == 0
+        assert open(op2, "rb").read() == g["vcfc"]
+        assert subprocess.run([pkg.CLI_PATH, "decompress", op2, rp2]).returncode == 0
+        assert open(rp2, "rb").read() == g["rt"]
+        bad = str(tmp_path / "bad.vcf")
+        open(bad, "wb").write(golden["abort_8cols"]["vcf"])
+        assert subprocess.run([pkg.CLI_PATH, "compress", bad, op2], capture_output=True).returncode != 0
+
+
+def test_query_matches_reference_outputs(codec, golden, tmp_path):
+    qs = goldenlib.manifest()["_queries"]
+    for name, cases in qs.items():
+        fp = str(tmp_path / (name + ".vcfc"))
+        open(fp, "wb").write(golden[name]["vcfc"])
+        for c in cases:
+            outp = str(tmp_path / "q.out")
+            fd = os.open(outp, os.O_CREAT | os.O_TRUNC | os.O_WRONLY, 0o644)
+            rc = codec.query(fp, c["q"], fd)
+            os.close(fd)
+            got = open(outp, "rb").read()
+            assert rc == 0 and len(got) == c["len"], (name, c["q"])
+            assert hashlib.sha256(got).hexdigest() == c["sha256"], (name, c["q"])
+    assert codec.query(fp, "1:5", 1) == pkg.E_QUERY
+
+
+def test_live_reference_binary_if_shipped(codec, tmp_path):
+    """oracle/_ref/main_release (the unmodified reference, prebuilt) travels to the GPU box."""
+    if not O.have_ref_binary():
+        pytest.skip("oracle/_ref/main_release not shipped")
+    h, d = vcfgen.random_vcf_like(150, 2504, seed=31)
+    ip, op, rp = (str(tmp_path / x) for x in ("a.vcf", "a.vcfc", "a.rt"))
+    open(ip, "wb").write(h + d)
+    if subprocess.run([O.REF_BIN, "compress", ip, op]).returncode != 0:
+        pytest.skip("reference binary does not run on this box")
+    rc, mine = codec.compress_vcf(h + d)
+    assert rc == 0 and mine == open(op, "rb").read()
+    assert subprocess.run([O.REF_BIN, "decompress", op, rp]).returncode == 0
+    rc, txt = codec.decompress_vcfc(mine)
+    assert rc == 0 and txt == open(rp, "rb").read() == h + d

@@ -1,0 +1,268 @@
+// vcfc_files.cu -- host-side file drivers with the reference's verb semantics.  Only host code:
+// '#' lines pass through on the host (compress.cpp:222-238), data-line regions go through the
+// block codecs (GPU).  Restates, does not copy:
+//   compress()                          src/compress.cpp:205-257
+//   decompress2_fd()                    src/compress.cpp:1214-1257
+//   decompress2_metadata_headers_fd()   src/compress.cpp:1108-1211
+//   query_compressed_file()             src/main.cpp:3777-3929
+//   parse_coordinate_string()           src/main.cpp:3993-4026
+#include <errno.h>
+#include <fcntl.h>
+#include <stdlib.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <string>
+#include <vector>
+
+#include "vcfc_internal.h"
+
+namespace {
+
+struct HostFile {
+    uint8_t* p = nullptr;
+    size_t   n = 0;
+    ~HostFile() { free(p); }
+    int load(const char* path) {
+        int fd = open(path, O_RDONLY);
+        if (fd < 0) return VCFC_E_IO;
+        struct stat st;
+        if (fstat(fd, &st) != 0) { close(fd); return VCFC_E_IO; }
+        n = (size_t)st.st_size;
+        p = (uint8_t*)malloc(n + 1);
+        if (!p) { close(fd); return VCFC_E_IO; }
+        size_t got = 0;
+        while (got < n) {
+            ssize_t r = read(fd, p + got, n - got);
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) break;
+            got += (size_t)r;
+        }
+        close(fd);
+        return got == n ? VCFC_OK : VCFC_E_IO;
+    }
+};
+
+int write_all(int fd, const uint8_t* p, size_t n) {
+    while (n) {
+        ssize_t w = write(fd, p, n);
+        if (w < 0 && errno == EINTR) continue;
+        if (w <= 0) return VCFC_E_IO;
+        p += w;
+        n -= (size_t)w;
+    }
+    return VCFC_OK;
+}
+
+// str_to_uint64 (utils.cpp:152-165): strtoul must consume the whole string.
+bool parse_u64(const std::string& s, uint64_t* v) {
+    char* end = nullptr;
+    unsigned long x = strtoul(s.c_str(), &end, 10);
+    if (end != s.c_str() + s.size()) return false;
+    *v = x;
+    return true;
+}
+
+struct Query {
+    std::string ref;
+    uint64_t start = 0, end = 0;
+    bool has_range = false;
+    // VcfCoordinateQuery::matches, main.cpp:75-86
+    bool matches(const std::string& r, uint64_t pos) const {
+        if (!ref.empty() && ref != r) return false;
+        if (has_range && pos < start) return false;
+        if (has_range && pos > end) return false;
+        return true;
+    }
+};
+
+// parse_coordinate_string, main.cpp:3993-4026
+int parse_query(const char* s0, Query* q) {
+    std::string s(s0 ? s0 : "");
+    size_t colon = s.find(':');
+    if (colon == std::string::npos) { q->ref = s; return VCFC_OK; }
+    q->ref = s.substr(0, colon);
+    size_t dash = s.find('-', colon + 1);
+    if (dash == std::string::npos) return VCFC_E_QUERY;
+    if (!parse_u64(s.substr(colon + 1, dash - (colon + 1)), &q->start)) return VCFC_E_QUERY;
+    if (!parse_u64(s.substr(dash + 1), &q->end)) return VCFC_E_QUERY;
+    q->has_range = true;
+    return VCFC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vcfc_parse_headers(const uint8_t* in, size_t in_len, size_t* header_len, uint64_t* sample_count) {
+    if (!in && in_len) return VCFC_E_ARG;
+    size_t p = 0;
+    bool got_meta = false, got_header = false;
+    uint64_t sc = 0;
+    for (;;) {
+        if (p >= in_len) {
+            // compress.cpp:1136-1153: at EOF the stale first byte is still '#': the reference throws
+            // "missing headers" before both kinds were seen and "row after header" afterwards.
+            return VCFC_E_HEADER;
+        }
+        if (in[p] != '#') {
+            if (!got_meta || !got_header) return VCFC_E_HEADER;
+            break;
+        }
+        if (got_header) return VCFC_E_HEADER;
+        if (p + 1 >= in_len) return VCFC_E_HEADER;
+        if (in[p + 1] == '#') got_meta = true;
+        else { if (!got_meta) return VCFC_E_HEADER; got_header = true; }
+        size_t q = p + 2, tabs = 0;
+        for (;;) {
+            if (q >= in_len) return VCFC_E_HEADER;
+            uint8_t c = in[q++];
+            if (c == '\n') break;
+            if (got_header && c == '\t' && ++tabs > 8) sc++;
+        }
+        p = q;
+    }
+    if (header_len) *header_len = p;
+    if (sample_count) *sample_count = sc;
+    return VCFC_OK;
+}
+
+int vcfc_compress_file(vcfc_ctx* ctx, const char* in_path, const char* out_path) {
+    if (!ctx || !in_path || !out_path) return VCFC_E_ARG;
+    HostFile f;
+    int rc = f.load(in_path);
+    if (rc) return rc;
+    int ofd = open(out_path, O_CREAT | O_TRUNC | O_WRONLY, 0644);
+    if (ofd < 0) return VCFC_E_IO;
+    std::vector<uint8_t> out;
+    size_t pos = 0;
+    const uint8_t* in = f.p;
+    while (pos < f.n && rc == VCFC_OK) {
+        if (in[pos] == '\n') { pos++; continue; }                       // compress.cpp:219-221
+        if (in[pos] == '#') {                                           // compress.cpp:222-238
+            const uint8_t* e = (const uint8_t*)memchr(in + pos, '\n', f.n - pos);
+            size_t len = e ? (size_t)(e - (in + pos)) : f.n - pos;
+            rc = write_all(ofd, in + pos, len);
+            if (rc == VCFC_OK) rc = write_all(ofd, (const uint8_t*)"\n", 1);
+            pos += len + 1;
+            continue;
+        }
+        // data region: up to the next line that starts with '#'
+        size_t end = f.n;
+        for (size_t s = pos;;) {
+            const uint8_t* h = (const uint8_t*)memmem(in + s, f.n - s, "\n#", 2);
+            if (!h) break;
+            end = (size_t)(h - in) + 1;
+            break;
+        }
+        size_t len = end - pos, olen = 0, nl = 0;
+        uint64_t el = 0;
+        size_t cap = vcfc_encode_bound(len);
+        out.resize(cap);
+        rc = vcfc_encode_block(ctx, in + pos, len, out.data(), cap, &olen, nullptr, 0, &nl, &el);
+        int wrc = write_all(ofd, out.data(), olen);                     // lines before a bad one stand
+        if (rc == VCFC_OK) rc = wrc;
+        pos = end;
+    }
+    close(ofd);
+    return rc;
+}
+
+int vcfc_decompress_file(vcfc_ctx* ctx, const char* in_path, const char* out_path) {
+    if (!ctx || !in_path || !out_path) return VCFC_E_ARG;
+    HostFile f;
+    int rc = f.load(in_path);
+    if (rc) return rc;
+    int ofd = open(out_path, O_CREAT | O_TRUNC | O_WRONLY, 0644);       // the reference truncates first (compress.cpp:1217)
+    if (ofd < 0) return VCFC_E_IO;
+    size_t hlen = 0;
+    uint64_t sc = 0;
+    rc = vcfc_parse_headers(f.p, f.n, &hlen, &sc);
+    if (rc) { close(ofd); return rc; }
+    rc = write_all(ofd, f.p, hlen);
+    // decoded size: required bytes pass through, a token byte expands to at most 127 * 4 bytes
+    const uint8_t* in = f.p + hlen;
+    size_t len = f.n - hlen, pos = 0;
+    std::vector<uint8_t> out;
+    const size_t piece = (size_t)64 << 20;
+    while (rc == VCFC_OK && len - pos >= 8) {
+        // take whole lines up to `piece` compressed bytes per call
+        size_t end = pos;
+        while (len - end >= 8 && (in[end] >> 6) == 3) {
+            size_t ll = ((size_t)(in[end] & 0x3F) << 24) | ((size_t)in[end + 1] << 16) | ((size_t)in[end + 2] << 8) | in[end + 3];
+            if (ll + 4 > len - end) { end = len; break; }
+            if (end + 4 + ll - pos > piece && end > pos) break;
+            end += 4 + ll;
+        }
+        if (end == pos || len - end < 8) end = len;
+        // exact output size from the per-line sample count: every sample is >= 2 bytes; use the device's count
+        size_t olen = 0, nl = 0;
+        uint64_t el = 0;
+        size_t cap = std::max<size_t>((end - pos) * 12, (size_t)1 << 20);
+        for (int attempt = 0; attempt < 8; attempt++) {
+            out.resize(cap);
+            rc = vcfc_decode_block(ctx, in + pos, end - pos, sc, out.data(), cap, &olen, &nl, &el);
+            if (rc != VCFC_E_CAP) break;
+            cap *= 4;
+        }
+        int wrc = write_all(ofd, out.data(), olen);
+        if (rc == VCFC_OK) rc = wrc;
+        pos = end;
+    }
+    close(ofd);
+    return rc;
+}
+
+int vcfc_query_file(vcfc_ctx* ctx, const char* in_path, const char* region, int out_fd) {
+    if (!ctx || !in_path) return VCFC_E_ARG;
+    Query q;
+    int rc = parse_query(region, &q);
+    if (rc) return rc;
+    HostFile f;
+    if ((rc = f.load(in_path))) return rc;
+    size_t hlen = 0;
+    uint64_t sc = 0;
+    if ((rc = vcfc_parse_headers(f.p, f.n, &hlen, &sc))) return rc;     // header lines are not printed (main.cpp:3789)
+    const uint8_t* in = f.p;
+    size_t pos = hlen;
+    std::vector<uint8_t> hits, out;
+    auto flush = [&]() -> int {
+        if (hits.empty()) return VCFC_OK;
+        size_t olen = 0, nl = 0, cap = std::max<size_t>(hits.size() * 12, (size_t)1 << 20);
+        uint64_t el = 0;
+        int r = VCFC_OK;
+        for (int attempt = 0; attempt < 8; attempt++) {
+            out.resize(cap);
+            r = vcfc_decode_block(ctx, hits.data(), hits.size(), sc, out.data(), cap, &olen, &nl, &el);
+            if (r != VCFC_E_CAP) break;
+            cap *= 4;
+        }
+        int w = write_all(out_fd, out.data(), olen);
+        hits.clear();
+        return r != VCFC_OK ? r : w;
+    };
+    while (pos < f.n) {                                                 // main.cpp:3799-3924
+        if (f.n - pos < 4) return VCFC_E_TRUNC;                          // "Only read %d bytes, expected 4"
+        if (f.n - pos < 8) return VCFC_E_TRUNC;
+        if ((in[pos] >> 6) != 3) { flush(); return VCFC_E_FORMAT; }
+        size_t ll = ((size_t)(in[pos] & 0x3F) << 24) | ((size_t)in[pos + 1] << 16) | ((size_t)in[pos + 2] << 8) | in[pos + 3];
+        size_t p = pos + 8;
+        std::string ref, ps;
+        while (true) { if (p >= f.n) { flush(); return VCFC_E_TRUNC; } uint8_t c = in[p++]; if (c == '\t') break; ref.push_back((char)c); }
+        while (true) { if (p >= f.n) { flush(); return VCFC_E_TRUNC; } uint8_t c = in[p++]; if (c == '\t') break; ps.push_back((char)c); }
+        uint64_t v = 0;
+        if (!parse_u64(ps, &v)) { flush(); return VCFC_E_FORMAT; }
+        if (ll + 4 > f.n - pos) {
+            rc = flush();
+            return rc ? rc : VCFC_E_TRUNC;
+        }
+        if (q.matches(ref, v)) {
+            hits.insert(hits.end(), in + pos, in + pos + 4 + ll);
+            if (hits.size() > ((size_t)64 << 20) && (rc = flush())) return rc;
+        }
+        pos += 4 + ll;
+    }
+    return flush();
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// vcfc_internal.h -- internals shared by the translation units of libvcfc_gpu.so.
+// Nothing here crosses the C ABI (include/vcfc_gpu.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/vcfc_gpu.h"
+
+namespace vcfc {
+
+// A growable device allocation owned by the context.
+struct DevBuf {
+    void*  p   = nullptr;
+    size_t cap = 0;
+};
+
+enum { kTimeEncode = 0, kTimeDecodeScan = 1, kTimeDecodeExpand = 2, kTimeSlots = 3 };
+
+// Which path the last block call took (bench/test introspection; see vcfc_last_path).
+enum { kPathNone = 0, kPathFast = 1, kPathGeneric = 2 };
+
+}  // namespace vcfc
+
+struct vcfc_ctx {
+    int          device      = -1;
+    int          sm_count    = 0;
+    cudaStream_t stream      = nullptr;  // default work stream
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    // workspace (device)
+    vcfc::DevBuf ws[12];
+    // device staging for the host-pointer API
+    vcfc::DevBuf d_in[2], d_out[2];
+    // pinned host staging (file drivers / pageable callers)
+    void*  h_pin[2]   = {nullptr, nullptr};
+    size_t h_pin_cap[2] = {0, 0};
+    vcfc_result* h_result = nullptr;      // pinned
+    vcfc_result* d_result = nullptr;
+    // instrumentation
+    int          timing      = 0;
+    cudaEvent_t  ev[2 * vcfc::kTimeSlots] = {};
+    float        last_ms[vcfc::kTimeSlots] = {0, 0, 0};
+    int          ev_pending[vcfc::kTimeSlots] = {0, 0, 0};
+    uint64_t     launches    = 0;
+    int          last_path   = 0;
+    int          force_generic = 0;
+    char         cuda_err[256] = {0};
+};
+
+namespace vcfc {
+
+// Records a CUDA failure in the context; returns VCFC_E_CUDA.
+int cuda_fail(vcfc_ctx* ctx, cudaError_t e, const char* what);
+
+#define VCFC_CUDA(ctx, call)                                              \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) return ::vcfc::cuda_fail((ctx), e__, #call); \
+    } while (0)
+
+// Ensures b has at least `bytes` capacity (contents are NOT preserved).
+int dev_reserve(vcfc_ctx* ctx, DevBuf* b, size_t bytes);
+
+// ---- generic (any input; slow, line-serial) path: vcfc_generic.cu ----
+// Both synchronise `stream` internally (they size their workspace from device counts).
+int encode_generic(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_out, size_t out_cap,
+                   uint64_t* d_line_out_offsets, size_t line_cap, vcfc_result* d_result,
+                   cudaStream_t stream);
+int decode_generic(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t sample_count,
+                   uint8_t* d_out, size_t out_cap, vcfc_result* d_result, bool size_only,
+                   cudaStream_t stream);
+
+// Exclusive prefix sum over n uint64 values (in place allowed: out may alias in); writes the
+// grand total to d_total (nullable).  `scratch` is grown as needed.
+int scan_exclusive_u64(vcfc_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, size_t n,
+                       uint64_t* d_total, DevBuf* scratch, cudaStream_t stream);
+
+// ---- fast (regular GT-only lines; single pass, tile-parallel) path ----
+// Return VCFC_OK with d_result->status == kStatusIrregular when the input needs the generic path.
+constexpr int kStatusIrregular = -100;
+int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_out, size_t out_cap,
+                uint64_t* d_line_out_offsets, size_t line_cap, vcfc_result* d_result,
+                cudaStream_t stream);
+int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t sample_count,
+                uint8_t* d_out, size_t out_cap, vcfc_result* d_result, bool size_only,
+                cudaStream_t stream);
+
+}  // namespace vcfc

@@ -1,0 +1,66 @@
+// vcfc -- command line with the reference's verb surface for the hot path
+// (/root/reference/src/main.cpp:4028-4184):
+//     vcfc compress   IN.vcf  OUT.vcfc
+//     vcfc decompress IN.vcfc OUT.vcf
+//     vcfc query      IN.vcfc REF[:START-END]
+// Host C++ only; all coding work is done by libvcfc_gpu.so through its C ABI.  Where the
+// reference lets an exception escape (abort, exit 134) this prints the reason and exits 1.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <string>
+
+#include "vcfc_gpu.h"
+
+static int usage() {
+    fprintf(stderr,
+            "usage: vcfc compress IN.vcf OUT.vcfc | decompress IN.vcfc OUT.vcf | query IN.vcfc REF[:START-END]\n"
+            "       env: VCFC_DEVICE (default 0), VCFC_CHUNK_MB (default 256)\n");
+    return 1;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) return usage();
+    std::string action(argv[1]);
+    const char* verbs_elsewhere[] = {"gap-analysis", "sparsify", "sparse-query", "create-binned-index",
+                                     "query-binned-index", "create-sparse-index", "query-sparse-index"};
+    for (const char* v : verbs_elsewhere)
+        if (action == v) {
+            fprintf(stderr, "vcfc: verb '%s' is outside the GPU hot path; use the reference binary for it\n", v);
+            return 2;
+        }
+    if (action != "compress" && action != "decompress" && action != "query") {
+        printf("Unknown action name: %s\n", action.c_str());   // main.cpp:4181-4183
+        return 0;
+    }
+    if (argc < 4) return usage();
+    const char* in = argv[2];
+    if (access(in, F_OK) != 0) printf("Input file does not exist: %s\n", in);   // main.cpp:4040-4042
+    int dev = getenv("VCFC_DEVICE") ? atoi(getenv("VCFC_DEVICE")) : 0;
+    vcfc_ctx* ctx = nullptr;
+    int rc = vcfc_gpu_init(dev, &ctx);
+    if (rc != VCFC_OK) {
+        fprintf(stderr, "vcfc: cannot use CUDA device %d: %s (there is no CPU path)\n", dev, vcfc_strerror(rc));
+        return 1;
+    }
+    if (action == "query") {
+        rc = vcfc_query_file(ctx, in, argv[3], STDOUT_FILENO);
+        if (rc == VCFC_E_QUERY) printf("Failed to parse query string: %s\n", argv[3]);   // main.cpp:4064-4067
+    } else {
+        if (strcmp(in, argv[3]) == 0) {
+            fprintf(stderr, "input and output file are the same\n");   // main.cpp:4044-4046
+            vcfc_gpu_destroy(ctx);
+            return 1;
+        }
+        rc = action == "compress" ? vcfc_compress_file(ctx, in, argv[3]) : vcfc_decompress_file(ctx, in, argv[3]);
+    }
+    if (rc != VCFC_OK) {
+        fprintf(stderr, "vcfc %s: %s", action.c_str(), vcfc_strerror(rc));
+        if (rc == VCFC_E_CUDA) fprintf(stderr, " [%s]", vcfc_last_cuda_error(ctx));
+        fprintf(stderr, "\n");
+    }
+    vcfc_gpu_destroy(ctx);
+    return rc == VCFC_OK ? 0 : 1;
+}
