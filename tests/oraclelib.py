@@ -52,7 +52,7 @@ def compress_block(data: bytes, want_offsets=False):
 
 
 def decompress_block(data: bytes, sample_count: int, cap=None):
-    cap = cap or (len(data) * 140 + 4096)
+    cap = cap or (len(data) * 520 + 4096)   # a 0x7f token byte expands to 127 * 4 bytes
     out = C.create_string_buffer(cap)
     olen, nl, el = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
     rc = lib().vcfc_oracle_decompress_block(data, len(data), sample_count, out, cap, C.byref(olen), C.byref(nl), C.byref(el))

@@ -120,6 +120,35 @@ def test_seeded_vs_oracle(any_path, maker, args):
     check_block(any_path, data, sample_count=args["n_samples"])
 
 
+def test_regular_blocks_take_the_tile_kernels(codec):
+    """GT-only data must be served by the single-pass tile kernels, not by the generic fallback."""
+    for maker, args in ((vcfgen.kg_like, dict(n_lines=120, n_samples=2504, seed=41)),
+                        (vcfgen.random_vcf_like, dict(n_lines=50, n_samples=2504, seed=42)),
+                        (vcfgen.random_vcf_like, dict(n_lines=2, n_samples=60000, seed=43, probs=(0.999, 0.001, 0.0)))):
+        _, data = maker(**args)
+        check_block(codec, data, sample_count=args["n_samples"], expect_path=pkg.PATH_FAST)
+
+
+@pytest.mark.parametrize("n_samples", [1, 2, 3, 5, 31, 32, 33, 127, 128, 129, 255, 1000, 3583, 3584, 3585, 7000, 20000])
+def test_tile_boundaries_sweep(codec, n_samples):
+    """Line widths around the 14 KB tile / 32-byte block / 127- and 31-sample chunk sizes, two allele mixes."""
+    for seed, probs in ((1, (0.90, 0.08, 0.02)), (2, (0.9995, 0.0005, 0.0)), (3, (0.0, 1.0, 0.0))):
+        n_lines = max(3, min(400, 300000 // (4 * n_samples + 40)))
+        _, data = vcfgen.random_vcf_like(n_lines, n_samples, seed=seed, probs=probs)
+        check_block(codec, data, sample_count=n_samples)
+
+
+def test_long_uniform_runs_across_tiles(codec):
+    """Runs of one genotype that span many tiles: the 127/31 chunking must stay anchored at the run head."""
+    req = b"7\t123\t.\tA\tC\t.\t.\tDP=1\tGT\t"
+    for gt in (b"0|0", b"0|1", b"1|0", b"1|1", b"0/0"):
+        for n in (3584 * 3 + 17, 50000):
+            lines = [req + b"\t".join([gt] * n) + b"\n",
+                     req + b"\t".join([b"1|1"] * 5 + [gt] * n + [b"0|1"]) + b"\n",
+                     req + b"\t".join([gt] * (n // 2) + [b"2|2"] + [gt] * (n // 2)) + b"\n"]
+            check_block(codec, b"".join(lines), sample_count=None)
+
+
 def test_edge_case_lines(any_path):
     for s in (1, 3, 8, 40, 129):
         lines = vcfgen.edge_case_lines(s)
@@ -170,7 +199,10 @@ def test_decode_rejects_bad_input(any_path):
     bad[0] = 0x40
     assert any_path.decompress_block(bytes(bad), 8)[0] == pkg.E_FORMAT
     assert any_path.decompress_block(out, 9)[0] != 0
-    assert any_path.decompress_block(out, 7)[0] != 0
+    for sc in (7, 5, 1):       # too small a sample count: whatever the reference's loop does, token by token
+        orc, otxt, _, _ = O.decompress_block(out, sc)
+        rc, txt, _, _ = any_path.decompress_block(out, sc)
+        assert (rc == 0) == (orc == 0) and txt == otxt
     rc, txt, nl, _ = any_path.decompress_block(out + b"\x01\x02\x03", 8)     # <8 trailing bytes = EOF
     assert rc == 0 and txt == data and nl == 3
     assert any_path.decompress_block(out, 8, out_cap=20)[0] == pkg.E_CAP
@@ -186,8 +218,8 @@ def test_chunked_host_path_matches_single_call(codec, monkeypatch):
     assert rc == 0 and out == ref[1] and nl == ref[2] and offs == ref[4]
     rc, txt, nl2, _ = codec.decompress_block(out, 2504)
     assert rc == 0 and txt == data and nl2 == nl
-    bad = data[:2_000_000] + b"oops\n" + data[2_000_000:]
-    bad = bad[:bad.rfind(b"\n", 0, 2_000_000) + 1] + b"oops\n" + data[data.rfind(b"\n", 0, 2_000_000) + 1:]
+    cut = data.rfind(b"\n", 0, 2_000_000) + 1
+    bad = data[:cut] + b"oops\n" + data[cut:]
     orc, oout, onl, oel = O.compress_block(bad)
     rc, out, nl, el = codec.compress_block(bad)
     assert rc == -orc and out == oout and nl == onl and el == oel

@@ -171,7 +171,7 @@ class Codec:
 
     def decompress_block(self, data, sample_count: int, out_cap: int | None = None):
         """.vcfc data lines -> text.  Returns (rc, out, n_lines, err_line)."""
-        cap = out_cap if out_cap is not None else len(data) * 140 + 4096
+        cap = out_cap if out_cap is not None else len(data) * 520 + 4096   # a 0x7f token expands to 508 bytes
         out = C.create_string_buffer(max(cap, 1))
         olen, nl, el = C.c_size_t(0), C.c_size_t(0), C.c_uint64(0)
         rc = lib().vcfc_decode_block(self._ctx, _ptr(data), len(data), sample_count, out, cap,
