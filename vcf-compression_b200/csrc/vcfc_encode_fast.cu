@@ -2,21 +2,22 @@
 //
 // "Regular" = what a GT-only VCF looks like: '\n'-terminated lines, single tabs, >= 10 columns,
 // every sample column exactly 3 bytes (a|b, a/b, ./. ...), required section (CHROM..FORMAT) of
-// at most kMaxReq bytes.  Anything else sets ctrl->irregular and the caller reruns the block on
-// the generic kernels (vcfc_generic.cu).  Output bytes are those of compress_data_line
-// (/root/reference/src/compress.cpp:5-203) for every line.
+// at most kMaxReq bytes, lines of at least ~0.5 KB.  Anything else sets ctrl->irregular and the
+// caller reruns the block on the generic kernels (vcfc_generic.cu).  Output bytes are those of
+// compress_data_line (/root/reference/src/compress.cpp:5-203) for every line.
 //
-// One CTA = one tile of ~14 KB of input, HBM traffic = input read once + output written once:
-//   1. bulk async copy (TMA engine, cp.async.bulk + mbarrier) of the tile and 1 KB halos into smem
-//   2. cut points: a tile owns the units (a sample column, or a whole required section) that START
-//      in [cut(i*T), cut((i+1)*T)); both neighbours compute the shared cut from the same bytes
-//   3. newline list -> line segments (required section end = 9th tab, warp ballot/popc)
-//   4. items = 32-byte blocks of 8 phase-aligned sample words: classify, run heads
-//   5. look-back #1 (tiny): run length carried into the tile  (chunks are 127 / 31 samples from
-//      the run's head, compress.cpp:129-170, so a tile must know how long the run already is)
-//   6. per-item byte counts, block scan, look-back #2 (decoupled, 16-byte status): output offset
-//      and line index of the tile
-//   7. emit tokens / literals / required sections into smem staging, 16-byte stores to HBM
+// One CTA = one tile of 14 KB of input; HBM traffic = input read once + output written once:
+//   1. bulk async copy (TMA engine: cp.async.bulk + mbarrier) of the tile and 1 KB halos into smem
+//   2. cut points: a tile owns the units (one sample column, or one whole required section) that
+//      START in [cut(i*T), cut((i+1)*T)); both neighbours derive the shared cut from the same bytes
+//   3. newline list (16-byte AND-filter) -> line segments (9th tab by warp ballot/popc)
+//   4. items = 32-byte blocks of 8 phase-aligned sample words, two per thread, kept in registers as
+//      8-bit masks: valid / coded / literal / run head / closing token
+//   5. look-back #1 (one word per tile): how long the run that enters the tile already is -- chunks
+//      are 127 / 31 samples counted from the run's head (compress.cpp:129-170)
+//   6. byte counts -> packed warp scan -> look-back #2 (decoupled, 16-byte status words): output
+//      offset and line index of the tile
+//   7. tokens / literals / required sections are written to smem staging and stored to HBM
 // A second tiny kernel patches the 4-byte line-length headers (they need the NEXT line's offset)
 // and writes the result block.
 #include <algorithm>
@@ -33,11 +34,11 @@ constexpr int kPad = 32;                // zeroed bytes in front of / behind the
 constexpr int kMaxReq = kHalo - 64;     // longest required section taken by this path
 constexpr int kWin = kTile + 2 * kHalo + 2 * kPad;
 constexpr int kStage = 21504 + 32;      // staging bytes (regular data expands at most ~1.45x)
-constexpr int kMaxSeg = 126;
-constexpr int kMaxItems = 768;
+constexpr int kMaxNl = 30;              // newlines per tile taken by this path (lines >= ~0.5 KB)
+constexpr int kMaxSeg = kMaxNl + 2;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kRound = 2 * kThreads;    // items per round (2 per thread)
+constexpr int kMaxItems = 2 * kThreads; // two items per thread, held in registers
 
 enum { kCutLine = 0, kCutSample = 1, kCutSampleFirst = 2, kCutEnd = 3, kCutBad = 4 };
 constexpr int kNone = 7;                // "no open run" class
@@ -58,30 +59,24 @@ struct Seg {                            // a run of sample words of one line ins
     int item0;                          // first item index
     int flags;                          // bit0: span ends with the line's '\n'; bit1: first sample of span is first of line
     int out0;                           // staging offset of the line start (header) -- valid if ls >= 0
+    int pad;
 };
 
 struct Smem {
     alignas(128) uint8_t win[kWin];
     alignas(16) uint8_t stage[kStage];
     alignas(8) uint64_t mbar;
-    uint32_t itemCls[kMaxItems];        // 8 x 4-bit classes
-    uint32_t itemMeta[kMaxItems];       // valid mask (8) | head mask (8) << 8 | prev class << 16 | line-end idx+1 << 20
-    int itemOff[kMaxItems];
-    Seg seg[kMaxSeg + 2];
-    int nlpos[kMaxSeg + 2];
-    int nlsorted[kMaxSeg + 2];
+    Seg seg[kMaxSeg];
+    int nlpos[kMaxNl + 2];
     int n_nl, n_seg, n_items, n_lines;
     int tile, irregular;
     int cs, cs_kind, ce, ce_kind;
-    int tile_last_head, tile_last_cls;
+    int tile_last_head;
     int ein_virtual;
-    int warp_h[kWarps + 1], warp_s[kWarps + 1];
-    int carry_i, carry_head;
-    int total_bytes;
+    int warp_h[kWarps], warp_s[kWarps];
     unsigned long long excl_bytes, excl_lines;
     int skip_write;
 };
-
 static_assert(sizeof(Smem) <= 53 * 1024, "4 CTAs per SM need <= ~56 KB each");
 
 __device__ __forceinline__ bool is_sep(uint32_t c) { return c == '\t' || c == '\n'; }
@@ -181,87 +176,156 @@ __device__ int line_scan(const uint8_t* __restrict__ win, int ls, int vhi_w, int
     return -1;
 }
 
-// ---- sample word helpers ------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t classify_word(uint32_t s) {     // 0..3 coded, 4 otherwise
-    uint32_t m = s & 0xFFFEFFFEu;
-    return (m == 0x09307C30u || m == 0x0A307C30u) ? (((s & 1u) << 1) | ((s >> 16) & 1u)) : 4u;
+// ---- sample helpers -----------------------------------------------------------------------------------
+// class of the 3-byte genotype at p: 0..3 = 0|0 0|1 1|0 1|1, 4 = anything else (compress.cpp:129,145)
+__device__ __forceinline__ int gt_class3(const uint8_t* p) {
+    uint32_t a = p[0], b = p[1], c = p[2];
+    if (b != '|' || (a & 0xFEu) != 0x30u || (c & 0xFEu) != 0x30u) return 4;
+    return (int)(((a & 1u) << 1) | (c & 1u));
 }
-__device__ __forceinline__ bool has_tab_low3(uint32_t s) {
-    uint32_t v = ((s ^ 0x00090909u) & 0x00FFFFFFu) | 0xFF000000u;
-    return ((v - 0x01010101u) & ~v & 0x80808080u) != 0;
-}
-__device__ __forceinline__ uint32_t cls_flag(uint32_t c) { return c == 0 ? kTok00 : c == 1 ? kTok01 : c == 2 ? kTok10 : kTok11; }
-__device__ __forceinline__ int cls_max(uint32_t c) { return c == 0 ? 127 : 31; }
+__device__ __forceinline__ uint32_t cls_flag(int c) { return (0x80C0A000u >> (8 * c)) & 0xFFu; }   // utils.hpp:44-55
+__device__ __forceinline__ int mod_chunk(int x, bool m127) { return m127 ? x % 127 : x % 31; }
 
-__device__ __forceinline__ int seg_of_item(const Smem& sm, int item) {
-    int lo = 0, hi = sm.n_seg - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (sm.seg[mid].item0 <= item) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-
-// Walks the (up to 8) samples of an item in order, replaying the reference's run logic
-// (compress.cpp:124-186).  cp/cnt = open run class / count before the item.  Returns bytes emitted;
-// when WRITE, stores them at dst.  *cp_out/*cnt_out = state after the item.
-template <bool WRITE>
-__device__ __forceinline__ int item_walk(const uint8_t* __restrict__ win, int blk, int phase, uint32_t cls8, uint32_t meta,
-                                         int cp, int cnt, uint8_t* __restrict__ dst, int* cp_out, int* cnt_out) {
-    int o = 0;
-    const uint32_t valid = meta & 0xFFu;
-    const int lineend = (int)((meta >> 20) & 0xFu) - 1;      // index of the sample that ends the line, or -1
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        if (!((valid >> k) & 1u)) continue;
-        int c = (int)((cls8 >> (4 * k)) & 0xFu);
-        if (cp < 4 && (c != cp || cnt == cls_max(cp))) {
-            if (WRITE) dst[o] = (uint8_t)(cls_flag(cp) | (uint32_t)cnt);
-            o++;
-            cp = kNone;
-        }
-        if (c == 4) {
-            if (WRITE) {
-                const uint8_t* s = win + blk + phase + 4 * k;
-                dst[o] = (uint8_t)(kTokLit | 1u);
-                dst[o + 1] = s[0]; dst[o + 2] = s[1]; dst[o + 3] = s[2];
-                if (k != lineend) dst[o + 4] = '\t';
-            }
-            o += (k != lineend) ? 5 : 4;
-        } else if (cp == kNone) {
-            cp = c;
-            cnt = 1;
-        } else {
-            cnt++;
-        }
-        if (k == lineend) {
-            if (cp < 4) { if (WRITE) dst[o] = (uint8_t)(cls_flag(cp) | (uint32_t)cnt); o++; }
-            if (WRITE) dst[o] = '\n';
-            o++;
-            cp = kNone;
-        }
-    }
-    *cp_out = cp;
-    *cnt_out = cnt;
-    return o;
-}
-
-// open-run state before the first valid sample of an item, from the last run head before it
-__device__ __forceinline__ void run_state_before(uint32_t meta, int first_addr, int ein, int* cp, int* cnt) {
-    int pc = (int)((meta >> 16) & 0xFu);
-    *cp = pc < 4 ? pc : kNone;
-    *cnt = 0;
-    if (pc < 4) {
-        int nrun = (first_addr - ein) >> 2;              // samples of the open run so far (>= 1)
-        *cnt = ((nrun - 1) % cls_max(pc)) + 1;
-    }
-}
+struct Item {                  // one 32-byte block of up to 8 samples of one line; lives in registers
+    int blk;                   // window offset of the block (multiple of 32)
+    int phase;                 // sample k sits at blk + phase + 4k
+    uint32_t V, C, L, Hd, CL;  // 8-bit masks: valid, coded, literal, run head, closing token before the sample
+    int kend;                  // index of the sample that ends the line, or -1
+    int pcoded;                // the sample before the first valid one is a coded sample of the same line
+    int hdr;                   // 8 + required length if this item carries a line start, else 0
+    int seg;
+};
 
 __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long a, unsigned long long b) {
     asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ void ld_status(const unsigned long long* p, unsigned long long* a, unsigned long long* b) {
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(*a), "=l"(*b) : "l"(p) : "memory");
+}
+
+// ---- classify one item ------------------------------------------------------------------------------------
+__device__ __forceinline__ void item_classify(Smem& sm, int item, Item& it, int* lasthead) {
+    it.blk = 0; it.V = it.C = it.L = it.Hd = it.CL = 0; it.kend = -1; it.pcoded = 0; it.hdr = 0; it.phase = 0; it.seg = 0;
+    *lasthead = kNoHead;
+    if (item >= sm.n_items) return;
+    int si = 0;
+    for (int j = 1; j < sm.n_seg; j++) si += (sm.seg[j].item0 <= item);
+    const int a = sm.seg[si].a, e = sm.seg[si].e, flags = sm.seg[si].flags, item0 = sm.seg[si].item0;
+    const int blk = ((a >> 5) + (item - item0)) << 5, phase = a & 3;
+    it.blk = blk; it.phase = phase; it.seg = si;
+    if (item == item0 && sm.seg[si].ls >= 0) it.hdr = 8 + sm.seg[si].s0 - sm.seg[si].ls;
+    const int base = blk + phase;
+    // valid samples: those that start in [a, e)
+    const int rel_a = a - base, rel_e = e - base;
+    const int klo = rel_a > 0 ? rel_a >> 2 : 0, khi = rel_e >= 32 ? 8 : (rel_e > 0 ? rel_e >> 2 : 0);
+    const uint32_t V = khi > klo ? (((1u << khi) - 1u) & ~((1u << klo) - 1u)) : 0u;
+    if (!V) return;
+    const uint32_t F = ((flags & 2) && rel_a >= 0) ? (1u << klo) : 0u;
+    int kend = -1;
+    if (flags & 1) { int r = e - 4 - base; if (r >= 0 && r < 32) kend = r >> 2; }
+    // the 10 words around the block; sample k = bytes base + 4k .. base + 4k + 3
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(sm.win + blk);
+    uint32_t W[10];
+    W[0] = wp[-1];
+    uint4 v0 = *reinterpret_cast<const uint4*>(wp), v1 = *reinterpret_cast<const uint4*>(wp + 4);
+    W[1] = v0.x; W[2] = v0.y; W[3] = v0.z; W[4] = v0.w; W[5] = v1.x; W[6] = v1.y; W[7] = v1.z; W[8] = v1.w;
+    W[9] = wp[8];
+    uint32_t Craw = 0, Q = 0, sp = __funnelshift_r(W[0], W[1], 8 * phase);
+    const uint32_t pc_all = ((sp & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u ? 1u : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t s = __funnelshift_r(W[k + 1], W[k + 2], 8 * phase);
+        Craw |= (((s & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u ? 1u : 0u) << k;   // "x|y\t" with x, y in {0,1}
+        Q |= (s == sp ? 1u : 0u) << k;                                         // same bytes as the previous word
+        sp = s;
+    }
+    // everything valid that is not "x|y\t": literals, and the sample that carries the line's '\n'
+    uint32_t L = 0, N = V & ~Craw;
+    bool irr = false;
+    while (N) {
+        const int k = __ffs(N) - 1;
+        N &= N - 1;
+        const uint8_t* p = sm.win + base + 4 * k;
+        const uint32_t b3 = p[3];
+        if (k == kend ? (b3 != '\n') : (b3 != '\t')) irr = true;
+        if (gt_class3(p) < 4) {            // coded sample terminated by the line's newline
+            Craw |= 1u << k;
+            const bool prev_coded = k > 0 ? ((Craw >> (k - 1)) & 1u) : pc_all;
+            if (prev_coded && p[-4] == p[0] && p[-2] == p[2]) Q |= 1u << k; else Q &= ~(1u << k);
+        } else {
+            if (p[0] == '\t' || p[1] == '\t' || p[2] == '\t') irr = true;
+            L |= 1u << k;
+        }
+    }
+    if (kend >= 0 && ((V >> kend) & 1u) && sm.win[base + 4 * kend + 3] != '\n') irr = true;
+    if (irr) sm.irregular = 1;
+    const uint32_t Hd = V & (F | ~(Craw & Q));
+    const uint32_t PC = (((Craw << 1) | pc_all) & 0xFFu) & ~F;     // the previous word is a coded sample of this line
+    it.V = V; it.C = Craw & V; it.L = L; it.Hd = Hd; it.CL = Hd & PC;
+    it.kend = (kend >= 0 && ((V >> kend) & 1u)) ? kend : -1;
+    it.pcoded = (int)((PC >> klo) & 1u);
+    if (Hd) *lasthead = base + 4 * (31 - __clz(Hd));
+}
+
+// bytes the item emits (tokens, literals, line end) -- compress.cpp:124-190 in closed form.
+// ein = address of the last run head before the item.  cnt_prev = chunk count (1..M) of the coded sample
+// just before the first valid one; cfbit = the sample before which the entering chunk fills up.
+__device__ __forceinline__ int item_count(const Smem& sm, const Item& it, int ein, uint32_t* cfbit, int* cnt_prev, bool* m127) {
+    *cfbit = 0; *cnt_prev = 0; *m127 = true;
+    if (!it.V) return it.hdr;
+    const int k0 = __ffs(it.V) - 1;
+    int n = it.hdr + __popc(it.CL) + 5 * __popc(it.L);
+    if (it.pcoded) {
+        const int paddr = it.blk + it.phase + 4 * k0 - 4;        // the previous sample
+        *m127 = ((sm.win[paddr] | sm.win[paddr + 2]) & 1u) == 0;  // 0|0 chunks by 127, the others by 31
+        *cnt_prev = mod_chunk((paddr - ein) >> 2, *m127) + 1;
+        const uint32_t t = (~it.Hd & it.V) >> k0;                 // leading samples that continue the entering run
+        const int nlead = __ffs(~t) - 1;
+        const int j = (*m127 ? 127 : 31) - *cnt_prev;             // the chunk is full before lead sample j
+        if (j < nlead) { *cfbit = 1u << (k0 + j); n++; }
+    }
+    if (it.kend >= 0) n += ((it.L >> it.kend) & 1u) ? 0 : 2;      // literal: its tab becomes the '\n'; coded: token + '\n'
+    return n;
+}
+
+__device__ __forceinline__ void item_emit(const Smem& sm, const Item& it, uint32_t cfbit, int cnt_prev, bool m127,
+                                          uint8_t* __restrict__ dst) {
+    if (!it.V) return;
+    const int k0 = __ffs(it.V) - 1;
+    const int base = it.blk + it.phase;
+    uint32_t ev = it.CL | cfbit | it.L | (it.kend >= 0 ? (1u << it.kend) : 0u);
+    int o = 0;
+    while (ev) {
+        const int k = __ffs(ev) - 1;
+        ev &= ev - 1;
+        const uint8_t* p = sm.win + base + 4 * k;
+        if (((it.CL | cfbit) >> k) & 1u) {                        // token closing the chunk that ends at sample k-1
+            const int c = (int)(((p[-4] & 1u) << 1) | (p[-2] & 1u));
+            const uint32_t hb = it.Hd & ((1u << k) - 1u);
+            int cnt;
+            if ((cfbit >> k) & 1u) cnt = m127 ? 127 : 31;
+            else if (hb) cnt = k - (31 - __clz(hb));
+            else cnt = mod_chunk(cnt_prev - 1 + (k - k0), m127) + 1;
+            dst[o++] = (uint8_t)(cls_flag(c) | (uint32_t)cnt);
+        }
+        if ((it.L >> k) & 1u) {                                   // literal escape (compress.cpp:171-185)
+            dst[o] = (uint8_t)(kTokLit | 1u);
+            dst[o + 1] = p[0]; dst[o + 2] = p[1]; dst[o + 3] = p[2];
+            o += 4;
+            if (k != it.kend) dst[o++] = '\t';
+        }
+        if (k == it.kend) {
+            if ((it.C >> k) & 1u) {                               // the open run ends with the line
+                const int c = (int)(((p[0] & 1u) << 1) | (p[2] & 1u));
+                const uint32_t hb = it.Hd & ((2u << k) - 1u);
+                int cnt;
+                if (hb) cnt = k - (31 - __clz(hb)) + 1;
+                else cnt = mod_chunk(cnt_prev + (k - k0), c == 0) + 1;
+                dst[o++] = (uint8_t)(cls_flag(c) | (uint32_t)cnt);
+            }
+            dst[o++] = '\n';
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, 4)
@@ -272,12 +336,14 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // ---- 0. ticket (tiles are started in index order, which look-back relies on) ------------------
+    // ---- 0. ticket (tiles are started in index order, which the look-backs rely on) ------------------
     if (tid == 0) {
         sm.tile = (int)atomicAdd(&ctrl->ticket, 1u);
         sm.irregular = *((volatile int*)&ctrl->irregular);
         sm.n_nl = 0;
         sm.skip_write = 0;
+        sm.tile_last_head = kNoHead;
+        sm.n_items = 0; sm.n_seg = 0; sm.n_lines = 0;
         mbar_init(&sm.mbar, 1);
         fence_mbar_init();
     }
@@ -325,12 +391,14 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
     }
     __syncthreads();
     const int cs = sm.cs, ce = sm.ce, cs_kind = sm.cs_kind;
-    bool bad = sm.irregular != 0;
 
-    // ---- 3. newline list of [cs, ce) ---------------------------------------------------------------------
-    if (!bad) {
+    // ---- 3. newline list of [cs, ce): AND-filter over 16 bytes, exact test only on a hit ------------------
+    if (!sm.irregular) {
         for (int c16 = (cs >> 4) + tid; (c16 << 4) < ce; c16 += kThreads) {
             uint4 v = *reinterpret_cast<const uint4*>(sm.win + (c16 << 4));
+            // a '\n' in any of the four words leaves a zero byte in the AND of (w ^ "\n\n\n\n")
+            uint32_t t = (v.x ^ 0x0A0A0A0Au) & (v.y ^ 0x0A0A0A0Au) & (v.z ^ 0x0A0A0A0Au) & (v.w ^ 0x0A0A0A0Au);
+            if (((t - 0x01010101u) & ~t & 0x80808080u) == 0u) continue;
             uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -341,173 +409,112 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
                     int g = (c16 << 4) + 4 * j + bpos;
                     if (g >= cs && g < ce) {
                         int slot = atomicAdd(&sm.n_nl, 1);
-                        if (slot < kMaxSeg) sm.nlpos[slot] = g;
+                        if (slot < kMaxNl) sm.nlpos[slot] = g;
                     }
                 }
             }
         }
     }
     __syncthreads();
-    int n_nl = sm.n_nl;
-    if (n_nl > kMaxSeg - 2) { bad = true; n_nl = 0; }
-    if (!bad) {   // rank sort (n_nl is tiny for real data)
-        for (int i = tid; i < n_nl; i += kThreads) {
-            int v = sm.nlpos[i], r = 0;
-            for (int j = 0; j < n_nl; j++) r += sm.nlpos[j] < v;
-            sm.nlsorted[r] = v;
-        }
-    }
-    __syncthreads();
 
-    // ---- 4. segments: [partial first line] + one per line start in (cs, ce) --------------------------------
-    // line starts: cs itself when cs_kind == kCutLine, and nl+1 for every newline with nl+1 < ce
+    // ---- 4. segments (warp 0): [partial first line] + one per line start in [cs, ce) ---------------------------
     const int first_partial = (cs_kind == kCutSample || cs_kind == kCutSampleFirst) && cs < ce ? 1 : 0;
-    int n_lines = 0;
-    if (!bad) {
-        n_lines = (cs_kind == kCutLine && cs < ce ? 1 : 0);
-        for (int i = 0; i < n_nl; i++) n_lines += (sm.nlsorted[i] + 1 < ce);     // uniform, tiny
-        const int n_seg = first_partial + n_lines;
-        if (n_seg > kMaxSeg) bad = true;
-        if (!bad) {
-            if (first_partial && tid == 0) {
-                Seg& s = sm.seg[0];
-                s.a = cs; s.ls = -1; s.s0 = -1;
-                s.e = n_nl ? sm.nlsorted[0] + 1 : ce;
-                s.flags = (n_nl ? 1 : 0) | (cs_kind == kCutSampleFirst ? 2 : 0);
+    if (warp == 0 && !sm.irregular) {
+        int n_nl = sm.n_nl;
+        if (n_nl > kMaxNl) { if (lane == 0) sm.irregular = 1; n_nl = 0; }
+        // sort the (few) newline positions: slot j ends up holding the j-th smallest
+        const int mine = lane < n_nl ? sm.nlpos[lane] : 0x7fffffff;
+        int rank = 0;
+        for (int j = 0; j < n_nl; j++) rank += (__shfl_sync(0xffffffffu, mine, j) < mine);
+        __syncwarp();
+        if (lane < n_nl) sm.nlpos[rank] = mine;
+        __syncwarp();
+        const int own_first = (cs_kind == kCutLine && cs < ce) ? 1 : 0;
+        int n_lines = own_first;
+        for (int j = 0; j < n_nl; j++) n_lines += (sm.nlpos[j] + 1 < ce);
+        if (first_partial && lane == 0) {
+            Seg& s = sm.seg[0];
+            s.a = cs; s.ls = -1; s.s0 = -1;
+            s.e = n_nl ? sm.nlpos[0] + 1 : ce;
+            s.flags = (n_nl ? 1 : 0) | (cs_kind == kCutSampleFirst ? 2 : 0);
+        }
+        for (int l = 0; l < n_lines; l++) {
+            const int nli = l - own_first;                 // index of the newline before this line
+            const int ls = nli < 0 ? cs : sm.nlpos[nli] + 1;
+            const int s0 = line_scan(sm.win, ls, vhi_w, lane);
+            if (lane == 0) {
+                Seg& s = sm.seg[first_partial + l];
+                const int nxt = nli + 1;                    // the newline that ends this line, if it is in the tile
+                s.ls = ls; s.s0 = s0; s.a = s0;
+                s.e = nxt < n_nl ? sm.nlpos[nxt] + 1 : ce;
+                s.flags = (nxt < n_nl ? 1 : 0) | 2;
+                if (s0 < 0 || s0 > s.e) sm.irregular = 1;
             }
-            const int own_first = (cs_kind == kCutLine && cs < ce) ? 1 : 0;
-            for (int l = warp; l < n_lines; l += kWarps) {
-                // line l starts at cs (if own_first and l == 0) or after newline (l - own_first)
-                int nli = l - own_first;                       // index of the newline before this line
-                int ls = nli < 0 ? cs : sm.nlsorted[nli] + 1;
-                int s0 = line_scan(sm.win, ls, vhi_w, lane);
-                if (lane == 0) {
-                    Seg& s = sm.seg[first_partial + l];
-                    int nxt = nli + 1;                          // the newline that ends this line, if in the tile
-                    s.ls = ls; s.s0 = s0; s.a = s0;
-                    s.e = nxt < n_nl ? sm.nlsorted[nxt] + 1 : ce;
-                    s.flags = (nxt < n_nl ? 1 : 0) | 2;
-                    if (s0 < 0 || s0 > s.e) sm.irregular = 1;
-                }
+        }
+        __syncwarp();
+        if (lane == 0 && !sm.irregular) {
+            const int n_seg = first_partial + n_lines;
+            int items = 0;
+            for (int i = 0; i < n_seg; i++) {
+                Seg& s = sm.seg[i];
+                if (((s.e - s.a) & 3) != 0) { sm.irregular = 1; break; }
+                s.item0 = items;
+                // blocks are indexed by where a sample word STARTS; a line start with no sample here still needs an item
+                items += s.e > s.a ? ((s.e - 4) >> 5) - (s.a >> 5) + 1 : 1;
             }
-            if (tid == 0) { sm.n_seg = n_seg; sm.n_lines = n_lines; }
+            if (items > kMaxItems) sm.irregular = 1;
+            if (!sm.irregular) { sm.n_seg = n_seg; sm.n_lines = n_lines; sm.n_items = items; }
         }
     }
     __syncthreads();
-    bad = bad || sm.irregular != 0;
-    if (!bad && tid == 0) {
-        int items = 0;
-        for (int i = 0; i < sm.n_seg; i++) {
-            Seg& s = sm.seg[i];
-            if (((s.e - s.a) & 3) != 0) { sm.irregular = 1; break; }
-            s.item0 = items;
-            // blocks are indexed by where a sample word STARTS; a line start with no sample here still needs an item
-            items += s.e > s.a ? ((s.e - 4) >> 5) - (s.a >> 5) + 1 : 1;
-        }
-        sm.n_items = items;
-        if (items > kMaxItems) sm.irregular = 1;
-        sm.tile_last_head = kNoHead;
-        sm.tile_last_cls = kNone;
-    }
-    __syncthreads();
-    bad = bad || sm.irregular != 0;
-    const int n_items = bad ? 0 : sm.n_items;
-    const int n_seg = bad ? 0 : sm.n_seg;
 
-    // ---- 5. classify items ---------------------------------------------------------------------------------
-    // item -> (segment, 32-byte block); sample k of the block sits at blk + phase + 4k
-    int my_last_head = kNoHead;
-    for (int base = 0; base < n_items; base += kRound) {
-#pragma unroll
-        for (int sub = 0; sub < 2; sub++) {
-            int item = base + warp * 64 + sub * 32 + lane;
-            if (item >= n_items) continue;
-            int si = seg_of_item(sm, item);
-            const Seg sg = sm.seg[si];
-            int blk = ((sg.a >> 5) + (item - sg.item0)) << 5;
-            int phase = sg.a & 3;
-            const uint32_t* wp = reinterpret_cast<const uint32_t*>(sm.win + blk);
-            uint32_t W[10];
-            W[0] = wp[-1];
-            uint4 v0 = *reinterpret_cast<const uint4*>(wp), v1 = *reinterpret_cast<const uint4*>(wp + 4);
-            W[1] = v0.x; W[2] = v0.y; W[3] = v0.z; W[4] = v0.w; W[5] = v1.x; W[6] = v1.y; W[7] = v1.z; W[8] = v1.w;
-            W[9] = wp[8];
-            uint32_t cls8 = 0, valid = 0, heads = 0;
-            int lineend = -1, prevc = kNone, lasthead = kNoHead, lastc = kNone;
-            bool first = true, irr = false;
-            int pc = 4;                                            // class of the previous word (4 = not coded)
-            {
-                uint32_t sp = __funnelshift_r(W[0], W[1], 8 * phase);
-                pc = (int)classify_word(sp);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                int addr = blk + phase + 4 * k;
-                uint32_t s = __funnelshift_r(W[k + 1], W[k + 2], 8 * phase);
-                int c = (int)classify_word(s);
-                bool v = addr >= sg.a && addr < sg.e;
-                if (v) {
-                    bool ends = (addr + 4 == sg.e) && (sg.flags & 1);
-                    uint32_t b3 = s >> 24;
-                    if (ends ? (b3 != '\n') : (b3 != '\t')) irr = true;
-                    if (c == 4 && has_tab_low3(s)) irr = true;
-                    bool fol = (addr == sg.a) && (sg.flags & 2);
-                    bool head = fol || c == 4 || c != pc;
-                    if (first) { prevc = fol ? kNone : pc; first = false; }
-                    valid |= 1u << k;
-                    cls8 |= (uint32_t)c << (4 * k);
-                    if (head) { heads |= 1u << k; lasthead = addr; }
-                    if (ends) lineend = k;
-                    lastc = ends ? kNone : c;
-                }
-                pc = c;
-            }
-            if (irr) sm.irregular = 1;
-            sm.itemCls[item] = cls8;
-            sm.itemMeta[item] = valid | (heads << 8) | ((uint32_t)prevc << 16) | ((uint32_t)(lineend + 1) << 20);
-            my_last_head = max(my_last_head, lasthead);
-            if (item == n_items - 1) sm.tile_last_cls = valid ? lastc : kNone;
-        }
-    }
-    // tile summary for look-back #1: last run head of the tile
+    // ---- 5. classify: two items per thread (lane l of warp w: items 64w + l and 64w + 32 + l) ---------------------
+    Item it0, it1;
+    int lh0, lh1;
+    item_classify(sm, warp * 64 + lane, it0, &lh0);
+    item_classify(sm, warp * 64 + 32 + lane, it1, &lh1);
+    // last run head before each item, inside the warp: nearest lower lane that has a head
+    int ein0, ein1;
     {
-        int m = my_last_head;
-#pragma unroll
-        for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-        if (lane == 0) sm.warp_h[warp] = m;
+        const unsigned hm0 = __ballot_sync(0xffffffffu, lh0 != kNoHead), hm1 = __ballot_sync(0xffffffffu, lh1 != kNoHead);
+        const unsigned below = (1u << lane) - 1u;
+        const int src0 = (hm0 & below) ? 31 - __clz(hm0 & below) : 0, src1 = (hm1 & below) ? 31 - __clz(hm1 & below) : 0;
+        const int g0 = __shfl_sync(0xffffffffu, lh0, src0), g1 = __shfl_sync(0xffffffffu, lh1, src1);
+        const int last0 = __shfl_sync(0xffffffffu, lh0, hm0 ? 31 - __clz(hm0) : 0);
+        const int last1 = __shfl_sync(0xffffffffu, lh1, hm1 ? 31 - __clz(hm1) : 0);
+        const int tot0 = hm0 ? last0 : kNoHead, tot1 = hm1 ? last1 : kNoHead;
+        ein0 = (hm0 & below) ? g0 : kNoHead;
+        ein1 = (hm1 & below) ? g1 : tot0;
+        const int warp_last = hm1 ? tot1 : tot0;
+        if (lane == 0) { sm.warp_h[warp] = warp_last; if (warp_last != kNoHead) atomicMax(&sm.tile_last_head, warp_last); }
     }
     __syncthreads();
-    bad = bad || sm.irregular != 0;
+    bool bad = sm.irregular != 0;
 
-    // ---- 6. look-back #1: run length carried into the tile -------------------------------------------------------
+    // ---- 6. look-back #1 (thread 0): chunk count of the run that enters the tile -------------------------------------
     if (tid == 0) {
-        int tl = kNoHead;
-        for (int w = 0; w < kWarps; w++) tl = max(tl, sm.warp_h[w]);
-        sm.tile_last_head = tl;
+        const int tl = sm.tile_last_head;
         int ein = kNoHead;
-        unsigned my = (2u << 30) | ((unsigned)kNone << 8);        // default: nothing carried out (bad tile / line end)
-        if (!bad) {
-            const int lc = sm.tile_last_cls;                       // class of the tile's last sample, kNone after '\n'
-            const bool need_in = first_partial && cs_kind == kCutSample;   // first sample continues a line
-            int pc0 = kNone;
-            if (need_in) {
-                uint32_t meta0 = sm.itemMeta[0];
-                pc0 = (int)((meta0 >> 16) & 0xFu);
-            }
-            const bool uniform = tl == kNoHead;                   // no run head in the tile: the incoming run covers it
-            const int nsamp = (ce - cs) >> 2;                      // only meaningful when uniform (single partial segment)
+        if (!bad && cs < ce) {
+            // class of the tile's last sample (kNone when the tile ends with a line end or a required section)
+            int lc = kNone;
+            if (sm.ce_kind == kCutSample) lc = gt_class3(sm.win + ce - 4);
+            const bool need_in = first_partial && cs_kind == kCutSample;      // the first sample continues a line
+            const int pc0 = need_in ? gt_class3(sm.win + cs - 4) : kNone;
+            const bool uniform = tl == kNoHead;                   // no run head in the tile: the entering run covers it
+            const int nsamp = (ce - cs) >> 2;                      // only used when uniform (one partial segment)
+            const int Ml = lc == 0 ? 127 : 31;
             if (!uniform) {
-                unsigned cnt = lc < 4 ? (unsigned)((((ce - tl) >> 2) - 1) % cls_max(lc)) + 1u : 0u;
-                my = (2u << 30) | ((unsigned)lc << 8) | cnt;
-                s1[tile] = my;                                     // absolute: publish before waiting
+                unsigned cnt = lc < 4 ? (unsigned)((((ce - tl) >> 2) - 1) % Ml) + 1u : 0u;
+                s1[tile] = (2u << 30) | ((unsigned)lc << 8) | cnt;    // absolute: publish before waiting
                 __threadfence();
             } else if (lc < 4) {
-                s1[tile] = (1u << 30) | ((unsigned)lc << 8) | (unsigned)(nsamp % cls_max(lc));   // relative
+                s1[tile] = (1u << 30) | ((unsigned)lc << 8) | (unsigned)(nsamp % Ml);   // relative to the entering run
                 __threadfence();
             }
             int cnt_in = 0;
             if (need_in && pc0 < 4 && tile > 0) {
-                const int M = cls_max(pc0);
+                const int M = pc0 == 0 ? 127 : 31;
                 int acc = 0;
                 for (int j = tile - 1; j >= 0; j--) {
                     unsigned v;
@@ -519,116 +526,61 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
                 ein = cs - 4 * cnt_in;
             }
             if (uniform) {
-                unsigned cnt = lc < 4 ? (unsigned)((cnt_in + nsamp - 1) % cls_max(lc)) + 1u : 0u;
+                unsigned cnt = lc < 4 ? (unsigned)((cnt_in + nsamp - 1) % Ml) + 1u : 0u;
                 s1[tile] = (2u << 30) | ((unsigned)lc << 8) | cnt;
                 __threadfence();
             }
         } else {
-            s1[tile] = my;
+            s1[tile] = (2u << 30) | ((unsigned)kNone << 8);          // nothing carried out
             __threadfence();
         }
 #ifdef VCFC_DEBUG
-        printf("tile %d cs=%d(k%d) ce=%d bad=%d n_items=%d n_seg=%d tl=%d lc=%d s1=%08x ein=%d wbase=%lld\n", tile, cs, cs_kind, ce, (int)bad,
-               n_items, n_seg, tl, sm.tile_last_cls, s1[tile], ein, wbase);
+        printf("tile %d cs=%d(k%d) ce=%d(k%d) bad=%d n_items=%d n_seg=%d tl=%d s1=%08x ein=%d wbase=%lld\n", tile, cs, cs_kind, ce,
+               sm.ce_kind, (int)bad, sm.n_items, sm.n_seg, tl, s1[tile], ein, wbase);
 #endif
         sm.ein_virtual = ein;
-        sm.carry_i = 0;
-        sm.carry_head = ein;
     }
     __syncthreads();
 
-    // ---- 7. byte counts: exclusive max-scan of run heads, walk, exclusive sum-scan ----------------------------------
-    for (int base = 0; base < n_items; base += kRound) {
-        int head_sub[2], cnt_sub[2], ein_sub[2];
-        uint32_t cls_sub[2], meta_sub[2];
-        int blk_sub[2], ph_sub[2], first_sub[2];
-        // (a) last head per item
-#pragma unroll
-        for (int sub = 0; sub < 2; sub++) {
-            int item = base + warp * 64 + sub * 32 + lane;
-            head_sub[sub] = kNoHead; cls_sub[sub] = 0; meta_sub[sub] = 0; blk_sub[sub] = 0; ph_sub[sub] = 0; first_sub[sub] = 0;
-            if (item < n_items) {
-                int si = seg_of_item(sm, item);
-                const Seg sg = sm.seg[si];
-                int blk = ((sg.a >> 5) + (item - sg.item0)) << 5, phase = sg.a & 3;
-                uint32_t meta = sm.itemMeta[item];
-                uint32_t heads = (meta >> 8) & 0xFFu, valid = meta & 0xFFu;
-                if (heads) head_sub[sub] = blk + phase + 4 * (31 - __clz(heads));
-                first_sub[sub] = valid ? blk + phase + 4 * (__ffs(valid) - 1) : 0;
-                cls_sub[sub] = sm.itemCls[item]; meta_sub[sub] = meta; blk_sub[sub] = blk; ph_sub[sub] = phase;
-            }
-        }
-        // (b) exclusive max-scan over the round's items (item order = warp-major, sub, lane)
-        int warp_tot;
-        {
-            int inc0 = head_sub[0];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc0, d); if (lane >= d) inc0 = max(inc0, t); }
-            int tot0 = __shfl_sync(0xffffffffu, inc0, 31);
-            int ex0 = __shfl_up_sync(0xffffffffu, inc0, 1);
-            if (lane == 0) ex0 = kNoHead;
-            int inc1 = head_sub[1];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc1, d); if (lane >= d) inc1 = max(inc1, t); }
-            int tot1 = __shfl_sync(0xffffffffu, inc1, 31);
-            int ex1 = __shfl_up_sync(0xffffffffu, inc1, 1);
-            if (lane == 0) ex1 = kNoHead;
-            ein_sub[0] = ex0;
-            ein_sub[1] = max(ex1, tot0);
-            warp_tot = max(tot0, tot1);
-        }
-        if (lane == 0) sm.warp_h[warp] = warp_tot;
-        __syncthreads();
-        {
-            int pre = sm.carry_head;
-            for (int w = 0; w < warp; w++) pre = max(pre, sm.warp_h[w]);
-            ein_sub[0] = max(ein_sub[0], pre);
-            ein_sub[1] = max(ein_sub[1], pre);
-        }
-        __syncthreads();
-        if (tid == 0) { int c = sm.carry_head; for (int w = 0; w < kWarps; w++) c = max(c, sm.warp_h[w]); sm.carry_head = c; }
-        // (c) count bytes per item (+ header and required section on the first item of a line that starts here)
-#pragma unroll
-        for (int sub = 0; sub < 2; sub++) {
-            int item = base + warp * 64 + sub * 32 + lane;
-            cnt_sub[sub] = 0;
-            if (item < n_items) {
-                int cp, cnt, cpo, cno;
-                run_state_before(meta_sub[sub], first_sub[sub], ein_sub[sub], &cp, &cnt);
-                int nb = item_walk<false>(sm.win, blk_sub[sub], ph_sub[sub], cls_sub[sub], meta_sub[sub], cp, cnt, nullptr, &cpo, &cno);
-                int si = seg_of_item(sm, item);
-                if (sm.seg[si].item0 == item && sm.seg[si].ls >= 0) nb += 8 + (sm.seg[si].s0 - sm.seg[si].ls);
-                cnt_sub[sub] = nb;
-            }
-        }
-        // (d) exclusive sum-scan
-        {
-            int inc0 = cnt_sub[0];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc0, d); if (lane >= d) inc0 += t; }
-            int tot0 = __shfl_sync(0xffffffffu, inc0, 31);
-            int inc1 = cnt_sub[1];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc1, d); if (lane >= d) inc1 += t; }
-            int tot1 = __shfl_sync(0xffffffffu, inc1, 31);
-            if (lane == 0) sm.warp_s[warp] = tot0 + tot1;
-            __syncthreads();
-            int pre = sm.carry_i;
-            for (int w = 0; w < warp; w++) pre += sm.warp_s[w];
-            int item0 = base + warp * 64 + lane, item1 = item0 + 32;
-            if (item0 < n_items) sm.itemOff[item0] = pre + inc0 - cnt_sub[0];
-            if (item1 < n_items) sm.itemOff[item1] = pre + tot0 + inc1 - cnt_sub[1];
-            __syncthreads();
-            if (tid == 0) { int c = sm.carry_i; for (int w = 0; w < kWarps; w++) c += sm.warp_s[w]; sm.carry_i = c; }
-        }
-        __syncthreads();
+    // ---- 7. byte counts and their exclusive scan -----------------------------------------------------------------------
+    {
+        int pre = sm.ein_virtual;                                  // heads of earlier warps (addresses grow with the item index)
+        for (int w = 0; w < warp; w++) pre = max(pre, sm.warp_h[w]);
+        ein0 = max(ein0, pre);
+        ein1 = max(ein1, pre);
     }
-    __syncthreads();
-    int total = bad ? 0 : sm.carry_i;
-    if (total > kStage - 32) { bad = true; total = 0; if (tid == 0) sm.irregular = 1; }
+    uint32_t cf0 = 0, cf1 = 0;
+    int cp0 = 0, cp1 = 0;
+    bool m0 = true, m1 = true;
+    const int n0 = bad ? 0 : item_count(sm, it0, ein0, &cf0, &cp0, &m0);
+    const int n1 = bad ? 0 : item_count(sm, it1, ein1, &cf1, &cp1, &m1);
+    int off0, off1, total;
+    {
+        // both sub-rounds in one scan: low half = items 64w + lane, high half = items 64w + 32 + lane
+        const unsigned packed = (unsigned)n0 | ((unsigned)n1 << 16);
+        unsigned inc = packed;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
+        const int tot0 = (int)(tot & 0xFFFFu), tot1 = (int)(tot >> 16);
+        if (lane == 0) sm.warp_s[warp] = tot0 + tot1;
+        __syncthreads();
+        int pre = 0, all = 0;
+        for (int w = 0; w < kWarps; w++) { int v = sm.warp_s[w]; all += v; if (w < warp) pre += v; }
+        off0 = pre + (int)(inc & 0xFFFFu) - n0;
+        off1 = pre + tot0 + (int)(inc >> 16) - n1;
+        total = all;
+    }
+    if (total > kStage - 32) { bad = true; total = 0; }
     if (bad && tid == 0) atomicExch(&ctrl->irregular, 1);
 
-    // ---- 8. look-back #2: output offset and line index of the tile ------------------------------------------------
+    // ---- 8. emit into staging (all warps), then look-back #2 (warp 0) ------------------------------------------------------
+    if (!bad) {
+        if (it0.hdr) sm.seg[it0.seg].out0 = off0;
+        if (it1.hdr) sm.seg[it1.seg].out0 = off1;
+        item_emit(sm, it0, cf0, cp0, m0, sm.stage + off0 + it0.hdr);
+        item_emit(sm, it1, cf1, cp1, m1, sm.stage + off1 + it1.hdr);
+    }
     if (warp == 0) {
         const unsigned long long my_b = (unsigned long long)total, my_l = (unsigned long long)(bad ? 0 : sm.n_lines);
         if (lane == 0) st_status(s2 + 2 * (size_t)tile, kFlagAgg | my_b, kFlagAgg | my_l);
@@ -661,109 +613,38 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
     __syncthreads();
     if (bad || sm.skip_write) return;
     const unsigned long long obase = sm.excl_bytes;
-    const int shift = (int)(obase & 15ull);                   // staging is laid out 16-byte congruent with the output
-    uint8_t* const stg = sm.stage + shift;
 
-    // ---- 9. emit into staging --------------------------------------------------------------------------------------
-    // (a) sample bytes; the max-scan is replayed from itemOff-independent data: ein is recomputed per item
-    sm.carry_head = sm.ein_virtual;   // all threads write the same value
-    __syncthreads();
-    for (int base = 0; base < n_items; base += kRound) {
-        int head_sub[2], ein_sub[2];
-#pragma unroll
-        for (int sub = 0; sub < 2; sub++) {
-            int item = base + warp * 64 + sub * 32 + lane;
-            head_sub[sub] = kNoHead;
-            if (item < n_items) {
-                int si = seg_of_item(sm, item);
-                const Seg sg = sm.seg[si];
-                int blk = ((sg.a >> 5) + (item - sg.item0)) << 5, phase = sg.a & 3;
-                uint32_t heads = (sm.itemMeta[item] >> 8) & 0xFFu;
-                if (heads) head_sub[sub] = blk + phase + 4 * (31 - __clz(heads));
-            }
-        }
-        int warp_tot;
-        {
-            int inc0 = head_sub[0];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc0, d); if (lane >= d) inc0 = max(inc0, t); }
-            int tot0 = __shfl_sync(0xffffffffu, inc0, 31);
-            int ex0 = __shfl_up_sync(0xffffffffu, inc0, 1);
-            if (lane == 0) ex0 = kNoHead;
-            int inc1 = head_sub[1];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc1, d); if (lane >= d) inc1 = max(inc1, t); }
-            int tot1 = __shfl_sync(0xffffffffu, inc1, 31);
-            int ex1 = __shfl_up_sync(0xffffffffu, inc1, 1);
-            if (lane == 0) ex1 = kNoHead;
-            ein_sub[0] = ex0;
-            ein_sub[1] = max(ex1, tot0);
-            warp_tot = max(tot0, tot1);
-        }
-        if (lane == 0) sm.warp_h[warp] = warp_tot;
-        __syncthreads();
-        {
-            int pre = sm.carry_head;
-            for (int w = 0; w < warp; w++) pre = max(pre, sm.warp_h[w]);
-            ein_sub[0] = max(ein_sub[0], pre);
-            ein_sub[1] = max(ein_sub[1], pre);
-        }
-        __syncthreads();
-        if (tid == 0) { int c = sm.carry_head; for (int w = 0; w < kWarps; w++) c = max(c, sm.warp_h[w]); sm.carry_head = c; }
-#pragma unroll
-        for (int sub = 0; sub < 2; sub++) {
-            int item = base + warp * 64 + sub * 32 + lane;
-            if (item < n_items) {
-                int si = seg_of_item(sm, item);
-                const Seg sg = sm.seg[si];
-                int blk = ((sg.a >> 5) + (item - sg.item0)) << 5, phase = sg.a & 3;
-                uint32_t meta = sm.itemMeta[item], cls8 = sm.itemCls[item], valid = meta & 0xFFu;
-                int first_addr = valid ? blk + phase + 4 * (__ffs(valid) - 1) : 0;
-                int cp, cnt, cpo, cno;
-                run_state_before(meta, first_addr, ein_sub[sub], &cp, &cnt);
-                int o = sm.itemOff[item];
-                if (sg.item0 == item && sg.ls >= 0) {
-                    sm.seg[si].out0 = o;
-                    o += 8 + (sg.s0 - sg.ls);
-                }
-                item_walk<true>(sm.win, blk, phase, cls8, meta, cp, cnt, stg + o, &cpo, &cno);
-            }
-        }
-        __syncthreads();
-    }
-    __syncthreads();
-    // (b) line starts: two length headers + required section; record the line's output offset
+    // ---- 9. line starts: two length headers + required section; record the line's output offset --------------------------
     {
         const unsigned long long lbase = sm.excl_lines;
-        for (int l = warp; l < sm.n_lines; l += kWarps) {
-            const Seg sg = sm.seg[first_partial + l];
-            const int rq = sg.s0 - sg.ls;
-            uint8_t* d = stg + sg.out0;
+        const int nl = sm.n_lines;
+        for (int l = warp; l < nl; l += kWarps) {
+            const int si = first_partial + l;
+            const int ls = sm.seg[si].ls, rq = sm.seg[si].s0 - ls, o0 = sm.seg[si].out0;
+            uint8_t* d = sm.stage + o0;
             if (lane < 4) d[lane] = lane == 0 ? 0xC0 : 0;                       // line length: patched by k_patch_headers
             if (lane >= 4 && lane < 8) {
                 unsigned v = (unsigned)rq;
                 d[lane] = lane == 4 ? (uint8_t)((v >> 24) | 0xC0) : (uint8_t)(v >> (8 * (7 - lane)));
             }
-            for (int k = lane; k < rq; k += 32) d[8 + k] = sm.win[sg.ls + k];
-            if (lane == 0) line_offs[lbase + (unsigned long long)l] = obase + (unsigned long long)sg.out0;
+            for (int k = lane; k < rq; k += 32) d[8 + k] = sm.win[ls + k];
+            if (lane == 0) line_offs[lbase + (unsigned long long)l] = obase + (unsigned long long)o0;
         }
+        if (nl) __syncthreads();
     }
-    __syncthreads();
 
-    // ---- 10. staging -> HBM, 16-byte stores -------------------------------------------------------------------------
+    // ---- 10. staging -> HBM: aligned 4-byte stores, source words funnel-shifted ----------------------------------------------
     {
-        uint8_t* dst = out + obase;                       // dst + k <-> stg[k]; (dst - shift) is 16-byte aligned
-        const int lo = shift, hi = shift + total;         // staging byte range [lo, hi) of sm.stage
-        const int body_lo = (lo + 15) & ~15, body_hi = hi & ~15;
-        if (body_lo >= body_hi) {
-            for (int k = lo + tid; k < hi; k += kThreads) dst[k - shift] = sm.stage[k];
-        } else {
-            for (int k = lo + tid; k < body_lo; k += kThreads) dst[k - shift] = sm.stage[k];
-            for (int k = body_hi + tid; k < hi; k += kThreads) dst[k - shift] = sm.stage[k];
-            uint4* d4 = reinterpret_cast<uint4*>(dst - shift);
-            const uint4* s4 = reinterpret_cast<const uint4*>(sm.stage);
-            for (int k = (body_lo >> 4) + tid; k < (body_hi >> 4); k += kThreads) d4[k] = s4[k];
-        }
+        uint8_t* dst = out + obase;
+        const int mis = (int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);      // bytes until dst is 4-byte aligned
+        const int head = min(mis, total);
+        if (tid < head) dst[tid] = sm.stage[tid];
+        const int nwords = (total - head) >> 2;
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(sm.stage);              // stage is 16-byte aligned
+        uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+        for (int k = tid; k < nwords; k += kThreads) dw[k] = __funnelshift_r(sw[k], sw[k + 1], 8 * head);   // stage[head + 4k ..]
+        const int tail0 = head + 4 * nwords;
+        if (tid < total - tail0) dst[tail0 + tid] = sm.stage[tail0 + tid];
     }
 }
 
@@ -815,7 +696,7 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         return VCFC_OK;
     }
     // host-checkable preconditions of the tile path; anything else goes to the generic kernels
-    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (reinterpret_cast<uintptr_t>(d_out) & 15) || in_len >= (1ull << 46)) {
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || in_len >= (1ull << 46)) {
         k_set_result<<<1, 1, 0, stream>>>(d_result, kStatusIrregular);
         ctx->launches++;
         return VCFC_OK;
@@ -835,11 +716,8 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
     uint8_t* base = (uint8_t*)ws.p;
     Ctrl* ctrl = (Ctrl*)base;
     VCFC_CUDA(ctx, cudaMemsetAsync(base, 0, off_lines, stream));
-    Ctrl h;
-    memset(&h, 0, sizeof(h));
-    h.line_cap = lines_cap;
-    // the last byte must be '\n' (a missing final newline is the generic path's business)
-    VCFC_CUDA(ctx, cudaMemcpyAsync(&ctrl->line_cap, &h.line_cap, sizeof(h.line_cap), cudaMemcpyHostToDevice, stream));
+    unsigned long long lc = lines_cap;
+    VCFC_CUDA(ctx, cudaMemcpyAsync(&ctrl->line_cap, &lc, sizeof(lc), cudaMemcpyHostToDevice, stream));
     if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeEncode], stream);
     k_encode_tiles<<<(unsigned)n_tiles, kThreads, sizeof(Smem), stream>>>(
         d_in, (long long)in_len, d_out, (unsigned long long)out_cap, ctrl, (unsigned int*)(base + off_s1),
