@@ -1,11 +1,573 @@
-// placeholder until the tile kernel lands: every block is reported irregular -> generic path
+// vcfc_decode_fast.cu -- tile-parallel decoder (sm_100a) for well-formed .vcfc data lines:
+// every line's token stream holds exactly sample_count samples, literals are single-column
+// (0xE1, what the reference encoder writes, compress.cpp:179-181), >= 1 sample per line.
+// Anything else sets ctrl->irregular and the caller reruns the block on the generic kernels,
+// which reproduce the reference decoder's behaviour on odd input token by token.
+//
+// Output bytes are those of decompress2_data_line (/root/reference/src/compress.cpp:741-986).
+// Pipeline (all on the launch stream; two small host reads size the workspace):
+//   D1 k_dec_walk     line table without a serial pointer chase: every 16 KB segment finds its first
+//                     plausible line start and follows the 4-byte length headers (utils.hpp:134-247)
+//                     to the segment end; k_dec_verify accepts the table only if every segment's
+//                     chain ends exactly where the next one began (induction from offset 0).
+//   D2 k_dec_sizes    one warp per line: validates the line and sizes its text.  The token/payload
+//                     state of a byte is the kind of the last "setter" before it (a byte >= 0xE0
+//                     enters a payload, a tab/newline leaves it), so 16-byte chunks parse in parallel.
+//   D3 scan           line text offsets; k_dec_tilemap: first line of every 16 KB output tile
+//   D4 k_dec_expand   one CTA per OUTPUT tile: parses the lines that overlap it from smem, expands
+//                     runs into an smem image of the tile (long runs warp-cooperatively) and stores
+//                     the tile with aligned 16-byte stores.  HBM traffic = 2 C + N.
+#include <algorithm>
+
 #include "vcfc_common.cuh"
 #include "vcfc_internal.h"
+
 namespace vcfc {
-__global__ void k_dec_irregular(vcfc_result* r) { r->status = kStatusIrregular; r->out_len = 0; r->n_lines = 0; r->err_line = 0; }
-int decode_fast(vcfc_ctx* ctx, const uint8_t*, size_t, uint64_t, uint8_t*, size_t, vcfc_result* d_result, bool, cudaStream_t stream) {
-    k_dec_irregular<<<1, 1, 0, stream>>>(d_result);
+namespace dec {
+
+constexpr int kSeg = 16384;             // D1 segment (compressed bytes)
+constexpr int kTile = 16384;            // D4 output tile
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kCmax = 24576;            // longest compressed line the tile kernel parses from smem
+constexpr int kLongRun = 12;            // runs of >= this many samples are expanded by a whole warp
+constexpr int kQueue = 1024;
+constexpr long long kNoCand = -1, kBroken = -2;
+
+constexpr int kMaxFix = 1024;
+struct Ctrl {
+    int irregular;
+    int n_fix;                                    // segments whose first plausible line start is not on the chain
+    unsigned long long n_lines, end_pos, total_out;
+    int fix[kMaxFix];
+};
+
+__device__ __forceinline__ long long hdr_len(const uint8_t* p) {     // utils.hpp:188-231; -1 = bad tag
+    if ((p[0] >> 6) != 3) return -1;
+    return ((long long)(p[0] & 0x3F) << 24) | ((long long)p[1] << 16) | ((long long)p[2] << 8) | p[3];
+}
+
+// a position where a line can start: both tags present, lengths consistent, line ends with '\n'
+__device__ __forceinline__ bool plausible_line(const uint8_t* __restrict__ in, long long n, long long p, long long* ll_out) {
+    if (n - p < 8) return false;
+    long long ll = hdr_len(in + p), rq = hdr_len(in + p + 4);
+    if (ll < 0 || rq < 1 || rq + 5 > ll || ll + 4 > n - p) return false;
+    if (in[p + 4 + ll - 1] != '\n') return false;
+    if (in[p + 8 + rq - 1] != '\t') return false;            // the required section of a line with samples ends with a tab
+    *ll_out = ll;
+    return true;
+}
+
+// ---- D1: speculative line table ---------------------------------------------------------------------
+__global__ void k_dec_walk(const uint8_t* __restrict__ in, long long n, long long n_seg, long long* __restrict__ cand,
+                           long long* __restrict__ endp, unsigned long long* __restrict__ cnt) {
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const long long lo = s * kSeg, hi = lo + kSeg < n ? lo + kSeg : n;
+    long long c = kNoCand, ll = 0;
+    for (long long p = lo; p < hi; p++) {
+        if (p != 0 && in[p - 1] != '\n') continue;
+        if (plausible_line(in, n, p, &ll)) { c = p; break; }
+        if (p == 0) break;                                   // offset 0 must be a line start
+    }
+    unsigned long long k = 0;
+    long long p = c;
+    if (c >= 0) {
+        while (true) {
+            k++;
+            p += 4 + ll;
+            if (p >= hi) break;
+            if (n - p < 8) break;                            // <8 bytes left: EOF for the reference (compress.cpp:770-777)
+            if (!plausible_line(in, n, p, &ll)) { p = kBroken; break; }
+        }
+    }
+    cand[s] = c;
+    endp[s] = p;
+    cnt[s] = k;
+}
+
+// Chain check, by induction from offset 0: a segment's first line start must be where the previous chain
+// ended, and a chain that ends inside a segment must find a line start there (so the last chain reaches
+// EOF: fewer than 8 bytes left, compress.cpp:770-777).  A '\n'-valued token followed by header-looking
+// bytes can fake a line start; such segments are listed (strict = 0) for k_dec_repair, and the table is
+// accepted only if a second, strict pass finds nothing.
+__global__ void k_dec_verify(long long n, long long n_seg, const long long* __restrict__ cand, const long long* __restrict__ endp,
+                             Ctrl* __restrict__ ctrl, int strict) {
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const long long c = cand[s], e = endp[s];
+    if (s == 0) { if (c != 0 || e == kBroken) atomicExch(&ctrl->irregular, 1); return; }
+    bool ok = true;
+    long long q = s - 1;                                      // previous segment that has a line start
+    while (q > 0 && cand[q] < 0) q--;
+    const long long pe = endp[q];                             // where its chain ends = where the next line starts
+    if (c >= 0) {
+        if (pe != c || e == kBroken) ok = false;
+    } else if (pe >= 0 && pe / kSeg == s && n - pe >= 8) {
+        ok = false;                                           // the chain says a line starts here but none was found
+    }
+    if (!ok) {
+        if (strict) atomicExch(&ctrl->irregular, 1);
+        else { int slot = atomicAdd(&ctrl->n_fix, 1); if (slot < kMaxFix) ctrl->fix[slot] = (int)s; }
+    }
+}
+
+// Re-walks the listed segments from where the chain really arrives (one thread, left to right: few entries).
+__global__ void k_dec_repair(const uint8_t* __restrict__ in, long long n, long long n_seg, long long* __restrict__ cand,
+                             long long* __restrict__ endp, unsigned long long* __restrict__ cnt, Ctrl* __restrict__ ctrl) {
+    const int nf = ctrl->n_fix;
+    if (nf == 0 || ctrl->irregular) return;
+    if (nf > kMaxFix || n_seg >= (1ll << 31)) { ctrl->irregular = 1; return; }
+    for (int i = 1; i < nf; i++) {                            // insertion sort
+        int v = ctrl->fix[i], j = i - 1;
+        while (j >= 0 && ctrl->fix[j] > v) { ctrl->fix[j + 1] = ctrl->fix[j]; j--; }
+        ctrl->fix[j + 1] = v;
+    }
+    for (int i = 0; i < nf; i++) {
+        const long long s = ctrl->fix[i];
+        long long q = s - 1;
+        while (q > 0 && cand[q] < 0) q--;
+        long long p = endp[q], ll = 0;
+        const long long hi = (s + 1) * kSeg < n ? (s + 1) * kSeg : n;
+        unsigned long long k = 0;
+        long long c = kNoCand, e = kNoCand;
+        if (p >= 0 && p / kSeg == s && n - p >= 8) {          // the chain arrives inside this segment: walk from there
+            c = p;
+            if (!plausible_line(in, n, p, &ll)) { ctrl->irregular = 1; return; }
+            while (true) {
+                k++;
+                p += 4 + ll;
+                if (p >= hi || n - p < 8) break;
+                if (!plausible_line(in, n, p, &ll)) { ctrl->irregular = 1; return; }
+            }
+            e = p;
+        } else if (!(p >= 0 && (p / kSeg > s || n - p < 8))) { // else: the chain passes over this segment -> it is empty
+            ctrl->irregular = 1;
+            return;
+        }
+        cand[s] = c;
+        endp[s] = e;
+        cnt[s] = k;
+    }
+}
+
+__global__ void k_dec_fill(const uint8_t* __restrict__ in, long long n, long long n_seg, const long long* __restrict__ cand,
+                           const unsigned long long* __restrict__ base, unsigned long long* __restrict__ line_start,
+                           unsigned long long n_lines, const Ctrl* __restrict__ ctrl) {
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg || ctrl->irregular) return;
+    long long p = cand[s];
+    if (p < 0) return;
+    const long long hi = (s + 1) * kSeg < n ? (s + 1) * kSeg : n;
+    unsigned long long k = base[s];
+    while (true) {
+        long long ll = hdr_len(in + p);
+        line_start[k++] = (unsigned long long)p;
+        p += 4 + ll;
+        if (p >= hi || n - p < 8) break;
+    }
+    if (k == n_lines) line_start[k] = (unsigned long long)p;
+}
+
+// ---- token stream parsing -----------------------------------------------------------------------------
+// kinds of setter: 1 = a byte >= 0xE0 (enters a literal payload when read as a token, stays in it when read as payload),
+// 2 = tab / newline (ends a payload; as a token it is a 0|0 run of 9 / 10 and the state stays "token")
+__device__ __forceinline__ int last_setter_kind(const uint8_t* b, int nb) {
+    int kind = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        uint32_t c = b[i];
+        if (i < nb) {
+            if (c >= 0xE0u) kind = 1;
+            else if (c == 9u || c == 10u) kind = 2;
+        }
+    }
+    return kind;
+}
+
+// Walks nb token-region bytes starting in `payload` state; accumulates text bytes and samples.
+// is_last: the chunk ends with the line's final '\n'.  err bits: 1 = malformed for this path.
+__device__ __forceinline__ void chunk_measure(const uint8_t* b, int nb, bool payload, bool is_last, unsigned* out_len,
+                                              unsigned* samples, int* err) {
+    unsigned o = 0, ns = 0;
+    int e = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t c = b[i];
+        const bool line_end = is_last && i == nb - 1;
+        if (i >= nb) {
+        } else if (payload) {
+            o++;
+            if (c == 9u) { payload = false; ns++; }
+            else if (c == 10u) { payload = false; ns++; if (!line_end) e = 1; }     // '\n' inside a payload: compress.cpp:875-884
+        } else if (line_end) {
+            // the newline after a run: it replaces the run's last tab, no text of its own
+        } else if (c < 0x80u) {
+            if (c == 0) e = 1;
+            o += 4u * c; ns += c;
+        } else if (c < 0xE0u) {
+            const uint32_t n = c & 0x1Fu;
+            if (n == 0) e = 1;
+            o += 4u * n; ns += n;
+        } else {
+            if ((c & 0x1Fu) != 1u) e = 1;                    // multi-column literal: generic path
+            payload = true;
+        }
+    }
+    *out_len = o; *samples = ns; *err = e;
+}
+
+// ---- D2: per-line validation and text size (one warp per line) ----------------------------------------------
+__global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ line_start,
+                            unsigned long long n_lines, unsigned long long sample_count, unsigned long long* __restrict__ sizes,
+                            Ctrl* __restrict__ ctrl) {
+    const unsigned long long k = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (k >= n_lines) return;
+    const unsigned long long ls = line_start[k], le = line_start[k + 1];
+    const uint8_t* p = in + ls;
+    const long long clen = (long long)(le - ls);
+    const long long rq = hdr_len(p + 4);
+    bool bad = clen > kCmax || rq < 1 || rq + 9 > clen + 0;
+    // required section: exactly 9 tabs (compress.cpp:820-828; the 8-tab form means no samples -> generic path)
+    unsigned tabs = 0;
+    if (!bad) for (long long i = lane; i < rq; i += 32) tabs += (p[8 + i] == '\t');
+#pragma unroll
+    for (int d = 16; d; d >>= 1) tabs += __shfl_xor_sync(0xffffffffu, tabs, d);
+    if (tabs != 9) bad = true;
+    unsigned long long total = 0, ns_total = 0;
+    if (!bad) {
+        const long long tb = 8 + rq, tn = clen - tb;            // token region, its last byte is the line's '\n'
+        int carry_kind = 0;                                     // last setter seen so far (0 = none: token state)
+        int err_any = 0;
+        for (long long base = 0; base < tn; base += 512) {
+            const long long off = base + 16ll * lane;
+            int nb = (int)(tn - off);
+            nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+            uint8_t b[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) b[i] = i < nb ? p[tb + off + i] : 0;
+            const int kind = last_setter_kind(b, nb);
+            // state at chunk start: last setter of the nearest lower lane that has one, else the carry
+            const unsigned has = __ballot_sync(0xffffffffu, kind != 0);
+            const unsigned below = has & ((1u << lane) - 1u);
+            const int src = below ? 31 - __clz(below) : 0;
+            const int k_src = __shfl_sync(0xffffffffu, kind, src);
+            const int k_in = below ? k_src : carry_kind;
+            unsigned o, ns;
+            int e;
+            chunk_measure(b, nb, k_in == 1, off + nb == tn && nb > 0, &o, &ns, &e);
+            err_any |= e;
+            unsigned long long o64 = o, n64 = ns;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) { o64 += __shfl_xor_sync(0xffffffffu, o64, d); n64 += __shfl_xor_sync(0xffffffffu, n64, d); }
+            total += o64; ns_total += n64;
+            if (has) carry_kind = __shfl_sync(0xffffffffu, kind, 31 - __clz(has));
+        }
+        err_any = __any_sync(0xffffffffu, err_any);
+        if (err_any || ns_total != sample_count) bad = true;
+        total += (unsigned long long)rq;
+    }
+    if (lane == 0) {
+        sizes[k] = bad ? 0ull : total;
+        if (bad) atomicExch(&ctrl->irregular, 1);
+    }
+}
+
+// first line of every output tile: line k covers text bytes [off[k], off[k+1])
+__global__ void k_dec_tilemap(const unsigned long long* __restrict__ off, unsigned long long n_lines, unsigned long long total,
+                              unsigned int* __restrict__ first_line) {
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_lines) return;
+    const unsigned long long a = off[k], b = k + 1 < n_lines ? off[k + 1] : total;
+    if (b == a) return;
+    for (unsigned long long t = (a + kTile - 1) / kTile; t * kTile < b; t++) first_line[t] = (unsigned int)k;
+}
+
+// ---- D4: expansion, one CTA per output tile --------------------------------------------------------------------
+struct Smem {
+    alignas(16) uint8_t stage[kTile];
+    alignas(16) uint8_t cbuf[kCmax + 16];
+    int q_pos[kQueue];
+    unsigned short q_cnt[kQueue];
+    unsigned char q_cls[kQueue];
+    int q_n;
+    int warp_kind[kWarps];
+    unsigned warp_out[kWarps];
+    int carry_kind;
+    unsigned carry_out;
+};
+
+// writes n copies of the 4-byte sample word w ("x|y\t") to text positions pos .. pos + 4n - 1 of the tile image
+__device__ __forceinline__ void put_run(uint8_t* stage, int tile_len, int pos, int n, uint32_t w, int lane0, int stride) {
+    // text byte (pos + j) = byte (j & 3) of w.  Aligned words of the image hold w rotated by ((-pos) & 3) bytes.
+    const int end = pos + 4 * n;
+    int a = pos < 0 ? 0 : pos, z = end > tile_len ? tile_len : end;
+    if (a >= z) return;
+    const int a4 = (a + 3) & ~3, z4 = z & ~3;
+    if (a4 >= z4) {
+        for (int i = a + lane0; i < z; i += stride) stage[i] = (uint8_t)(w >> (8 * ((i - pos) & 3)));
+        return;
+    }
+    if (lane0 == 0) {
+        for (int i = a; i < a4; i++) stage[i] = (uint8_t)(w >> (8 * ((i - pos) & 3)));
+        for (int i = z4; i < z; i++) stage[i] = (uint8_t)(w >> (8 * ((i - pos) & 3)));
+    }
+    const uint32_t rw = __funnelshift_r(w, w, 8 * ((a4 - pos) & 3));
+    uint32_t* sw = reinterpret_cast<uint32_t*>(stage);
+    for (int i = (a4 >> 2) + lane0; i < (z4 >> 2); i += stride) sw[i] = rw;
+}
+
+__device__ __forceinline__ uint32_t sample_word(uint32_t tok) {      // token byte -> "x|y\t" little-endian
+    uint32_t a = '0', b = '0';
+    if (tok & 0x80u) {
+        const uint32_t f = tok & 0xE0u;
+        a = f == kTok01 ? '0' : '1';
+        b = f == kTok10 ? '0' : '1';
+    }
+    return a | ((uint32_t)'|' << 8) | (b << 16) | ((uint32_t)'\t' << 24);
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
+k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ line_start,
+             const unsigned long long* __restrict__ off, unsigned long long n_lines, unsigned long long total,
+             const unsigned int* __restrict__ first_line, uint8_t* __restrict__ out, const Ctrl* __restrict__ ctrl) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    if (ctrl->irregular) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long T0 = (unsigned long long)blockIdx.x * kTile;
+    const int tile_len = (int)(total - T0 < (unsigned long long)kTile ? total - T0 : (unsigned long long)kTile);
+    unsigned long long k = first_line[blockIdx.x];
+    if (tid == 0) sm.q_n = 0;
+    __syncthreads();
+
+    for (; k < n_lines; k++) {
+        const unsigned long long o0 = off[k], o1 = k + 1 < n_lines ? off[k + 1] : total;
+        if (o0 >= T0 + (unsigned long long)tile_len) break;
+        if (o1 == o0) continue;
+        const int lpos = (int)((long long)o0 - (long long)T0);      // line's first text byte relative to the tile (may be < 0)
+        const unsigned long long ls = line_start[k];
+        const int clen = (int)(line_start[k + 1] - ls);
+        // stage the compressed line: 4-byte loads where the source allows
+        {
+            const uint8_t* src = in + ls;
+            const int mis = (int)((4 - (reinterpret_cast<uintptr_t>(src) & 3)) & 3);
+            const int head = mis < clen ? mis : clen;
+            if (tid < head) sm.cbuf[tid] = src[tid];
+            const int nw = (clen - head) >> 2;
+            const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src + head);
+            for (int i = tid; i < nw; i += kThreads) {
+                uint32_t v = s4[i];
+                uint8_t* d = sm.cbuf + head + 4 * i;
+                d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
+            }
+            const int t0 = head + 4 * nw;
+            if (tid < clen - t0) sm.cbuf[t0 + tid] = src[t0 + tid];
+            if (tid == 0) { sm.carry_kind = 0; sm.carry_out = 0; }
+        }
+        __syncthreads();
+        const int rq = (int)hdr_len(sm.cbuf + 4);
+        // required section passes through (compress.cpp:788-807)
+        for (int i = tid; i < rq; i += kThreads) {
+            const int t = lpos + i;
+            if (t >= 0 && t < tile_len) sm.stage[t] = sm.cbuf[8 + i];
+        }
+        const int tb = 8 + rq, tn = clen - tb;
+        const int tpos = lpos + rq;                                   // text position of the first sample
+        for (int base = 0; base < tn; base += 16 * kThreads) {
+            const int offc = base + 16 * tid;
+            int nb = tn - offc;
+            nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
+            uint8_t b[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) b[i] = i < nb ? sm.cbuf[tb + offc + i] : 0;
+            const int kind = last_setter_kind(b, nb);
+            const unsigned has = __ballot_sync(0xffffffffu, kind != 0);
+            const unsigned below = has & ((1u << lane) - 1u);
+            const int k_src = __shfl_sync(0xffffffffu, kind, below ? 31 - __clz(below) : 0);
+            const int warp_last = has ? __shfl_sync(0xffffffffu, kind, 31 - __clz(has)) : 0;
+            if (lane == 0) sm.warp_kind[warp] = warp_last;
+            __syncthreads();
+            int k_in = sm.carry_kind;
+            for (int w = 0; w < warp; w++) if (sm.warp_kind[w]) k_in = sm.warp_kind[w];
+            if (below) k_in = k_src;
+            const bool is_last = nb > 0 && offc + nb == tn;
+            unsigned o, ns;
+            int e;
+            chunk_measure(b, nb, k_in == 1, is_last, &o, &ns, &e);
+            // exclusive scan of text lengths over the CTA
+            unsigned inc = o;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            if (lane == 31) sm.warp_out[warp] = inc;
+            __syncthreads();
+            unsigned pre = sm.carry_out;
+            for (int w = 0; w < warp; w++) pre += sm.warp_out[w];
+            int pos = tpos + (int)(pre + inc - o);
+            // write this chunk's text
+            bool payload = k_in == 1;
+            if (pos < tile_len && pos + (int)o > 0) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const uint32_t c = b[i];
+                    const bool line_end = is_last && i == nb - 1;
+                    if (i >= nb) {
+                    } else if (payload) {
+                        if (pos >= 0 && pos < tile_len) sm.stage[pos] = (uint8_t)c;
+                        pos++;
+                        if (c == 9u || c == 10u) payload = false;
+                    } else if (line_end) {
+                    } else if (c < 0xE0u) {
+                        const int n = (int)(c < 0x80u ? c : (c & 0x1Fu));
+                        if (n >= kLongRun) {
+                            if (pos < tile_len && pos + 4 * n > 0) {
+                                const int slot = atomicAdd(&sm.q_n, 1);
+                                if (slot < kQueue) { sm.q_pos[slot] = pos; sm.q_cnt[slot] = (unsigned short)n; sm.q_cls[slot] = (unsigned char)c; }
+                                else put_run(sm.stage, tile_len, pos, n, sample_word(c), 0, 1);
+                            }
+                        } else {
+                            put_run(sm.stage, tile_len, pos, n, sample_word(c), 0, 1);
+                        }
+                        pos += 4 * n;
+                    } else {
+                        payload = true;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == kThreads - 1) {
+                sm.carry_out = pre + inc;
+                int kk = sm.carry_kind;
+                for (int w = 0; w < kWarps; w++) if (sm.warp_kind[w]) kk = sm.warp_kind[w];
+                sm.carry_kind = kk;
+            }
+            __syncthreads();
+        }
+        // long runs, one warp per run
+        {
+            const int qn = sm.q_n < kQueue ? sm.q_n : kQueue;
+            for (int q = warp; q < qn; q += kWarps)
+                put_run(sm.stage, tile_len, sm.q_pos[q], (int)sm.q_cnt[q], sample_word(sm.q_cls[q]), lane, 32);
+        }
+        __syncthreads();
+        // the last byte of the line is '\n' (it replaced the last sample's tab, compress.cpp:865-868)
+        if (tid == 0) {
+            sm.q_n = 0;
+            const long long endp = (long long)o1 - 1 - (long long)T0;
+            if (endp >= 0 && endp < tile_len) sm.stage[endp] = '\n';
+        }
+        __syncthreads();
+    }
+
+    // tile image -> HBM
+    {
+        uint8_t* dst = out + T0;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            const int n16 = tile_len >> 4;
+            const uint4* s4 = reinterpret_cast<const uint4*>(sm.stage);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            for (int i = tid; i < n16; i += kThreads) d4[i] = s4[i];
+            for (int i = (n16 << 4) + tid; i < tile_len; i += kThreads) dst[i] = sm.stage[i];
+        } else {
+            for (int i = tid; i < tile_len; i += kThreads) dst[i] = sm.stage[i];
+        }
+    }
+}
+
+__global__ void k_dec_result(vcfc_result* r, const Ctrl* ctrl, int status, unsigned long long out_len, unsigned long long n_lines) {
+    r->reserved = 0;
+    r->err_line = 0;
+    if (ctrl && ctrl->irregular) { r->status = kStatusIrregular; r->out_len = 0; r->n_lines = 0; }
+    else { r->status = status; r->out_len = out_len; r->n_lines = n_lines; }
+}
+
+}  // namespace dec
+
+int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t sample_count, uint8_t* d_out, size_t out_cap,
+                vcfc_result* d_result, bool size_only, cudaStream_t stream) {
+    using namespace dec;
+    ctx->last_path = kPathFast;
+    if (in_len < 8) {                      // nothing but (at most) a few trailing bytes: clean EOF
+        k_dec_result<<<1, 1, 0, stream>>>(d_result, nullptr, VCFC_OK, 0, 0);
+        ctx->launches++;
+        return VCFC_OK;
+    }
+    if (sample_count == 0 || in_len >= (1ull << 46)) {
+        k_dec_result<<<1, 1, 0, stream>>>(d_result, nullptr, kStatusIrregular, 0, 0);
+        ctx->launches++;
+        return VCFC_OK;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        VCFC_CUDA(ctx, cudaFuncSetAttribute(k_dec_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        attr_set = true;
+    }
+    int rc;
+    const long long n = (long long)in_len, n_seg = (n + kSeg - 1) / kSeg;
+    DevBuf &b_ctrl = ctx->ws[2], &b_seg = ctx->ws[0], &b_scr = ctx->ws[1], &b_ls = ctx->ws[3], &b_sizes = ctx->ws[4],
+           &b_offs = ctx->ws[7], &b_tiles = ctx->ws[5];
+    if ((rc = dev_reserve(ctx, &b_ctrl, sizeof(Ctrl) + 64))) return rc;
+    if ((rc = dev_reserve(ctx, &b_seg, (size_t)n_seg * 8 * 4 + 64))) return rc;
+    Ctrl* ctrl = (Ctrl*)b_ctrl.p;
+    long long* cand = (long long*)b_seg.p;
+    long long* endp = cand + n_seg;
+    unsigned long long* cnt = (unsigned long long*)(endp + n_seg);
+    unsigned long long* base = cnt + n_seg;
+    VCFC_CUDA(ctx, cudaMemsetAsync(ctrl, 0, sizeof(Ctrl), stream));
+    const unsigned gs = (unsigned)((n_seg + 127) / 128);
+    if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeDecodeScan], stream);
+    k_dec_walk<<<gs, 128, 0, stream>>>(d_in, n, n_seg, cand, endp, cnt);
+    k_dec_verify<<<gs, 128, 0, stream>>>(n, n_seg, cand, endp, ctrl, 0);
+    k_dec_repair<<<1, 1, 0, stream>>>(d_in, n, n_seg, cand, endp, cnt, ctrl);
+    k_dec_verify<<<gs, 128, 0, stream>>>(n, n_seg, cand, endp, ctrl, 1);
+    ctx->launches += 4;
+    if ((rc = scan_exclusive_u64(ctx, (const uint64_t*)cnt, (uint64_t*)base, (size_t)n_seg, (uint64_t*)&ctrl->n_lines, &b_scr, stream))) return rc;
+    struct { int irregular, n_fix; unsigned long long n_lines, end_pos, total_out; } h;
+    VCFC_CUDA(ctx, cudaMemcpyAsync(&h, ctrl, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    VCFC_CUDA(ctx, cudaStreamSynchronize(stream));
+    if (h.irregular || h.n_lines == 0 || h.n_lines >= (1ull << 32)) {
+        k_dec_result<<<1, 1, 0, stream>>>(d_result, nullptr, kStatusIrregular, 0, 0);
+        ctx->launches++;
+        return VCFC_OK;
+    }
+    const unsigned long long n_lines = h.n_lines;
+    if ((rc = dev_reserve(ctx, &b_ls, (n_lines + 2) * 8))) return rc;
+    if ((rc = dev_reserve(ctx, &b_sizes, (n_lines + 1) * 8))) return rc;
+    if ((rc = dev_reserve(ctx, &b_offs, (n_lines + 1) * 8))) return rc;
+    unsigned long long* line_start = (unsigned long long*)b_ls.p;
+    k_dec_fill<<<gs, 128, 0, stream>>>(d_in, n, n_seg, cand, base, line_start, n_lines, ctrl);
+    k_dec_sizes<<<(unsigned)((n_lines * 32 + 127) / 128), 128, 0, stream>>>(d_in, line_start, n_lines, sample_count,
+                                                                             (unsigned long long*)b_sizes.p, ctrl);
+    ctx->launches += 2;
+    if ((rc = scan_exclusive_u64(ctx, (uint64_t*)b_sizes.p, (uint64_t*)b_offs.p, (size_t)n_lines, (uint64_t*)&ctrl->total_out, &b_scr, stream)))
+        return rc;
+    if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeDecodeScan + 1], stream); ctx->ev_pending[kTimeDecodeScan] = 1; }
+    VCFC_CUDA(ctx, cudaMemcpyAsync(&h, ctrl, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    VCFC_CUDA(ctx, cudaStreamSynchronize(stream));
+    if (h.irregular) {
+        k_dec_result<<<1, 1, 0, stream>>>(d_result, nullptr, kStatusIrregular, 0, 0);
+        ctx->launches++;
+        return VCFC_OK;
+    }
+    const unsigned long long total = h.total_out;
+    if (size_only || total > out_cap) {
+        k_dec_result<<<1, 1, 0, stream>>>(d_result, nullptr, size_only ? VCFC_OK : VCFC_E_CAP, total, size_only ? n_lines : 0);
+        ctx->launches++;
+        return VCFC_OK;
+    }
+    const unsigned long long n_tiles = (total + kTile - 1) / kTile;
+    if ((rc = dev_reserve(ctx, &b_tiles, n_tiles * 4 + 64))) return rc;
+    k_dec_tilemap<<<(unsigned)((n_lines + 255) / 256), 256, 0, stream>>>((unsigned long long*)b_offs.p, n_lines, total,
+                                                                          (unsigned int*)b_tiles.p);
+    if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeDecodeExpand], stream);
+    k_dec_expand<<<(unsigned)n_tiles, kThreads, sizeof(Smem), stream>>>(d_in, line_start, (unsigned long long*)b_offs.p, n_lines,
+                                                                        total, (unsigned int*)b_tiles.p, d_out, ctrl);
+    if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeDecodeExpand + 1], stream); ctx->ev_pending[kTimeDecodeExpand] = 1; }
+    k_dec_result<<<1, 1, 0, stream>>>(d_result, ctrl, VCFC_OK, total, n_lines);
+    ctx->launches += 3;
     VCFC_CUDA(ctx, cudaGetLastError());
     return VCFC_OK;
 }
-}
+
+}  // namespace vcfc
