@@ -30,8 +30,6 @@ constexpr int kTile = 16384;            // D4 output tile
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kCmax = 24576;            // longest compressed line the tile kernel parses from smem
-constexpr int kLongRun = 12;            // runs of >= this many samples are expanded by a whole warp
-constexpr int kQueue = 1024;
 constexpr long long kNoCand = -1, kBroken = -2;
 
 constexpr int kMaxFix = 1024;
@@ -285,38 +283,22 @@ __global__ void k_dec_tilemap(const unsigned long long* __restrict__ off, unsign
 }
 
 // ---- D4: expansion, one CTA per output tile --------------------------------------------------------------------
+// Every thread produces one contiguous 64-byte span of the tile image, so the work is balanced whatever the
+// token mix.  Per line that overlaps the tile: (1) the compressed line is staged in smem, (2) a chunk table
+// (text offset + token/payload state at every 16th compressed byte) is built with one block scan, (3) each
+// thread binary-searches the table for its span, walks to the token that covers it and generates its bytes.
+constexpr int kSpan = kTile / kThreads;     // 64
+constexpr int kChunks = kCmax / 16 + 2;
+
 struct Smem {
     alignas(16) uint8_t stage[kTile];
     alignas(16) uint8_t cbuf[kCmax + 16];
-    int q_pos[kQueue];
-    unsigned short q_cnt[kQueue];
-    unsigned char q_cls[kQueue];
-    int q_n;
+    unsigned ctab[kChunks];                  // (text offset at chunk start) << 1 | payload state
     int warp_kind[kWarps];
     unsigned warp_out[kWarps];
     int carry_kind;
     unsigned carry_out;
 };
-
-// writes n copies of the 4-byte sample word w ("x|y\t") to text positions pos .. pos + 4n - 1 of the tile image
-__device__ __forceinline__ void put_run(uint8_t* stage, int tile_len, int pos, int n, uint32_t w, int lane0, int stride) {
-    // text byte (pos + j) = byte (j & 3) of w.  Aligned words of the image hold w rotated by ((-pos) & 3) bytes.
-    const int end = pos + 4 * n;
-    int a = pos < 0 ? 0 : pos, z = end > tile_len ? tile_len : end;
-    if (a >= z) return;
-    const int a4 = (a + 3) & ~3, z4 = z & ~3;
-    if (a4 >= z4) {
-        for (int i = a + lane0; i < z; i += stride) stage[i] = (uint8_t)(w >> (8 * ((i - pos) & 3)));
-        return;
-    }
-    if (lane0 == 0) {
-        for (int i = a; i < a4; i++) stage[i] = (uint8_t)(w >> (8 * ((i - pos) & 3)));
-        for (int i = z4; i < z; i++) stage[i] = (uint8_t)(w >> (8 * ((i - pos) & 3)));
-    }
-    const uint32_t rw = __funnelshift_r(w, w, 8 * ((a4 - pos) & 3));
-    uint32_t* sw = reinterpret_cast<uint32_t*>(stage);
-    for (int i = (a4 >> 2) + lane0; i < (z4 >> 2); i += stride) sw[i] = rw;
-}
 
 __device__ __forceinline__ uint32_t sample_word(uint32_t tok) {      // token byte -> "x|y\t" little-endian
     uint32_t a = '0', b = '0';
@@ -326,6 +308,18 @@ __device__ __forceinline__ uint32_t sample_word(uint32_t tok) {      // token by
         b = f == kTok10 ? '0' : '1';
     }
     return a | ((uint32_t)'|' << 8) | (b << 16) | ((uint32_t)'\t' << 24);
+}
+
+// text bytes [lo, hi) of a run whose first byte has text offset `cur`, to stage[sp ..]
+__device__ __forceinline__ void put_pattern(uint8_t* __restrict__ stage, int sp, int lo, int hi, int cur, uint32_t w) {
+    int n = hi - lo, ph = (lo - cur) & 3;
+    while (n > 0 && (sp & 3)) { stage[sp++] = (uint8_t)(w >> (8 * ph)); ph = (ph + 1) & 3; n--; }
+    const uint32_t rw = __funnelshift_r(w, w, 8 * ph);
+    uint32_t* sw = reinterpret_cast<uint32_t*>(stage + sp);
+    const int nw = n >> 2;
+    for (int i = 0; i < nw; i++) sw[i] = rw;
+    sp += 4 * nw; n -= 4 * nw;
+    while (n > 0) { stage[sp++] = (uint8_t)(w >> (8 * ph)); ph = (ph + 1) & 3; n--; }
 }
 
 __global__ void __launch_bounds__(kThreads, 4)
@@ -338,18 +332,17 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long T0 = (unsigned long long)blockIdx.x * kTile;
     const int tile_len = (int)(total - T0 < (unsigned long long)kTile ? total - T0 : (unsigned long long)kTile);
-    unsigned long long k = first_line[blockIdx.x];
-    if (tid == 0) sm.q_n = 0;
-    __syncthreads();
+    const int s_lo = tid * kSpan, s_hi = min(s_lo + kSpan, tile_len);   // this thread's span of the tile image
 
-    for (; k < n_lines; k++) {
+    for (unsigned long long k = first_line[blockIdx.x]; k < n_lines; k++) {
         const unsigned long long o0 = off[k], o1 = k + 1 < n_lines ? off[k + 1] : total;
         if (o0 >= T0 + (unsigned long long)tile_len) break;
         if (o1 == o0) continue;
         const int lpos = (int)((long long)o0 - (long long)T0);      // line's first text byte relative to the tile (may be < 0)
+        const int lend = (int)min((long long)o1 - (long long)T0, (long long)tile_len);   // end of its text inside the tile
         const unsigned long long ls = line_start[k];
         const int clen = (int)(line_start[k + 1] - ls);
-        // stage the compressed line: 4-byte loads where the source allows
+        // (1) stage the compressed line: 4-byte loads where the source allows
         {
             const uint8_t* src = in + ls;
             const int mis = (int)((4 - (reinterpret_cast<uintptr_t>(src) & 3)) & 3);
@@ -368,13 +361,9 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
         }
         __syncthreads();
         const int rq = (int)hdr_len(sm.cbuf + 4);
-        // required section passes through (compress.cpp:788-807)
-        for (int i = tid; i < rq; i += kThreads) {
-            const int t = lpos + i;
-            if (t >= 0 && t < tile_len) sm.stage[t] = sm.cbuf[8 + i];
-        }
-        const int tb = 8 + rq, tn = clen - tb;
-        const int tpos = lpos + rq;                                   // text position of the first sample
+        const int tb = 8 + rq, tn = clen - tb;                        // token region (its last byte is the line's '\n')
+        const int tpos = lpos + rq;                                   // tile position of the first sample's text
+        // (2) chunk table
         for (int base = 0; base < tn; base += 16 * kThreads) {
             const int offc = base + 16 * tid;
             int nb = tn - offc;
@@ -392,11 +381,9 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
             int k_in = sm.carry_kind;
             for (int w = 0; w < warp; w++) if (sm.warp_kind[w]) k_in = sm.warp_kind[w];
             if (below) k_in = k_src;
-            const bool is_last = nb > 0 && offc + nb == tn;
             unsigned o, ns;
             int e;
-            chunk_measure(b, nb, k_in == 1, is_last, &o, &ns, &e);
-            // exclusive scan of text lengths over the CTA
+            chunk_measure(b, nb, k_in == 1, nb > 0 && offc + nb == tn, &o, &ns, &e);
             unsigned inc = o;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
@@ -404,37 +391,7 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
             __syncthreads();
             unsigned pre = sm.carry_out;
             for (int w = 0; w < warp; w++) pre += sm.warp_out[w];
-            int pos = tpos + (int)(pre + inc - o);
-            // write this chunk's text
-            bool payload = k_in == 1;
-            if (pos < tile_len && pos + (int)o > 0) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const uint32_t c = b[i];
-                    const bool line_end = is_last && i == nb - 1;
-                    if (i >= nb) {
-                    } else if (payload) {
-                        if (pos >= 0 && pos < tile_len) sm.stage[pos] = (uint8_t)c;
-                        pos++;
-                        if (c == 9u || c == 10u) payload = false;
-                    } else if (line_end) {
-                    } else if (c < 0xE0u) {
-                        const int n = (int)(c < 0x80u ? c : (c & 0x1Fu));
-                        if (n >= kLongRun) {
-                            if (pos < tile_len && pos + 4 * n > 0) {
-                                const int slot = atomicAdd(&sm.q_n, 1);
-                                if (slot < kQueue) { sm.q_pos[slot] = pos; sm.q_cnt[slot] = (unsigned short)n; sm.q_cls[slot] = (unsigned char)c; }
-                                else put_run(sm.stage, tile_len, pos, n, sample_word(c), 0, 1);
-                            }
-                        } else {
-                            put_run(sm.stage, tile_len, pos, n, sample_word(c), 0, 1);
-                        }
-                        pos += 4 * n;
-                    } else {
-                        payload = true;
-                    }
-                }
-            }
+            if (nb > 0) sm.ctab[offc >> 4] = ((pre + inc - o) << 1) | (k_in == 1 ? 1u : 0u);
             __syncthreads();
             if (tid == kThreads - 1) {
                 sm.carry_out = pre + inc;
@@ -444,18 +401,43 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
             }
             __syncthreads();
         }
-        // long runs, one warp per run
-        {
-            const int qn = sm.q_n < kQueue ? sm.q_n : kQueue;
-            for (int q = warp; q < qn; q += kWarps)
-                put_run(sm.stage, tile_len, sm.q_pos[q], (int)sm.q_cnt[q], sample_word(sm.q_cls[q]), lane, 32);
-        }
-        __syncthreads();
-        // the last byte of the line is '\n' (it replaced the last sample's tab, compress.cpp:865-868)
-        if (tid == 0) {
-            sm.q_n = 0;
+        // (3) generate this thread's part of the line: tile positions [g_lo, g_hi)
+        const int g_lo = max(s_lo, max(lpos, 0)), g_hi = min(s_hi, lend);
+        if (g_lo < g_hi) {
+            int sp = g_lo;
+            // required section passes through (compress.cpp:788-807)
+            for (; sp < g_hi && sp < tpos; sp++) sm.stage[sp] = sm.cbuf[8 + (sp - lpos)];
+            if (sp < g_hi) {
+                int x = sp - tpos;                                    // text offset inside the sample text
+                const int x_end = g_hi - tpos;
+                // chunk whose start offset is the last one <= x
+                int lo = 0, hi = (tn + 15) >> 4;
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)(sm.ctab[mid] >> 1) <= x) lo = mid; else hi = mid; }
+                int ci = lo << 4, cur = (int)(sm.ctab[lo] >> 1);
+                bool payload = (sm.ctab[lo] & 1u) != 0;
+                while (x < x_end) {
+                    const uint32_t c = sm.cbuf[tb + ci];
+                    if (payload) {
+                        if (cur == x) { sm.stage[sp++] = (uint8_t)c; x++; }
+                        cur++; ci++;
+                        if (c == 9u || c == 10u) payload = false;
+                    } else if (c >= 0xE0u) {
+                        payload = true; ci++;
+                    } else {
+                        const int len = 4 * (int)(c < 0x80u ? c : (c & 0x1Fu));
+                        if (cur + len > x) {
+                            const int stop = min(cur + len, x_end);
+                            put_pattern(sm.stage, sp, x, stop, cur, sample_word(c));
+                            sp += stop - x; x = stop;
+                            if (stop < cur + len) break;
+                        }
+                        cur += len; ci++;
+                    }
+                }
+            }
+            // the line's last text byte is '\n' (it replaces the last sample's tab, compress.cpp:865-868)
             const long long endp = (long long)o1 - 1 - (long long)T0;
-            if (endp >= 0 && endp < tile_len) sm.stage[endp] = '\n';
+            if (endp >= g_lo && endp < g_hi) sm.stage[endp] = '\n';
         }
         __syncthreads();
     }
