@@ -284,20 +284,24 @@ __global__ void k_dec_tilemap(const unsigned long long* __restrict__ off, unsign
 
 // ---- D4: expansion, one CTA per output tile --------------------------------------------------------------------
 // Every thread produces one contiguous 64-byte span of the tile image, so the work is balanced whatever the
-// token mix.  Per line that overlaps the tile: (1) the compressed line is staged in smem, (2) a chunk table
-// (text offset + token/payload state at every 16th compressed byte) is built with one block scan, (3) each
+// token mix.  Per batch of lines that overlap the tile: (1) warp 0 reads the line table entries, (2) the lines'
+// compressed bytes (contiguous in the block) are staged in smem with 16-byte copies, (3) one warp per line builds
+// a chunk table (text offset + token/payload state at every 16th token byte) with warp scans only, (4) each
 // thread binary-searches the table for its span, walks to the token that covers it and generates its bytes.
 constexpr int kSpan = kTile / kThreads;     // 64
-constexpr int kChunks = kCmax / 16 + 2;
+constexpr int kChunks = kCmax / 16 + 2 * 32;
+constexpr int kMaxL = 31;                   // lines per batch
 
 struct Smem {
     alignas(16) uint8_t stage[kTile];
-    alignas(16) uint8_t cbuf[kCmax + 16];
+    alignas(16) uint8_t cbuf[kCmax + 32];
     unsigned ctab[kChunks];                  // (text offset at chunk start) << 1 | payload state
-    int warp_kind[kWarps];
-    unsigned warp_out[kWarps];
-    int carry_kind;
-    unsigned carry_out;
+    int l_pos[kMaxL + 1];                    // tile position of the line's first text byte (may be < 0)
+    int l_end[kMaxL + 1];                    // tile position one past its last text byte, clipped to the tile
+    int l_last[kMaxL + 1];                   // tile position of its final '\n' (may lie outside the tile)
+    int l_coff[kMaxL + 2];                   // offset of its compressed bytes in cbuf
+    int l_ctab[kMaxL + 1];                   // its first chunk table slot
+    int n_batch, more;
 };
 
 __device__ __forceinline__ uint32_t sample_word(uint32_t tok) {      // token byte -> "x|y\t" little-endian
@@ -315,10 +319,10 @@ __device__ __forceinline__ void put_pattern(uint8_t* __restrict__ stage, int sp,
     int n = hi - lo, ph = (lo - cur) & 3;
     while (n > 0 && (sp & 3)) { stage[sp++] = (uint8_t)(w >> (8 * ph)); ph = (ph + 1) & 3; n--; }
     const uint32_t rw = __funnelshift_r(w, w, 8 * ph);
-    uint32_t* sw = reinterpret_cast<uint32_t*>(stage + sp);
-    const int nw = n >> 2;
-    for (int i = 0; i < nw; i++) sw[i] = rw;
-    sp += 4 * nw; n -= 4 * nw;
+    while (n >= 4 && (sp & 15)) { *reinterpret_cast<uint32_t*>(stage + sp) = rw; sp += 4; n -= 4; }
+    const uint4 rw4 = make_uint4(rw, rw, rw, rw);
+    while (n >= 16) { *reinterpret_cast<uint4*>(stage + sp) = rw4; sp += 16; n -= 16; }
+    while (n >= 4) { *reinterpret_cast<uint32_t*>(stage + sp) = rw; sp += 4; n -= 4; }
     while (n > 0) { stage[sp++] = (uint8_t)(w >> (8 * ph)); ph = (ph + 1) & 3; n--; }
 }
 
@@ -332,91 +336,133 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long T0 = (unsigned long long)blockIdx.x * kTile;
     const int tile_len = (int)(total - T0 < (unsigned long long)kTile ? total - T0 : (unsigned long long)kTile);
+    const unsigned long long T1 = T0 + (unsigned long long)tile_len;
     const int s_lo = tid * kSpan, s_hi = min(s_lo + kSpan, tile_len);   // this thread's span of the tile image
+    unsigned long long k0 = first_line[blockIdx.x];
 
-    for (unsigned long long k = first_line[blockIdx.x]; k < n_lines; k++) {
-        const unsigned long long o0 = off[k], o1 = k + 1 < n_lines ? off[k + 1] : total;
-        if (o0 >= T0 + (unsigned long long)tile_len) break;
-        if (o1 == o0) continue;
-        const int lpos = (int)((long long)o0 - (long long)T0);      // line's first text byte relative to the tile (may be < 0)
-        const int lend = (int)min((long long)o1 - (long long)T0, (long long)tile_len);   // end of its text inside the tile
-        const unsigned long long ls = line_start[k];
-        const int clen = (int)(line_start[k + 1] - ls);
-        // (1) stage the compressed line: 4-byte loads where the source allows
-        {
-            const uint8_t* src = in + ls;
-            const int mis = (int)((4 - (reinterpret_cast<uintptr_t>(src) & 3)) & 3);
-            const int head = mis < clen ? mis : clen;
-            if (tid < head) sm.cbuf[tid] = src[tid];
-            const int nw = (clen - head) >> 2;
-            const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src + head);
-            for (int i = tid; i < nw; i += kThreads) {
-                uint32_t v = s4[i];
-                uint8_t* d = sm.cbuf + head + 4 * i;
-                d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
+    for (;;) {
+        // (1) line table entries of the next batch: lines k0 .. k0 + nb - 1 overlap the tile
+        unsigned long long c_lo = 0;
+        if (warp == 0) {
+            const unsigned long long kk = k0 + (unsigned long long)lane;
+            const unsigned long long o = kk < n_lines ? off[kk] : total;
+            const unsigned long long ls = kk <= n_lines ? line_start[kk] : 0ull;
+            c_lo = __shfl_sync(0xffffffffu, ls, 0);
+            const bool overlaps = kk < n_lines && o < T1;
+            unsigned m = __ballot_sync(0xffffffffu, overlaps) & 0x7fffffffu;         // lane 31 only supplies the end of line 30
+            int nb = __popc(m);                                                        // off[] is monotone: a prefix of the lanes
+            // the batch's compressed bytes must fit in cbuf (a single line always does, k_dec_sizes checked it)
+            const unsigned fits = __ballot_sync(0xffffffffu, ls - c_lo <= (unsigned long long)kCmax);
+            while (nb > 1 && !((fits >> nb) & 1u)) nb--;
+            const unsigned long long o_next = __shfl_down_sync(0xffffffffu, o, 1);
+            const unsigned long long ls_next = __shfl_down_sync(0xffffffffu, ls, 1);
+            if (lane < nb) {
+                sm.l_pos[lane] = (int)((long long)o - (long long)T0);
+                sm.l_end[lane] = (int)(o_next < T1 ? o_next - T0 : (unsigned long long)tile_len);
+                sm.l_last[lane] = (int)min((long long)o_next - 1 - (long long)T0, (long long)(1 << 30));
+                sm.l_coff[lane] = (int)(ls - c_lo);
+                if (lane == nb - 1) sm.l_coff[nb] = (int)(ls_next - c_lo);
             }
-            const int t0 = head + 4 * nw;
-            if (tid < clen - t0) sm.cbuf[t0 + tid] = src[t0 + tid];
-            if (tid == 0) { sm.carry_kind = 0; sm.carry_out = 0; }
+            const unsigned long long o_after = __shfl_sync(0xffffffffu, o, nb);       // nb <= 31
+            if (lane == 0) {
+                sm.n_batch = nb;
+                sm.more = (nb > 0 && k0 + (unsigned long long)nb < n_lines && o_after < T1) ? 1 : 0;   // another batch follows
+            }
         }
         __syncthreads();
-        const int rq = (int)hdr_len(sm.cbuf + 4);
-        const int tb = 8 + rq, tn = clen - tb;                        // token region (its last byte is the line's '\n')
-        const int tpos = lpos + rq;                                   // tile position of the first sample's text
-        // (2) chunk table
-        for (int base = 0; base < tn; base += 16 * kThreads) {
-            const int offc = base + 16 * tid;
-            int nb = tn - offc;
-            nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-            uint8_t b[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) b[i] = i < nb ? sm.cbuf[tb + offc + i] : 0;
-            const int kind = last_setter_kind(b, nb);
-            const unsigned has = __ballot_sync(0xffffffffu, kind != 0);
-            const unsigned below = has & ((1u << lane) - 1u);
-            const int k_src = __shfl_sync(0xffffffffu, kind, below ? 31 - __clz(below) : 0);
-            const int warp_last = has ? __shfl_sync(0xffffffffu, kind, 31 - __clz(has)) : 0;
-            if (lane == 0) sm.warp_kind[warp] = warp_last;
-            __syncthreads();
-            int k_in = sm.carry_kind;
-            for (int w = 0; w < warp; w++) if (sm.warp_kind[w]) k_in = sm.warp_kind[w];
-            if (below) k_in = k_src;
-            unsigned o, ns;
-            int e;
-            chunk_measure(b, nb, k_in == 1, nb > 0 && offc + nb == tn, &o, &ns, &e);
-            unsigned inc = o;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-            if (lane == 31) sm.warp_out[warp] = inc;
-            __syncthreads();
-            unsigned pre = sm.carry_out;
-            for (int w = 0; w < warp; w++) pre += sm.warp_out[w];
-            if (nb > 0) sm.ctab[offc >> 4] = ((pre + inc - o) << 1) | (k_in == 1 ? 1u : 0u);
-            __syncthreads();
-            if (tid == kThreads - 1) {
-                sm.carry_out = pre + inc;
-                int kk = sm.carry_kind;
-                for (int w = 0; w < kWarps; w++) if (sm.warp_kind[w]) kk = sm.warp_kind[w];
-                sm.carry_kind = kk;
-            }
-            __syncthreads();
+        const int nb = sm.n_batch;
+        if (nb == 0) break;
+        c_lo = line_start[k0];
+        // (2) stage the batch's compressed bytes; cbuf keeps the source's 16-byte phase so both sides are aligned
+        const int phase = (int)(reinterpret_cast<uintptr_t>(in + c_lo) & 15);
+        {
+            const int clen = sm.l_coff[nb];
+            const uint8_t* src = in + c_lo;
+            const int head = min((16 - phase) & 15, clen);
+            if (tid < head) sm.cbuf[phase + tid] = src[tid];
+            const int n16 = (clen - head) >> 4;
+            const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+            uint4* d4 = reinterpret_cast<uint4*>(sm.cbuf + phase + head);
+            for (int i = tid; i < n16; i += kThreads) d4[i] = s4[i];
+            const int t0 = head + 16 * n16;
+            if (tid < clen - t0) sm.cbuf[phase + t0 + tid] = src[t0 + tid];
         }
-        // (3) generate this thread's part of the line: tile positions [g_lo, g_hi)
-        const int g_lo = max(s_lo, max(lpos, 0)), g_hi = min(s_hi, lend);
-        if (g_lo < g_hi) {
+        __syncthreads();
+        // chunk table slots per line (tiny: nb <= 31)
+        if (warp == 0) {
+            int nch = 0;
+            if (lane < nb) {
+                const uint8_t* lp = sm.cbuf + phase + sm.l_coff[lane];
+                const int rq = (int)hdr_len(lp + 4);
+                nch = ((sm.l_coff[lane + 1] - sm.l_coff[lane]) - 8 - rq + 15) >> 4;
+            }
+            int inc = nch;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            if (lane < nb) sm.l_ctab[lane] = inc - nch;
+        }
+        __syncthreads();
+        // (3) chunk tables, one warp per line, warp scans only
+        for (int li = warp; li < nb; li += kWarps) {
+            const uint8_t* lp = sm.cbuf + phase + sm.l_coff[li];
+            const int clen = sm.l_coff[li + 1] - sm.l_coff[li];
+            const int rq = (int)hdr_len(lp + 4);
+            const int tb = 8 + rq, tn = clen - tb;
+            unsigned* tab = sm.ctab + sm.l_ctab[li];
+            int carry_kind = 0;
+            unsigned carry_out = 0;
+            for (int base = 0; base < tn; base += 512) {
+                const int offc = base + 16 * lane;
+                int nbytes = tn - offc;
+                nbytes = nbytes < 0 ? 0 : (nbytes > 16 ? 16 : nbytes);
+                uint8_t b[16];
+                int kind = 0;
+                if (nbytes > 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) b[i] = i < nbytes ? lp[tb + offc + i] : 0;
+                    kind = last_setter_kind(b, nbytes);
+                }
+                const unsigned has = __ballot_sync(0xffffffffu, kind != 0);
+                const unsigned below = has & ((1u << lane) - 1u);
+                const int k_src = __shfl_sync(0xffffffffu, kind, below ? 31 - __clz(below) : 0);
+                const int k_in = below ? k_src : carry_kind;
+                unsigned o = 0, ns = 0;
+                int e = 0;
+                if (nbytes > 0) chunk_measure(b, nbytes, k_in == 1, offc + nbytes == tn, &o, &ns, &e);
+                unsigned inc = o;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+                if (nbytes > 0) tab[offc >> 4] = ((carry_out + inc - o) << 1) | (k_in == 1 ? 1u : 0u);
+                carry_out += __shfl_sync(0xffffffffu, inc, 31);
+                if (has) carry_kind = __shfl_sync(0xffffffffu, kind, 31 - __clz(has));
+            }
+        }
+        __syncthreads();
+        // (4) generate: the lines of the batch that intersect this thread's span
+        for (int li = 0; li < nb; li++) {
+            const int lpos = sm.l_pos[li], lend = sm.l_end[li];
+            if (lend <= s_lo) continue;
+            if (lpos >= s_hi) break;
+            const int g_lo = max(s_lo, max(lpos, 0)), g_hi = min(s_hi, lend);
+            if (g_lo >= g_hi) continue;
+            const uint8_t* lp = sm.cbuf + phase + sm.l_coff[li];
+            const int clen = sm.l_coff[li + 1] - sm.l_coff[li];
+            const int rq = (int)hdr_len(lp + 4);
+            const int tb = 8 + rq, tn = clen - tb;
+            const int tpos = lpos + rq;                               // tile position of the first sample's text
             int sp = g_lo;
             // required section passes through (compress.cpp:788-807)
-            for (; sp < g_hi && sp < tpos; sp++) sm.stage[sp] = sm.cbuf[8 + (sp - lpos)];
+            for (; sp < g_hi && sp < tpos; sp++) sm.stage[sp] = lp[8 + (sp - lpos)];
             if (sp < g_hi) {
+                const unsigned* tab = sm.ctab + sm.l_ctab[li];
                 int x = sp - tpos;                                    // text offset inside the sample text
                 const int x_end = g_hi - tpos;
-                // chunk whose start offset is the last one <= x
-                int lo = 0, hi = (tn + 15) >> 4;
-                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)(sm.ctab[mid] >> 1) <= x) lo = mid; else hi = mid; }
-                int ci = lo << 4, cur = (int)(sm.ctab[lo] >> 1);
-                bool payload = (sm.ctab[lo] & 1u) != 0;
+                int lo = 0, hi = (tn + 15) >> 4;                      // chunk whose start offset is the last one <= x
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)(tab[mid] >> 1) <= x) lo = mid; else hi = mid; }
+                int ci = lo << 4, cur = (int)(tab[lo] >> 1);
+                bool payload = (tab[lo] & 1u) != 0;
                 while (x < x_end) {
-                    const uint32_t c = sm.cbuf[tb + ci];
+                    const uint32_t c = lp[tb + ci];
                     if (payload) {
                         if (cur == x) { sm.stage[sp++] = (uint8_t)c; x++; }
                         cur++; ci++;
@@ -436,10 +482,13 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
                 }
             }
             // the line's last text byte is '\n' (it replaces the last sample's tab, compress.cpp:865-868)
-            const long long endp = (long long)o1 - 1 - (long long)T0;
+            const int endp = sm.l_last[li];
             if (endp >= g_lo && endp < g_hi) sm.stage[endp] = '\n';
         }
+        const int more = sm.more;
         __syncthreads();
+        if (!more) break;
+        k0 += (unsigned long long)nb;
     }
 
     // tile image -> HBM
