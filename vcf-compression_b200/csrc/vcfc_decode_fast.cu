@@ -314,17 +314,33 @@ __device__ __forceinline__ uint32_t sample_word(uint32_t tok) {      // token by
     return a | ((uint32_t)'|' << 8) | (b << 16) | ((uint32_t)'\t' << 24);
 }
 
-// text bytes [lo, hi) of a run whose first byte has text offset `cur`, to stage[sp ..]
-__device__ __forceinline__ void put_pattern(uint8_t* __restrict__ stage, int sp, int lo, int hi, int cur, uint32_t w) {
-    int n = hi - lo, ph = (lo - cur) & 3;
-    while (n > 0 && (sp & 3)) { stage[sp++] = (uint8_t)(w >> (8 * ph)); ph = (ph + 1) & 3; n--; }
-    const uint32_t rw = __funnelshift_r(w, w, 8 * ph);
-    while (n >= 4 && (sp & 15)) { *reinterpret_cast<uint32_t*>(stage + sp) = rw; sp += 4; n -= 4; }
-    const uint4 rw4 = make_uint4(rw, rw, rw, rw);
-    while (n >= 16) { *reinterpret_cast<uint4*>(stage + sp) = rw4; sp += 16; n -= 16; }
-    while (n >= 4) { *reinterpret_cast<uint32_t*>(stage + sp) = rw; sp += 4; n -= 4; }
-    while (n > 0) { stage[sp++] = (uint8_t)(w >> (8 * ph)); ph = (ph + 1) & 3; n--; }
-}
+// Sequential writer for one thread's span of the tile image: bytes are collected in a register and stored as
+// aligned 32-bit words (a sample is 4 bytes but starts at any byte offset, so byte stores would cost 4x more).
+struct Writer {
+    uint32_t* wp;          // next word of the image
+    uint32_t acc;          // pending bytes, low byte first
+    int fill;              // number of pending bytes, 0..3
+    __device__ __forceinline__ void byte(uint32_t c) {
+        acc |= c << (8 * fill);
+        if (++fill == 4) { *wp++ = acc; acc = 0; fill = 0; }
+    }
+    // n bytes of the periodic stream w[ph], w[ph+1], ... (w = 4-byte sample word)
+    __device__ __forceinline__ void run(uint32_t w, int ph, int n) {
+        const uint32_t P = __funnelshift_r(w, w, 8 * ph);              // stream bytes 0..3
+        const int tot = fill + n, nw = tot >> 2, rem = tot & 3;
+        if (nw == 0) { acc |= (P & ((1u << (8 * n)) - 1u)) << (8 * fill); fill = tot; return; }
+        *wp++ = acc | (P << (8 * fill));
+        const uint32_t Q = __funnelshift_r(P, P, 8 * ((4 - fill) & 3));  // the stream, re-aligned to image words
+        for (int i = 1; i < nw; i++) *wp++ = Q;
+        acc = rem ? (Q & ((1u << (8 * rem)) - 1u)) : 0u;
+        fill = rem;
+    }
+    __device__ __forceinline__ void flush_tail() {                     // only the image's last, partial word
+        uint8_t* bp = reinterpret_cast<uint8_t*>(wp);
+        for (int i = 0; i < fill; i++) bp[i] = (uint8_t)(acc >> (8 * i));
+        fill = 0; acc = 0;
+    }
+};
 
 __global__ void __launch_bounds__(kThreads, 4)
 k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ line_start,
@@ -339,6 +355,10 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
     const unsigned long long T1 = T0 + (unsigned long long)tile_len;
     const int s_lo = tid * kSpan, s_hi = min(s_lo + kSpan, tile_len);   // this thread's span of the tile image
     unsigned long long k0 = first_line[blockIdx.x];
+    Writer wr;
+    wr.wp = reinterpret_cast<uint32_t*>(sm.stage + s_lo);
+    wr.acc = 0;
+    wr.fill = 0;
 
     for (;;) {
         // (1) line table entries of the next batch: lines k0 .. k0 + nb - 1 overlap the tile
@@ -438,7 +458,7 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
             }
         }
         __syncthreads();
-        // (4) generate: the lines of the batch that intersect this thread's span
+        // (4) generate: the lines of the batch that intersect this thread's span, strictly left to right
         for (int li = 0; li < nb; li++) {
             const int lpos = sm.l_pos[li], lend = sm.l_end[li];
             if (lend <= s_lo) continue;
@@ -452,11 +472,12 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
             const int tpos = lpos + rq;                               // tile position of the first sample's text
             int sp = g_lo;
             // required section passes through (compress.cpp:788-807)
-            for (; sp < g_hi && sp < tpos; sp++) sm.stage[sp] = lp[8 + (sp - lpos)];
+            for (; sp < g_hi && sp < tpos; sp++) wr.byte(lp[8 + (sp - lpos)]);
             if (sp < g_hi) {
                 const unsigned* tab = sm.ctab + sm.l_ctab[li];
                 int x = sp - tpos;                                    // text offset inside the sample text
                 const int x_end = g_hi - tpos;
+                const int x_nl = sm.l_last[li] - tpos;                // the line's last text byte: '\n' instead of the tab
                 int lo = 0, hi = (tn + 15) >> 4;                      // chunk whose start offset is the last one <= x
                 while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)(tab[mid] >> 1) <= x) lo = mid; else hi = mid; }
                 int ci = lo << 4, cur = (int)(tab[lo] >> 1);
@@ -464,7 +485,7 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
                 while (x < x_end) {
                     const uint32_t c = lp[tb + ci];
                     if (payload) {
-                        if (cur == x) { sm.stage[sp++] = (uint8_t)c; x++; }
+                        if (cur == x) { wr.byte(c); x++; }
                         cur++; ci++;
                         if (c == 9u || c == 10u) payload = false;
                     } else if (c >= 0xE0u) {
@@ -473,17 +494,16 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
                         const int len = 4 * (int)(c < 0x80u ? c : (c & 0x1Fu));
                         if (cur + len > x) {
                             const int stop = min(cur + len, x_end);
-                            put_pattern(sm.stage, sp, x, stop, cur, sample_word(c));
-                            sp += stop - x; x = stop;
+                            const bool nl = stop > x_nl;               // this run carries the line's final byte
+                            wr.run(sample_word(c), (x - cur) & 3, stop - x - (nl ? 1 : 0));
+                            if (nl) wr.byte('\n');
+                            x = stop;
                             if (stop < cur + len) break;
                         }
                         cur += len; ci++;
                     }
                 }
             }
-            // the line's last text byte is '\n' (it replaces the last sample's tab, compress.cpp:865-868)
-            const int endp = sm.l_last[li];
-            if (endp >= g_lo && endp < g_hi) sm.stage[endp] = '\n';
         }
         const int more = sm.more;
         __syncthreads();
@@ -491,6 +511,8 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
         k0 += (unsigned long long)nb;
     }
 
+    if (wr.fill) wr.flush_tail();
+    __syncthreads();
     // tile image -> HBM
     {
         uint8_t* dst = out + T0;
