@@ -218,7 +218,7 @@ __device__ __forceinline__ void chunk_measure(const uint8_t* b, int nb, bool pay
 // ---- D2: per-line validation and text size (one warp per line) ----------------------------------------------
 __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ line_start,
                             unsigned long long n_lines, unsigned long long sample_count, unsigned long long* __restrict__ sizes,
-                            Ctrl* __restrict__ ctrl) {
+                            unsigned* __restrict__ ctab, Ctrl* __restrict__ ctrl) {
     const unsigned long long k = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (k >= n_lines) return;
@@ -256,10 +256,17 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
             int e;
             chunk_measure(b, nb, k_in == 1, off + nb == tn && nb > 0, &o, &ns, &e);
             err_any |= e;
-            unsigned long long o64 = o, n64 = ns;
+            // chunk table (text offset << 1 | payload state at the chunk's first byte), consumed by k_dec_expand;
+            // line k owns the slots [(ls >> 4) + k, ...): disjoint between lines, <= clen / 16 + 1 of them
+            unsigned inc = o, n32 = ns;
 #pragma unroll
-            for (int d = 16; d; d >>= 1) { o64 += __shfl_xor_sync(0xffffffffu, o64, d); n64 += __shfl_xor_sync(0xffffffffu, n64, d); }
-            total += o64; ns_total += n64;
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned t = __shfl_up_sync(0xffffffffu, inc, d), u = __shfl_up_sync(0xffffffffu, n32, d);
+                if (lane >= d) { inc += t; n32 += u; }
+            }
+            if (nb > 0) ctab[(ls >> 4) + k + (unsigned long long)(off >> 4)] = (((unsigned)total + inc - o) << 1) | (k_in == 1 ? 1u : 0u);
+            total += __shfl_sync(0xffffffffu, inc, 31);
+            ns_total += __shfl_sync(0xffffffffu, n32, 31);
             if (has) carry_kind = __shfl_sync(0xffffffffu, kind, 31 - __clz(has));
         }
         err_any = __any_sync(0xffffffffu, err_any);
@@ -331,7 +338,11 @@ struct Writer {
         if (nw == 0) { acc |= (P & ((1u << (8 * n)) - 1u)) << (8 * fill); fill = tot; return; }
         *wp++ = acc | (P << (8 * fill));
         const uint32_t Q = __funnelshift_r(P, P, 8 * ((4 - fill) & 3));  // the stream, re-aligned to image words
-        for (int i = 1; i < nw; i++) *wp++ = Q;
+        int m = nw - 1;
+        while (m > 0 && (reinterpret_cast<uintptr_t>(wp) & 15)) { *wp++ = Q; m--; }
+        const uint4 Q4 = make_uint4(Q, Q, Q, Q);
+        while (m >= 4) { *reinterpret_cast<uint4*>(wp) = Q4; wp += 4; m -= 4; }
+        while (m > 0) { *wp++ = Q; m--; }
         acc = rem ? (Q & ((1u << (8 * rem)) - 1u)) : 0u;
         fill = rem;
     }
@@ -345,7 +356,8 @@ struct Writer {
 __global__ void __launch_bounds__(kThreads, 4)
 k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ line_start,
              const unsigned long long* __restrict__ off, unsigned long long n_lines, unsigned long long total,
-             const unsigned int* __restrict__ first_line, uint8_t* __restrict__ out, const Ctrl* __restrict__ ctrl) {
+             const unsigned int* __restrict__ first_line, const unsigned* __restrict__ gtab, uint8_t* __restrict__ out,
+             const Ctrl* __restrict__ ctrl) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     if (ctrl->irregular) return;
@@ -422,40 +434,15 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
             if (lane < nb) sm.l_ctab[lane] = inc - nch;
         }
         __syncthreads();
-        // (3) chunk tables, one warp per line, warp scans only
+        // (3) chunk tables of the batch's lines, built once per line by k_dec_sizes: copy them in
         for (int li = warp; li < nb; li += kWarps) {
             const uint8_t* lp = sm.cbuf + phase + sm.l_coff[li];
             const int clen = sm.l_coff[li + 1] - sm.l_coff[li];
             const int rq = (int)hdr_len(lp + 4);
-            const int tb = 8 + rq, tn = clen - tb;
+            const int nch = (clen - 8 - rq + 15) >> 4;
+            const unsigned* src = gtab + ((c_lo + (unsigned long long)sm.l_coff[li]) >> 4) + (k0 + (unsigned long long)li);
             unsigned* tab = sm.ctab + sm.l_ctab[li];
-            int carry_kind = 0;
-            unsigned carry_out = 0;
-            for (int base = 0; base < tn; base += 512) {
-                const int offc = base + 16 * lane;
-                int nbytes = tn - offc;
-                nbytes = nbytes < 0 ? 0 : (nbytes > 16 ? 16 : nbytes);
-                uint8_t b[16];
-                int kind = 0;
-                if (nbytes > 0) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) b[i] = i < nbytes ? lp[tb + offc + i] : 0;
-                    kind = last_setter_kind(b, nbytes);
-                }
-                const unsigned has = __ballot_sync(0xffffffffu, kind != 0);
-                const unsigned below = has & ((1u << lane) - 1u);
-                const int k_src = __shfl_sync(0xffffffffu, kind, below ? 31 - __clz(below) : 0);
-                const int k_in = below ? k_src : carry_kind;
-                unsigned o = 0, ns = 0;
-                int e = 0;
-                if (nbytes > 0) chunk_measure(b, nbytes, k_in == 1, offc + nbytes == tn, &o, &ns, &e);
-                unsigned inc = o;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-                if (nbytes > 0) tab[offc >> 4] = ((carry_out + inc - o) << 1) | (k_in == 1 ? 1u : 0u);
-                carry_out += __shfl_sync(0xffffffffu, inc, 31);
-                if (has) carry_kind = __shfl_sync(0xffffffffu, kind, 31 - __clz(has));
-            }
+            for (int i = lane; i < nch; i += 32) tab[i] = src[i];
         }
         __syncthreads();
         // (4) generate: the lines of the batch that intersect this thread's span, strictly left to right
@@ -559,7 +546,7 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
     int rc;
     const long long n = (long long)in_len, n_seg = (n + kSeg - 1) / kSeg;
     DevBuf &b_ctrl = ctx->ws[2], &b_seg = ctx->ws[0], &b_scr = ctx->ws[1], &b_ls = ctx->ws[3], &b_sizes = ctx->ws[4],
-           &b_offs = ctx->ws[7], &b_tiles = ctx->ws[5];
+           &b_offs = ctx->ws[7], &b_tiles = ctx->ws[5], &b_tab = ctx->ws[8];
     if ((rc = dev_reserve(ctx, &b_ctrl, sizeof(Ctrl) + 64))) return rc;
     if ((rc = dev_reserve(ctx, &b_seg, (size_t)n_seg * 8 * 4 + 64))) return rc;
     Ctrl* ctrl = (Ctrl*)b_ctrl.p;
@@ -588,10 +575,11 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
     if ((rc = dev_reserve(ctx, &b_ls, (n_lines + 2) * 8))) return rc;
     if ((rc = dev_reserve(ctx, &b_sizes, (n_lines + 1) * 8))) return rc;
     if ((rc = dev_reserve(ctx, &b_offs, (n_lines + 1) * 8))) return rc;
+    if ((rc = dev_reserve(ctx, &b_tab, ((size_t)in_len / 16 + n_lines + 8) * 4))) return rc;
     unsigned long long* line_start = (unsigned long long*)b_ls.p;
     k_dec_fill<<<gs, 128, 0, stream>>>(d_in, n, n_seg, cand, base, line_start, n_lines, ctrl);
     k_dec_sizes<<<(unsigned)((n_lines * 32 + 127) / 128), 128, 0, stream>>>(d_in, line_start, n_lines, sample_count,
-                                                                             (unsigned long long*)b_sizes.p, ctrl);
+                                                                             (unsigned long long*)b_sizes.p, (unsigned*)b_tab.p, ctrl);
     ctx->launches += 2;
     if ((rc = scan_exclusive_u64(ctx, (uint64_t*)b_sizes.p, (uint64_t*)b_offs.p, (size_t)n_lines, (uint64_t*)&ctrl->total_out, &b_scr, stream)))
         return rc;
@@ -615,7 +603,7 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
                                                                           (unsigned int*)b_tiles.p);
     if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeDecodeExpand], stream);
     k_dec_expand<<<(unsigned)n_tiles, kThreads, sizeof(Smem), stream>>>(d_in, line_start, (unsigned long long*)b_offs.p, n_lines,
-                                                                        total, (unsigned int*)b_tiles.p, d_out, ctrl);
+                                                                        total, (unsigned int*)b_tiles.p, (const unsigned*)b_tab.p, d_out, ctrl);
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeDecodeExpand + 1], stream); ctx->ev_pending[kTimeDecodeExpand] = 1; }
     k_dec_result<<<1, 1, 0, stream>>>(d_result, ctrl, VCFC_OK, total, n_lines);
     ctx->launches += 3;
