@@ -33,12 +33,13 @@ constexpr int kHalo = 1024;
 constexpr int kPad = 32;                // zeroed bytes in front of / behind the window
 constexpr int kMaxReq = kHalo - 64;     // longest required section taken by this path
 constexpr int kWin = kTile + 2 * kHalo + 2 * kPad;
-constexpr int kStage = 21504 + 32;      // staging bytes (regular data expands at most ~1.45x)
+constexpr int kStage = 12288;           // smem staging; tiles that expand beyond it store straight to HBM
 constexpr int kMaxNl = 30;              // newlines per tile taken by this path (lines >= ~0.5 KB)
 constexpr int kMaxSeg = kMaxNl + 2;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxItems = 2 * kThreads; // two items per thread, held in registers
+constexpr int kCtasPerSm = 4;
 
 enum { kCutLine = 0, kCutSample = 1, kCutSampleFirst = 2, kCutEnd = 3, kCutBad = 4 };
 constexpr int kNone = 7;                // "no open run" class
@@ -51,6 +52,7 @@ struct Ctrl {                           // one per launch, zeroed by the host
     int line2big;
     unsigned long long total_bytes, total_lines;
     unsigned long long line_cap;
+    unsigned long long log_cursor, log_cap;   // the tile log: tile outputs in arrival order, gathered by k_gather_tiles
 };
 
 struct Seg {                            // a run of sample words of one line inside the tile
@@ -58,22 +60,24 @@ struct Seg {                            // a run of sample words of one line ins
     int ls, s0;                         // line start / first sample if the line starts in this tile, else ls = -1
     int item0;                          // first item index
     int flags;                          // bit0: span ends with the line's '\n'; bit1: first sample of span is first of line
-    int out0;                           // staging offset of the line start (header) -- valid if ls >= 0
+    int out0;                           // output offset (tile-relative) of the line start -- valid if ls >= 0
     int pad;
 };
 
 struct Smem {
-    alignas(128) uint8_t win[kWin];
-    alignas(16) uint8_t stage[kStage];
-    alignas(8) uint64_t mbar;
+    alignas(128) uint8_t win[2][kWin];  // double-buffered window: the next tile loads while this one is processed
+    alignas(16) uint8_t stage[kStage + 16];
+    alignas(8) uint64_t mbar[2];
     Seg seg[kMaxSeg];
-    int nlpos[kMaxNl + 2];
+    int nlpos[kMaxNl + 2], nls0[kMaxNl + 2];   // newline positions of the scanned range and the first sample after each
     int n_nl, n_seg, n_items, n_lines;
-    int tile, irregular;
-    int cs, cs_kind, ce, ce_kind;
+    int tile, next_tile, issued[2], irregular;
+    int cs, cs_kind, ce, ce_kind, cs_s0;
     int tile_last_head;
     int ein_virtual;
     int warp_h[kWarps], warp_s[kWarps];
+    int lb_has[kWarps];
+    unsigned long long lb_a[kWarps], lb_b[kWarps];
     unsigned long long excl_bytes, excl_lines;
     int skip_write;
 };
@@ -204,7 +208,7 @@ __device__ __forceinline__ void ld_status(const unsigned long long* p, unsigned 
 }
 
 // ---- classify one item ------------------------------------------------------------------------------------
-__device__ __forceinline__ void item_classify(Smem& sm, int item, Item& it, int* lasthead) {
+__device__ __forceinline__ void item_classify(Smem& sm, const uint8_t* __restrict__ win, int item, Item& it, int* lasthead) {
     it.blk = 0; it.V = it.C = it.L = it.Hd = it.CL = 0; it.kend = -1; it.pcoded = 0; it.hdr = 0; it.phase = 0; it.seg = 0;
     *lasthead = kNoHead;
     if (item >= sm.n_items) return;
@@ -224,7 +228,7 @@ __device__ __forceinline__ void item_classify(Smem& sm, int item, Item& it, int*
     int kend = -1;
     if (flags & 1) { int r = e - 4 - base; if (r >= 0 && r < 32) kend = r >> 2; }
     // the 10 words around the block; sample k = bytes base + 4k .. base + 4k + 3
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(sm.win + blk);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(win + blk);
     uint32_t W[10];
     W[0] = wp[-1];
     uint4 v0 = *reinterpret_cast<const uint4*>(wp), v1 = *reinterpret_cast<const uint4*>(wp + 4);
@@ -245,7 +249,7 @@ __device__ __forceinline__ void item_classify(Smem& sm, int item, Item& it, int*
     while (N) {
         const int k = __ffs(N) - 1;
         N &= N - 1;
-        const uint8_t* p = sm.win + base + 4 * k;
+        const uint8_t* p = win + base + 4 * k;
         const uint32_t b3 = p[3];
         if (k == kend ? (b3 != '\n') : (b3 != '\t')) irr = true;
         if (gt_class3(p) < 4) {            // coded sample terminated by the line's newline
@@ -257,7 +261,7 @@ __device__ __forceinline__ void item_classify(Smem& sm, int item, Item& it, int*
             L |= 1u << k;
         }
     }
-    if (kend >= 0 && ((V >> kend) & 1u) && sm.win[base + 4 * kend + 3] != '\n') irr = true;
+    if (kend >= 0 && ((V >> kend) & 1u) && win[base + 4 * kend + 3] != '\n') irr = true;
     if (irr) sm.irregular = 1;
     const uint32_t Hd = V & (F | ~(Craw & Q));
     const uint32_t PC = (((Craw << 1) | pc_all) & 0xFFu) & ~F;     // the previous word is a coded sample of this line
@@ -270,14 +274,14 @@ __device__ __forceinline__ void item_classify(Smem& sm, int item, Item& it, int*
 // bytes the item emits (tokens, literals, line end) -- compress.cpp:124-190 in closed form.
 // ein = address of the last run head before the item.  cnt_prev = chunk count (1..M) of the coded sample
 // just before the first valid one; cfbit = the sample before which the entering chunk fills up.
-__device__ __forceinline__ int item_count(const Smem& sm, const Item& it, int ein, uint32_t* cfbit, int* cnt_prev, bool* m127) {
+__device__ __forceinline__ int item_count(const uint8_t* __restrict__ win, const Item& it, int ein, uint32_t* cfbit, int* cnt_prev, bool* m127) {
     *cfbit = 0; *cnt_prev = 0; *m127 = true;
     if (!it.V) return it.hdr;
     const int k0 = __ffs(it.V) - 1;
     int n = it.hdr + __popc(it.CL) + 5 * __popc(it.L);
     if (it.pcoded) {
         const int paddr = it.blk + it.phase + 4 * k0 - 4;        // the previous sample
-        *m127 = ((sm.win[paddr] | sm.win[paddr + 2]) & 1u) == 0;  // 0|0 chunks by 127, the others by 31
+        *m127 = ((win[paddr] | win[paddr + 2]) & 1u) == 0;  // 0|0 chunks by 127, the others by 31
         *cnt_prev = mod_chunk((paddr - ein) >> 2, *m127) + 1;
         const uint32_t t = (~it.Hd & it.V) >> k0;                 // leading samples that continue the entering run
         const int nlead = __ffs(~t) - 1;
@@ -288,7 +292,7 @@ __device__ __forceinline__ int item_count(const Smem& sm, const Item& it, int ei
     return n;
 }
 
-__device__ __forceinline__ void item_emit(const Smem& sm, const Item& it, uint32_t cfbit, int cnt_prev, bool m127,
+__device__ __forceinline__ void item_emit(const uint8_t* __restrict__ win, const Item& it, uint32_t cfbit, int cnt_prev, bool m127,
                                           uint8_t* __restrict__ dst) {
     if (!it.V) return;
     const int k0 = __ffs(it.V) - 1;
@@ -298,7 +302,7 @@ __device__ __forceinline__ void item_emit(const Smem& sm, const Item& it, uint32
     while (ev) {
         const int k = __ffs(ev) - 1;
         ev &= ev - 1;
-        const uint8_t* p = sm.win + base + 4 * k;
+        const uint8_t* p = win + base + 4 * k;
         if (((it.CL | cfbit) >> k) & 1u) {                        // token closing the chunk that ends at sample k-1
             const int c = (int)(((p[-4] & 1u) << 1) | (p[-2] & 1u));
             const uint32_t hb = it.Hd & ((1u << k) - 1u);
@@ -328,323 +332,368 @@ __device__ __forceinline__ void item_emit(const Smem& sm, const Item& it, uint32
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 4)
-k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict__ out, unsigned long long out_cap,
-               Ctrl* __restrict__ ctrl, unsigned int* __restrict__ s1, unsigned long long* __restrict__ s2,
-               unsigned long long* __restrict__ line_offs, int n_tiles) {
+// ---- window staging: one bulk async copy (TMA engine) per tile, completion on an mbarrier -------------------
+__device__ __forceinline__ void issue_window_load(Smem& sm, int buf, const uint8_t* __restrict__ in, long long n, int tile) {
+    const long long t0 = (long long)tile * kTile, wbase = t0 - kHalo - kPad;
+    const long long vlo = t0 - kHalo > 0 ? t0 - kHalo : 0;
+    const long long vhi = t0 + kTile + kHalo < n ? t0 + kTile + kHalo : n;
+    const unsigned bulk = (unsigned)((vhi - vlo) & ~15ll);
+    fence_proxy_async();                       // the buffer was last touched through the generic proxy
+    mbar_expect_tx(&sm.mbar[buf], bulk);
+    if (bulk)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sm.win[buf] + (int)(vlo - wbase))), "l"(in + vlo), "r"(bulk), "r"(smem_u32(&sm.mbar[buf])) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
+               unsigned int* __restrict__ s1, unsigned long long* __restrict__ rec_pos, unsigned long long* __restrict__ rec_size,
+               unsigned long long* __restrict__ rec_lines, int n_tiles) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // ---- 0. ticket (tiles are started in index order, which the look-backs rely on) ------------------
+    // ---- persistent CTA: CTA c processes tiles c, c + G, c + 2G, ... (G = gridDim.x <= resident CTAs, so the tile a
+    //      look-back waits for is always being processed); the next window loads while this one is processed --------
+    const int G = (int)gridDim.x;
     if (tid == 0) {
-        sm.tile = (int)atomicAdd(&ctrl->ticket, 1u);
-        sm.irregular = *((volatile int*)&ctrl->irregular);
-        sm.n_nl = 0;
-        sm.skip_write = 0;
-        sm.tile_last_head = kNoHead;
-        sm.n_items = 0; sm.n_seg = 0; sm.n_lines = 0;
-        mbar_init(&sm.mbar, 1);
+        mbar_init(&sm.mbar[0], 1);
+        mbar_init(&sm.mbar[1], 1);
         fence_mbar_init();
+        sm.issued[0] = sm.issued[1] = 0;
+        if ((int)blockIdx.x < n_tiles) { issue_window_load(sm, 0, in, n, (int)blockIdx.x); sm.issued[0] = 1; }
     }
     __syncthreads();
-    const int tile = sm.tile;
-    if (tile >= n_tiles) return;
-    const long long t0 = (long long)tile * kTile;
-    const long long wbase = t0 - kHalo - kPad;                 // global offset of win[0] (multiple of 32)
-    const long long vlo = t0 - kHalo > 0 ? t0 - kHalo : 0;      // valid global range held in the window
-    const long long vhi = t0 + kTile + kHalo < n ? t0 + kTile + kHalo : n;
-    const int vlo_w = (int)(vlo - wbase), vhi_w = (int)(vhi - wbase);
+    int buf = 0;
+    unsigned par[2] = {0u, 0u};
 
-    if (sm.irregular) {          // some tile already gave up: keep the look-back chains alive and leave
+    for (int tile = (int)blockIdx.x; tile < n_tiles; tile += G) {
+        const int tile_next = tile + G;
         if (tid == 0) {
-            s1[tile] = (2u << 30) | ((unsigned)kNone << 8);
-            st_status(s2 + 2 * (size_t)tile, kFlagAgg, kFlagAgg);
+            sm.irregular = *((volatile int*)&ctrl->irregular);
+            sm.n_nl = 0;
+            sm.skip_write = 0;
+            sm.tile_last_head = kNoHead;
+            sm.n_items = 0; sm.n_seg = 0; sm.n_lines = 0;
+            sm.issued[buf ^ 1] = 0;
+            if (tile_next < n_tiles && !sm.irregular) { issue_window_load(sm, buf ^ 1, in, n, tile_next); sm.issued[buf ^ 1] = 1; }
         }
-        return;
-    }
+        const uint8_t* const win = sm.win[buf];
+        uint8_t* const winw = sm.win[buf];
+        const long long t0 = (long long)tile * kTile;
+        const long long wbase = t0 - kHalo - kPad;                 // global offset of win[0] (multiple of 32)
+        const long long vlo = t0 - kHalo > 0 ? t0 - kHalo : 0;      // valid global range held in the window
+        const long long vhi = t0 + kTile + kHalo < n ? t0 + kTile + kHalo : n;
+        const int vlo_w = (int)(vlo - wbase), vhi_w = (int)(vhi - wbase);
+        const bool was_issued = sm.issued[buf] != 0;               // (written in the previous iteration / prologue)
 
-    // ---- 1. stage the window: one bulk async copy + a few tail bytes --------------------------------
-    const unsigned bulk = (unsigned)((vhi - vlo) & ~15ll);
-    if (tid == 0) {
-        mbar_expect_tx(&sm.mbar, bulk);
-        if (bulk)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(sm.win + vlo_w)), "l"(in + vlo), "r"(bulk), "r"(smem_u32(&sm.mbar)) : "memory");
-    }
-    for (int g = vlo_w + (int)bulk + tid; g < vhi_w; g += kThreads) sm.win[g] = in[wbase + g];
-    if (tid < kPad) { sm.win[vlo_w - kPad + tid] = 0; }
-    if (tid >= 32 && tid < 32 + kPad + 16) { int g = vhi_w + tid - 32; if (g < kWin) sm.win[g] = 0; }
-    mbar_wait(&sm.mbar, 0);
-    __syncthreads();
-    if (tid == 0 && vhi == n && sm.win[vhi_w - 1] != '\n') sm.irregular = 1;   // no final newline: generic path
-
-    // ---- 2. cut points ---------------------------------------------------------------------------------
-    if (warp < 2) {
-        int kind;
-        long long c = cut_find(sm.win, wbase, vlo, vhi, n, warp == 0 ? t0 : t0 + kTile, lane, &kind);
-        if (lane == 0) {
-            if (warp == 0) { sm.cs = (int)(c - wbase); sm.cs_kind = kind; }
-            else           { sm.ce = (int)(c - wbase); sm.ce_kind = kind; }
-            if (kind == kCutBad) sm.irregular = 1;
+        // ---- 1. window: wait for the bulk copy, add the <16 tail bytes and the zero pads ----------------------
+        if (was_issued) { mbar_wait(&sm.mbar[buf], par[buf]); par[buf] ^= 1u; }
+        {
+            const unsigned bulk = (unsigned)((vhi - vlo) & ~15ll);
+            for (int g = vlo_w + (int)bulk + tid; g < vhi_w; g += kThreads) winw[g] = in[wbase + g];
+            if (tid < kPad) winw[vlo_w - kPad + tid] = 0;
+            if (tid >= 32 && tid < 32 + kPad + 16) { int g = vhi_w + tid - 32; if (g < kWin) winw[g] = 0; }
         }
-    }
-    __syncthreads();
-    const int cs = sm.cs, ce = sm.ce, cs_kind = sm.cs_kind;
+        __syncthreads();
+        if (sm.irregular || !was_issued) {     // some tile already gave up: keep the look-back chains alive and move on
+            if (tid == 0) {
+                s1[tile] = (2u << 30) | ((unsigned)kNone << 8);
+                atomicExch(&ctrl->irregular, 1);
+            }
+            buf ^= 1;
+            __syncthreads();
+            continue;
+        }
+        if (tid == 0 && vhi == n && win[vhi_w - 1] != '\n') sm.irregular = 1;   // no final newline: generic path
 
-    // ---- 3. newline list of [cs, ce): AND-filter over 16 bytes, exact test only on a hit ------------------
-    if (!sm.irregular) {
-        for (int c16 = (cs >> 4) + tid; (c16 << 4) < ce; c16 += kThreads) {
-            uint4 v = *reinterpret_cast<const uint4*>(sm.win + (c16 << 4));
-            // a '\n' in any of the four words leaves a zero byte in the AND of (w ^ "\n\n\n\n")
-            uint32_t t = (v.x ^ 0x0A0A0A0Au) & (v.y ^ 0x0A0A0A0Au) & (v.z ^ 0x0A0A0A0Au) & (v.w ^ 0x0A0A0A0Au);
-            if (((t - 0x01010101u) & ~t & 0x80808080u) == 0u) continue;
-            uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                uint32_t z = zero_bytes(w[j] ^ 0x0A0A0A0Au);
-                while (z) {
-                    int bpos = (__ffs(z) - 1) >> 3;
-                    z &= z - 1;
-                    int g = (c16 << 4) + 4 * j + bpos;
-                    if (g >= cs && g < ce) {
-                        int slot = atomicAdd(&sm.n_nl, 1);
-                        if (slot < kMaxNl) sm.nlpos[slot] = g;
+        // ---- 2. cut points (warps 0, 1) and the newline list of the nominal range + forward halo (all warps) -----
+        if (warp < 2) {
+            int kind;
+            long long c = cut_find(win, wbase, vlo, vhi, n, warp == 0 ? t0 : t0 + kTile, lane, &kind);
+            int s0c = -1;
+            if (warp == 0 && kind == kCutLine) s0c = line_scan(win, (int)(c - wbase), vhi_w, lane);
+            if (lane == 0) {
+                if (warp == 0) { sm.cs = (int)(c - wbase); sm.cs_kind = kind; sm.cs_s0 = s0c; }
+                else           { sm.ce = (int)(c - wbase); sm.ce_kind = kind; }
+                if (kind == kCutBad) sm.irregular = 1;
+            }
+        }
+        {
+            const int lo16 = (kHalo + kPad) >> 4, hi16 = (min(vhi_w, kHalo + kPad + kTile + kMaxReq) + 15) >> 4;
+            for (int base16 = lo16; base16 < hi16; base16 += kThreads) {          // warp-uniform trip count
+                const int c16 = base16 + tid;
+                unsigned nlmask = 0;
+                if (c16 < hi16) {
+                    uint4 v = *reinterpret_cast<const uint4*>(win + (c16 << 4));
+                    // a '\n' in any of the four words leaves a zero byte in the AND of (w ^ "\n\n\n\n")
+                    uint32_t t = (v.x ^ 0x0A0A0A0Au) & (v.y ^ 0x0A0A0A0Au) & (v.z ^ 0x0A0A0A0Au) & (v.w ^ 0x0A0A0A0Au);
+                    if (((t - 0x01010101u) & ~t & 0x80808080u) != 0u)
+                        nlmask = nibble_of(zero_bytes(v.x ^ 0x0A0A0A0Au)) | (nibble_of(zero_bytes(v.y ^ 0x0A0A0A0Au)) << 4) |
+                                 (nibble_of(zero_bytes(v.z ^ 0x0A0A0A0Au)) << 8) | (nibble_of(zero_bytes(v.w ^ 0x0A0A0A0Au)) << 12);
+                }
+                // every newline: the warp that found it also finds the first sample of the line that follows
+                unsigned any;
+                while ((any = __ballot_sync(0xffffffffu, nlmask != 0)) != 0) {
+                    const int leader = __ffs(any) - 1;
+                    const int q = __shfl_sync(0xffffffffu, (c16 << 4) + __ffs(nlmask) - 1, leader);
+                    if (lane == leader) nlmask &= nlmask - 1;
+                    int s0 = -2;                                     // -2: the line starts outside the window
+                    if (q + 1 < vhi_w && q < vhi_w) s0 = line_scan(win, q + 1, vhi_w, lane);
+                    if (lane == 0 && q < vhi_w) {
+                        const int slot = atomicAdd(&sm.n_nl, 1);
+                        if (slot < kMaxNl) { sm.nlpos[slot] = q; sm.nls0[slot] = s0; }
                     }
                 }
             }
         }
-    }
-    __syncthreads();
-
-    // ---- 4. segments (warp 0): [partial first line] + one per line start in [cs, ce) ---------------------------
-    const int first_partial = (cs_kind == kCutSample || cs_kind == kCutSampleFirst) && cs < ce ? 1 : 0;
-    if (warp == 0 && !sm.irregular) {
-        int n_nl = sm.n_nl;
-        if (n_nl > kMaxNl) { if (lane == 0) sm.irregular = 1; n_nl = 0; }
-        // sort the (few) newline positions: slot j ends up holding the j-th smallest
-        const int mine = lane < n_nl ? sm.nlpos[lane] : 0x7fffffff;
-        int rank = 0;
-        for (int j = 0; j < n_nl; j++) rank += (__shfl_sync(0xffffffffu, mine, j) < mine);
-        __syncwarp();
-        if (lane < n_nl) sm.nlpos[rank] = mine;
-        __syncwarp();
-        const int own_first = (cs_kind == kCutLine && cs < ce) ? 1 : 0;
-        int n_lines = own_first;
-        for (int j = 0; j < n_nl; j++) n_lines += (sm.nlpos[j] + 1 < ce);
-        if (first_partial && lane == 0) {
-            Seg& s = sm.seg[0];
-            s.a = cs; s.ls = -1; s.s0 = -1;
-            s.e = n_nl ? sm.nlpos[0] + 1 : ce;
-            s.flags = (n_nl ? 1 : 0) | (cs_kind == kCutSampleFirst ? 2 : 0);
-        }
-        for (int l = 0; l < n_lines; l++) {
-            const int nli = l - own_first;                 // index of the newline before this line
-            const int ls = nli < 0 ? cs : sm.nlpos[nli] + 1;
-            const int s0 = line_scan(sm.win, ls, vhi_w, lane);
-            if (lane == 0) {
-                Seg& s = sm.seg[first_partial + l];
-                const int nxt = nli + 1;                    // the newline that ends this line, if it is in the tile
-                s.ls = ls; s.s0 = s0; s.a = s0;
-                s.e = nxt < n_nl ? sm.nlpos[nxt] + 1 : ce;
-                s.flags = (nxt < n_nl ? 1 : 0) | 2;
-                if (s0 < 0 || s0 > s.e) sm.irregular = 1;
-            }
-        }
-        __syncwarp();
-        if (lane == 0 && !sm.irregular) {
-            const int n_seg = first_partial + n_lines;
-            int items = 0;
-            for (int i = 0; i < n_seg; i++) {
-                Seg& s = sm.seg[i];
-                if (((s.e - s.a) & 3) != 0) { sm.irregular = 1; break; }
-                s.item0 = items;
-                // blocks are indexed by where a sample word STARTS; a line start with no sample here still needs an item
-                items += s.e > s.a ? ((s.e - 4) >> 5) - (s.a >> 5) + 1 : 1;
-            }
-            if (items > kMaxItems) sm.irregular = 1;
-            if (!sm.irregular) { sm.n_seg = n_seg; sm.n_lines = n_lines; sm.n_items = items; }
-        }
-    }
-    __syncthreads();
-
-    // ---- 5. classify: two items per thread (lane l of warp w: items 64w + l and 64w + 32 + l) ---------------------
-    Item it0, it1;
-    int lh0, lh1;
-    item_classify(sm, warp * 64 + lane, it0, &lh0);
-    item_classify(sm, warp * 64 + 32 + lane, it1, &lh1);
-    // last run head before each item, inside the warp: nearest lower lane that has a head
-    int ein0, ein1;
-    {
-        const unsigned hm0 = __ballot_sync(0xffffffffu, lh0 != kNoHead), hm1 = __ballot_sync(0xffffffffu, lh1 != kNoHead);
-        const unsigned below = (1u << lane) - 1u;
-        const int src0 = (hm0 & below) ? 31 - __clz(hm0 & below) : 0, src1 = (hm1 & below) ? 31 - __clz(hm1 & below) : 0;
-        const int g0 = __shfl_sync(0xffffffffu, lh0, src0), g1 = __shfl_sync(0xffffffffu, lh1, src1);
-        const int last0 = __shfl_sync(0xffffffffu, lh0, hm0 ? 31 - __clz(hm0) : 0);
-        const int last1 = __shfl_sync(0xffffffffu, lh1, hm1 ? 31 - __clz(hm1) : 0);
-        const int tot0 = hm0 ? last0 : kNoHead, tot1 = hm1 ? last1 : kNoHead;
-        ein0 = (hm0 & below) ? g0 : kNoHead;
-        ein1 = (hm1 & below) ? g1 : tot0;
-        const int warp_last = hm1 ? tot1 : tot0;
-        if (lane == 0) { sm.warp_h[warp] = warp_last; if (warp_last != kNoHead) atomicMax(&sm.tile_last_head, warp_last); }
-    }
-    __syncthreads();
-    bool bad = sm.irregular != 0;
-
-    // ---- 6. look-back #1 (thread 0): chunk count of the run that enters the tile -------------------------------------
-    if (tid == 0) {
-        const int tl = sm.tile_last_head;
-        int ein = kNoHead;
-        if (!bad && cs < ce) {
-            // class of the tile's last sample (kNone when the tile ends with a line end or a required section)
-            int lc = kNone;
-            if (sm.ce_kind == kCutSample) lc = gt_class3(sm.win + ce - 4);
-            const bool need_in = first_partial && cs_kind == kCutSample;      // the first sample continues a line
-            const int pc0 = need_in ? gt_class3(sm.win + cs - 4) : kNone;
-            const bool uniform = tl == kNoHead;                   // no run head in the tile: the entering run covers it
-            const int nsamp = (ce - cs) >> 2;                      // only used when uniform (one partial segment)
-            const int Ml = lc == 0 ? 127 : 31;
-            if (!uniform) {
-                unsigned cnt = lc < 4 ? (unsigned)((((ce - tl) >> 2) - 1) % Ml) + 1u : 0u;
-                s1[tile] = (2u << 30) | ((unsigned)lc << 8) | cnt;    // absolute: publish before waiting
-                __threadfence();
-            } else if (lc < 4) {
-                s1[tile] = (1u << 30) | ((unsigned)lc << 8) | (unsigned)(nsamp % Ml);   // relative to the entering run
-                __threadfence();
-            }
-            int cnt_in = 0;
-            if (need_in && pc0 < 4 && tile > 0) {
-                const int M = pc0 == 0 ? 127 : 31;
-                int acc = 0;
-                for (int j = tile - 1; j >= 0; j--) {
-                    unsigned v;
-                    do { v = *((volatile unsigned*)&s1[j]); } while ((v >> 30) == 0);
-                    acc += (int)(v & 0xFFu);
-                    if ((v >> 30) == 2u) break;
-                }
-                cnt_in = ((acc - 1) % M + M) % M + 1;              // open chunk count before the tile, 1..M
-                ein = cs - 4 * cnt_in;
-            }
-            if (uniform) {
-                unsigned cnt = lc < 4 ? (unsigned)((cnt_in + nsamp - 1) % Ml) + 1u : 0u;
-                s1[tile] = (2u << 30) | ((unsigned)lc << 8) | cnt;
-                __threadfence();
-            }
-        } else {
-            s1[tile] = (2u << 30) | ((unsigned)kNone << 8);          // nothing carried out
-            __threadfence();
-        }
-#ifdef VCFC_DEBUG
-        printf("tile %d cs=%d(k%d) ce=%d(k%d) bad=%d n_items=%d n_seg=%d tl=%d s1=%08x ein=%d wbase=%lld\n", tile, cs, cs_kind, ce,
-               sm.ce_kind, (int)bad, sm.n_items, sm.n_seg, tl, s1[tile], ein, wbase);
-#endif
-        sm.ein_virtual = ein;
-    }
-    __syncthreads();
-
-    // ---- 7. byte counts and their exclusive scan -----------------------------------------------------------------------
-    {
-        int pre = sm.ein_virtual;                                  // heads of earlier warps (addresses grow with the item index)
-        for (int w = 0; w < warp; w++) pre = max(pre, sm.warp_h[w]);
-        ein0 = max(ein0, pre);
-        ein1 = max(ein1, pre);
-    }
-    uint32_t cf0 = 0, cf1 = 0;
-    int cp0 = 0, cp1 = 0;
-    bool m0 = true, m1 = true;
-    const int n0 = bad ? 0 : item_count(sm, it0, ein0, &cf0, &cp0, &m0);
-    const int n1 = bad ? 0 : item_count(sm, it1, ein1, &cf1, &cp1, &m1);
-    int off0, off1, total;
-    {
-        // both sub-rounds in one scan: low half = items 64w + lane, high half = items 64w + 32 + lane
-        const unsigned packed = (unsigned)n0 | ((unsigned)n1 << 16);
-        unsigned inc = packed;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-        const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
-        const int tot0 = (int)(tot & 0xFFFFu), tot1 = (int)(tot >> 16);
-        if (lane == 0) sm.warp_s[warp] = tot0 + tot1;
         __syncthreads();
-        int pre = 0, all = 0;
-        for (int w = 0; w < kWarps; w++) { int v = sm.warp_s[w]; all += v; if (w < warp) pre += v; }
-        off0 = pre + (int)(inc & 0xFFFFu) - n0;
-        off1 = pre + tot0 + (int)(inc >> 16) - n1;
-        total = all;
-    }
-    if (total > kStage - 32) { bad = true; total = 0; }
-    if (bad && tid == 0) atomicExch(&ctrl->irregular, 1);
+        const int cs = sm.cs, ce = sm.ce, cs_kind = sm.cs_kind;
 
-    // ---- 8. emit into staging (all warps), then look-back #2 (warp 0) ------------------------------------------------------
-    if (!bad) {
-        if (it0.hdr) sm.seg[it0.seg].out0 = off0;
-        if (it1.hdr) sm.seg[it1.seg].out0 = off1;
-        item_emit(sm, it0, cf0, cp0, m0, sm.stage + off0 + it0.hdr);
-        item_emit(sm, it1, cf1, cp1, m1, sm.stage + off1 + it1.hdr);
-    }
-    if (warp == 0) {
-        const unsigned long long my_b = (unsigned long long)total, my_l = (unsigned long long)(bad ? 0 : sm.n_lines);
-        if (lane == 0) st_status(s2 + 2 * (size_t)tile, kFlagAgg | my_b, kFlagAgg | my_l);
-        unsigned long long eb = 0, el = 0;
-        int j = tile - 1;
-        while (j >= 0) {
-            int idx = j - lane;
-            unsigned long long a = kFlagPrefix, b = kFlagPrefix;
-            if (idx >= 0) {
-                do { ld_status(s2 + 2 * (size_t)idx, &a, &b); } while ((a >> 62) == 0 || (a >> 62) != (b >> 62));
+        // ---- 3. segments (warp 0, one lane per segment): [partial first line] + one per line start in [cs, ce) ------
+        const int first_partial = (cs_kind == kCutSample || cs_kind == kCutSampleFirst) && cs < ce ? 1 : 0;
+        if (warp == 0 && !sm.irregular) {
+            int n_nl = sm.n_nl;
+            if (n_nl > kMaxNl) { if (lane == 0) sm.irregular = 1; n_nl = 0; }
+            // sort: lane j ends up holding the j-th smallest newline position (and its first-sample offset)
+            int q = lane < n_nl ? sm.nlpos[lane] : 0x3fffffff, qs0 = lane < n_nl ? sm.nls0[lane] : -2, rank = 0;
+            for (int j = 0; j < n_nl; j++) rank += (__shfl_sync(0xffffffffu, q, j) < q);
+            __syncwarp();
+            if (lane < n_nl) { sm.nlpos[rank] = q; sm.nls0[rank] = qs0; }
+            __syncwarp();
+            q = lane < n_nl ? sm.nlpos[lane] : 0x3fffffff;
+            const int idx_lo = __popc(__ballot_sync(0xffffffffu, q < cs));                 // newlines before the tile
+            const int n_in = __popc(__ballot_sync(0xffffffffu, q >= cs && q < ce));         // newlines inside it
+            const int n_start = __popc(__ballot_sync(0xffffffffu, q >= cs && q + 1 < ce)); // ... that start a line inside it
+            const int own_first = (cs_kind == kCutLine && cs < ce) ? 1 : 0;
+            const int n_lines = own_first + n_start, n_seg = first_partial + n_lines;
+            int a = 0, e = 0, ls = -1, s0 = -1, flags = 0, nitems = 0;
+            bool irr = false;
+            if (lane < n_seg) {
+                if (first_partial && lane == 0) {
+                    a = cs;
+                    e = n_in ? sm.nlpos[idx_lo] + 1 : ce;
+                    flags = (n_in ? 1 : 0) | (cs_kind == kCutSampleFirst ? 2 : 0);
+                } else {
+                    const int l = lane - first_partial, nli = l - own_first;   // nli: newline before the line (-1: the line at cs)
+                    ls = nli < 0 ? cs : sm.nlpos[idx_lo + nli] + 1;
+                    s0 = nli < 0 ? sm.cs_s0 : sm.nls0[idx_lo + nli];
+                    const int nxt = nli + 1;                                    // the newline that ends the line, if in the tile
+                    a = s0;
+                    e = nxt < n_in ? sm.nlpos[idx_lo + nxt] + 1 : ce;
+                    flags = (nxt < n_in ? 1 : 0) | 2;
+                    if (s0 < 0 || s0 > e) irr = true;
+                }
+                if (((e - a) & 3) != 0) irr = true;
+                // blocks are indexed by where a sample word STARTS; a line start with no sample here still needs an item
+                nitems = e > a ? ((e - 4) >> 5) - (a >> 5) + 1 : 1;
             }
-            unsigned pm = __ballot_sync(0xffffffffu, (a >> 62) == 2ull);
-            int firstp = pm ? __ffs(pm) - 1 : 32;
-            unsigned long long ca = lane <= firstp ? (a & kValMask) : 0ull, cb = lane <= firstp ? (b & kValMask) : 0ull;
+            int inc = nitems;
 #pragma unroll
-            for (int d = 16; d; d >>= 1) { ca += __shfl_xor_sync(0xffffffffu, ca, d); cb += __shfl_xor_sync(0xffffffffu, cb, d); }
-            eb += ca; el += cb;
-            if (pm) break;
-            j -= 32;
-        }
-        if (lane == 0) {
-            st_status(s2 + 2 * (size_t)tile, kFlagPrefix | (eb + my_b), kFlagPrefix | (el + my_l));
-            sm.excl_bytes = eb;
-            sm.excl_lines = el;
-            if (eb + my_b > out_cap) { sm.skip_write = 1; atomicExch(&ctrl->cap_exceeded, 1); }
-            if (el + my_l > ctrl->line_cap) { sm.skip_write = 1; atomicExch(&ctrl->irregular, 1); }
-            if (tile == n_tiles - 1) { ctrl->total_bytes = eb + my_b; ctrl->total_lines = el + my_l; }
-        }
-    }
-    __syncthreads();
-    if (bad || sm.skip_write) return;
-    const unsigned long long obase = sm.excl_bytes;
-
-    // ---- 9. line starts: two length headers + required section; record the line's output offset --------------------------
-    {
-        const unsigned long long lbase = sm.excl_lines;
-        const int nl = sm.n_lines;
-        for (int l = warp; l < nl; l += kWarps) {
-            const int si = first_partial + l;
-            const int ls = sm.seg[si].ls, rq = sm.seg[si].s0 - ls, o0 = sm.seg[si].out0;
-            uint8_t* d = sm.stage + o0;
-            if (lane < 4) d[lane] = lane == 0 ? 0xC0 : 0;                       // line length: patched by k_patch_headers
-            if (lane >= 4 && lane < 8) {
-                unsigned v = (unsigned)rq;
-                d[lane] = lane == 4 ? (uint8_t)((v >> 24) | 0xC0) : (uint8_t)(v >> (8 * (7 - lane)));
+            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            const int items = __shfl_sync(0xffffffffu, inc, 31);
+            irr = __any_sync(0xffffffffu, irr) || items > kMaxItems || n_seg > kMaxSeg;
+            if (lane < n_seg && !irr) {
+                Seg& sg = sm.seg[lane];
+                sg.a = a; sg.e = e; sg.ls = ls; sg.s0 = s0; sg.flags = flags; sg.item0 = inc - nitems; sg.out0 = 0;
             }
-            for (int k = lane; k < rq; k += 32) d[8 + k] = sm.win[ls + k];
-            if (lane == 0) line_offs[lbase + (unsigned long long)l] = obase + (unsigned long long)o0;
+            if (lane == 0) {
+                if (irr) sm.irregular = 1;
+                else { sm.n_seg = n_seg; sm.n_lines = n_lines; sm.n_items = items; }
+            }
         }
-        if (nl) __syncthreads();
-    }
+        __syncthreads();
 
-    // ---- 10. staging -> HBM: aligned 4-byte stores, source words funnel-shifted ----------------------------------------------
-    {
-        uint8_t* dst = out + obase;
-        const int mis = (int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);      // bytes until dst is 4-byte aligned
-        const int head = min(mis, total);
-        if (tid < head) dst[tid] = sm.stage[tid];
-        const int nwords = (total - head) >> 2;
-        const uint32_t* sw = reinterpret_cast<const uint32_t*>(sm.stage);              // stage is 16-byte aligned
-        uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
-        for (int k = tid; k < nwords; k += kThreads) dw[k] = __funnelshift_r(sw[k], sw[k + 1], 8 * head);   // stage[head + 4k ..]
-        const int tail0 = head + 4 * nwords;
-        if (tid < total - tail0) dst[tail0 + tid] = sm.stage[tail0 + tid];
+        // ---- 4. classify: two items per thread (lane l of warp w: items 64w + l and 64w + 32 + l) ------------------
+        Item it0, it1;
+        int lh0, lh1;
+        item_classify(sm, win, warp * 64 + lane, it0, &lh0);
+        item_classify(sm, win, warp * 64 + 32 + lane, it1, &lh1);
+        // last run head before each item, inside the warp: nearest lower lane that has a head
+        int ein0, ein1;
+        {
+            const unsigned hm0 = __ballot_sync(0xffffffffu, lh0 != kNoHead), hm1 = __ballot_sync(0xffffffffu, lh1 != kNoHead);
+            const unsigned below = (1u << lane) - 1u;
+            const int src0 = (hm0 & below) ? 31 - __clz(hm0 & below) : 0, src1 = (hm1 & below) ? 31 - __clz(hm1 & below) : 0;
+            const int g0 = __shfl_sync(0xffffffffu, lh0, src0), g1 = __shfl_sync(0xffffffffu, lh1, src1);
+            const int last0 = __shfl_sync(0xffffffffu, lh0, hm0 ? 31 - __clz(hm0) : 0);
+            const int last1 = __shfl_sync(0xffffffffu, lh1, hm1 ? 31 - __clz(hm1) : 0);
+            const int tot0 = hm0 ? last0 : kNoHead, tot1 = hm1 ? last1 : kNoHead;
+            ein0 = (hm0 & below) ? g0 : kNoHead;
+            ein1 = (hm1 & below) ? g1 : tot0;
+            const int warp_last = hm1 ? tot1 : tot0;
+            if (lane == 0) { sm.warp_h[warp] = warp_last; if (warp_last != kNoHead) atomicMax(&sm.tile_last_head, warp_last); }
+        }
+        __syncthreads();
+        bool bad = sm.irregular != 0;
+
+        // ---- 5. look-back #1 (thread 0): chunk count of the run that enters the tile ----------------------------------
+        if (tid == 0) {
+            const int tl = sm.tile_last_head;
+            int ein = kNoHead;
+            if (!bad && cs < ce) {
+                // class of the tile's last sample (kNone when the tile ends with a line end or a required section)
+                int lc = kNone;
+                if (sm.ce_kind == kCutSample) lc = gt_class3(win + ce - 4);
+                const bool need_in = first_partial && cs_kind == kCutSample;      // the first sample continues a line
+                const int pc0 = need_in ? gt_class3(win + cs - 4) : kNone;
+                const bool uniform = tl == kNoHead;                   // no run head in the tile: the entering run covers it
+                const int nsamp = (ce - cs) >> 2;                      // only used when uniform (one partial segment)
+                const int Ml = lc == 0 ? 127 : 31;
+                if (!uniform) {
+                    unsigned cnt = lc < 4 ? (unsigned)((((ce - tl) >> 2) - 1) % Ml) + 1u : 0u;
+                    *((volatile unsigned*)&s1[tile]) = (2u << 30) | ((unsigned)lc << 8) | cnt;    // absolute: publish before waiting
+                } else if (lc < 4) {
+                    *((volatile unsigned*)&s1[tile]) = (1u << 30) | ((unsigned)lc << 8) | (unsigned)(nsamp % Ml);   // relative
+                }
+                int cnt_in = 0;
+                if (need_in && pc0 < 4 && tile > 0) {
+                    const int M = pc0 == 0 ? 127 : 31;
+                    int acc = 0;
+                    for (int j = tile - 1; j >= 0; j--) {
+                        unsigned v;
+                        do { v = *((volatile unsigned*)&s1[j]); } while ((v >> 30) == 0);
+                        acc += (int)(v & 0xFFu);
+                        if ((v >> 30) == 2u) break;
+                    }
+                    cnt_in = ((acc - 1) % M + M) % M + 1;              // open chunk count before the tile, 1..M
+                    ein = cs - 4 * cnt_in;
+                }
+                if (uniform) {
+                    unsigned cnt = lc < 4 ? (unsigned)((cnt_in + nsamp - 1) % Ml) + 1u : 0u;
+                    *((volatile unsigned*)&s1[tile]) = (2u << 30) | ((unsigned)lc << 8) | cnt;
+                }
+            } else {
+                *((volatile unsigned*)&s1[tile]) = (2u << 30) | ((unsigned)kNone << 8);          // nothing carried out
+            }
+#ifdef VCFC_DEBUG
+            printf("tile %d cs=%d(k%d) ce=%d(k%d) bad=%d n_items=%d n_seg=%d tl=%d s1=%08x ein=%d wbase=%lld\n", tile, cs, cs_kind, ce,
+                   sm.ce_kind, (int)bad, sm.n_items, sm.n_seg, tl, s1[tile], ein, wbase);
+#endif
+            sm.ein_virtual = ein;
+        }
+        __syncthreads();
+
+        // ---- 6. byte counts and their exclusive scan ----------------------------------------------------------------------
+        {
+            int pre = sm.ein_virtual;                                  // heads of earlier warps (addresses grow with the item index)
+            for (int w = 0; w < warp; w++) pre = max(pre, sm.warp_h[w]);
+            ein0 = max(ein0, pre);
+            ein1 = max(ein1, pre);
+        }
+        uint32_t cf0 = 0, cf1 = 0;
+        int cp0 = 0, cp1 = 0;
+        bool m0 = true, m1 = true;
+        const int n0 = bad ? 0 : item_count(win, it0, ein0, &cf0, &cp0, &m0);
+        const int n1 = bad ? 0 : item_count(win, it1, ein1, &cf1, &cp1, &m1);
+        int off0, off1, total;
+        {
+            // both sub-rounds in one scan: low half = items 64w + lane, high half = items 64w + 32 + lane
+            unsigned inc = (unsigned)n0 | ((unsigned)n1 << 16);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
+            const int tot0 = (int)(tot & 0xFFFFu), tot1 = (int)(tot >> 16);
+            if (lane == 0) sm.warp_s[warp] = tot0 + tot1;
+            __syncthreads();
+            int pre = 0, all = 0;
+            for (int w = 0; w < kWarps; w++) { int v = sm.warp_s[w]; all += v; if (w < warp) pre += v; }
+            off0 = pre + (int)(inc & 0xFFFFu) - n0;
+            off1 = pre + tot0 + (int)(inc >> 16) - n1;
+            total = all;
+        }
+        if (bad) total = 0;
+        const bool staged = total <= kStage;                           // else: store straight to HBM once the offset is known
+        if (bad && tid == 0) atomicExch(&ctrl->irregular, 1);
+
+        // ---- 7. emit into staging; reserve the tile's place in the log with one atomic (no scan chain: the final
+        //         positions come from a device scan over the tile records, k_gather_tiles moves the bytes) -----------
+        const int nl = bad ? 0 : sm.n_lines;
+        if (!bad) {
+            if (it0.hdr) sm.seg[it0.seg].out0 = off0;
+            if (it1.hdr) sm.seg[it1.seg].out0 = off1;
+            if (staged) {
+                item_emit(win, it0, cf0, cp0, m0, sm.stage + off0 + it0.hdr);
+                item_emit(win, it1, cf1, cp1, m1, sm.stage + off1 + it1.hdr);
+            }
+        }
+        if (tid == 0) {
+            const unsigned long long need = (unsigned long long)total + 2ull * (unsigned long long)nl;   // bytes + u16 line offsets
+            const unsigned long long pos = need ? atomicAdd(&ctrl->log_cursor, need) : 0ull;
+            rec_pos[tile] = pos; rec_size[tile] = (unsigned long long)total; rec_lines[tile] = (unsigned long long)nl;
+            if (pos + need > ctrl->log_cap) { sm.skip_write = 1; atomicExch(&ctrl->cap_exceeded, 1); }
+            sm.excl_bytes = pos;
+        }
+        __syncthreads();
+        if (!bad && !sm.skip_write && total > 0) {
+            uint8_t* const dst = log + sm.excl_bytes;
+            uint8_t* const image = staged ? sm.stage : dst;            // where the tile's output bytes are assembled
+            if (!staged) {
+                item_emit(win, it0, cf0, cp0, m0, image + off0 + it0.hdr);
+                item_emit(win, it1, cf1, cp1, m1, image + off1 + it1.hdr);
+            }
+            // ---- 8. line starts: two length headers + required section; the line's offset goes to the trailer -------
+            for (int l = warp; l < nl; l += kWarps) {
+                const int si = first_partial + l;
+                const int ls = sm.seg[si].ls, rq = sm.seg[si].s0 - ls, o0 = sm.seg[si].out0;
+                uint8_t* d = image + o0;
+                if (lane < 4) d[lane] = lane == 0 ? 0xC0 : 0;                       // line length: patched by k_patch_headers
+                if (lane >= 4 && lane < 8) {
+                    unsigned v = (unsigned)rq;
+                    d[lane] = lane == 4 ? (uint8_t)((v >> 24) | 0xC0) : (uint8_t)(v >> (8 * (7 - lane)));
+                }
+                for (int k = lane; k < rq; k += 32) d[8 + k] = win[ls + k];
+                if (lane < 2) dst[total + 2 * l + lane] = (uint8_t)((unsigned)o0 >> (8 * lane));
+            }
+            // ---- 9. staging -> log: aligned 4-byte stores, source words funnel-shifted ----------------------------
+            if (staged) {
+                __syncthreads();
+                const int mis = (int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);      // bytes until dst is 4-byte aligned
+                const int head = min(mis, total);
+                if (tid < head) dst[tid] = sm.stage[tid];
+                const int nwords = (total - head) >> 2;
+                const uint32_t* sw = reinterpret_cast<const uint32_t*>(sm.stage);
+                uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+                for (int k = tid; k < nwords; k += kThreads) dw[k] = __funnelshift_r(sw[k], sw[k + 1], 8 * head);
+                const int tail0 = head + 4 * nwords;
+                if (tid < total - tail0) dst[tail0 + tid] = sm.stage[tail0 + tid];
+            }
+        }
+        buf ^= 1;
+        __syncthreads();                                               // the window and the staging area are free again
+    }
+}
+
+// Final totals from the tile-record scans; decides capacity before any byte reaches the caller's buffer.
+__global__ void k_enc_totals(Ctrl* __restrict__ ctrl, unsigned long long out_cap) {
+    if (ctrl->total_bytes > out_cap) ctrl->cap_exceeded = 1;
+    if (ctrl->total_lines > ctrl->line_cap) ctrl->irregular = 1;
+}
+
+// One warp per tile: log[pos .. pos + size) -> out[off ..], line offsets rebased from the tile's trailer.
+__global__ void k_gather_tiles(const uint8_t* __restrict__ log, uint8_t* __restrict__ out, const Ctrl* __restrict__ ctrl,
+                               const unsigned long long* __restrict__ rec_pos, const unsigned long long* __restrict__ rec_size,
+                               const unsigned long long* __restrict__ rec_lines, const unsigned long long* __restrict__ off_b,
+                               const unsigned long long* __restrict__ off_l, unsigned long long* __restrict__ line_offs, int n_tiles) {
+    const int t = (int)(((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (t >= n_tiles || ctrl->irregular || ctrl->cap_exceeded) return;
+    const unsigned long long pos = rec_pos[t], ob = off_b[t], ol = off_l[t];
+    const int size = (int)rec_size[t], nl = (int)rec_lines[t];
+    const uint8_t* src = log + pos;
+    uint8_t* dst = out + ob;
+    const int head = min((int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), size);
+    if (lane < head) dst[lane] = src[lane];
+    const int nwords = (size - head) >> 2;
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(src + head);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
+    const int sh = 8 * (int)(sa & 3);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+    for (int k = lane; k < nwords; k += 32) dw[k] = __funnelshift_r(sw[k], sw[k + 1], sh);   // the log has slack behind it
+    const int tail0 = head + 4 * nwords;
+    if (lane < size - tail0) dst[tail0 + lane] = src[tail0 + lane];
+    for (int l = lane; l < nl; l += 32) {
+        const unsigned o16 = (unsigned)src[size + 2 * l] | ((unsigned)src[size + 2 * l + 1] << 8);
+        line_offs[ol + (unsigned long long)l] = ob + (unsigned long long)o16;
     }
 }
 
@@ -708,26 +757,44 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
     }
     const size_t n_tiles = (in_len + kTile - 1) / kTile;
     const size_t lines_cap = in_len / 64 + 1024;
-    DevBuf& ws = ctx->ws[10];
-    const size_t off_s1 = 256, off_s2 = off_s1 + ((n_tiles * 4 + 255) & ~size_t(255));
-    const size_t off_lines = off_s2 + n_tiles * 16, total_ws = off_lines + lines_cap * 8;
+    DevBuf &ws = ctx->ws[10], &b_log = ctx->ws[11], &b_scr = ctx->ws[1];
+    const size_t off_s1 = 256, off_rec = off_s1 + ((n_tiles * 4 + 255) & ~size_t(255));
+    const size_t off_zero_end = off_rec + 3 * n_tiles * 8;                       // ctrl, s1, rec_*: zeroed every call
+    const size_t off_scan = off_zero_end, off_lines = off_scan + 2 * n_tiles * 8, total_ws = off_lines + lines_cap * 8;
     int rc = dev_reserve(ctx, &ws, total_ws);
     if (rc) return rc;
+    const size_t log_cap = out_cap + 2 * lines_cap + 64;
+    if ((rc = dev_reserve(ctx, &b_log, log_cap + 64))) return rc;
     uint8_t* base = (uint8_t*)ws.p;
     Ctrl* ctrl = (Ctrl*)base;
-    VCFC_CUDA(ctx, cudaMemsetAsync(base, 0, off_lines, stream));
-    unsigned long long lc = lines_cap;
-    VCFC_CUDA(ctx, cudaMemcpyAsync(&ctrl->line_cap, &lc, sizeof(lc), cudaMemcpyHostToDevice, stream));
+    unsigned long long* rec_pos = (unsigned long long*)(base + off_rec);
+    unsigned long long *rec_size = rec_pos + n_tiles, *rec_lines = rec_size + n_tiles;
+    unsigned long long *off_b = (unsigned long long*)(base + off_scan), *off_l = off_b + n_tiles;
+    unsigned long long* line_offs = (unsigned long long*)(base + off_lines);
+    VCFC_CUDA(ctx, cudaMemsetAsync(base, 0, off_zero_end, stream));
+    unsigned long long caps[3] = {lines_cap, 0ull, (unsigned long long)log_cap};  // line_cap, log_cursor, log_cap
+    VCFC_CUDA(ctx, cudaMemcpyAsync(&ctrl->line_cap, caps, sizeof(caps), cudaMemcpyHostToDevice, stream));
+    static int resident = 0;        // CTAs that are guaranteed to be co-resident (look-back #1 spins on its neighbour)
+    if (!resident) {
+        int per_sm = 0;
+        VCFC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_tiles, kThreads, sizeof(Smem)));
+        resident = std::max(1, per_sm) * ctx->sm_count;
+    }
+    const unsigned grid = (unsigned)std::min<size_t>(n_tiles, (size_t)resident);
     if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeEncode], stream);
-    k_encode_tiles<<<(unsigned)n_tiles, kThreads, sizeof(Smem), stream>>>(
-        d_in, (long long)in_len, d_out, (unsigned long long)out_cap, ctrl, (unsigned int*)(base + off_s1),
-        (unsigned long long*)(base + off_s2), (unsigned long long*)(base + off_lines), (int)n_tiles);
+    k_encode_tiles<<<grid, kThreads, sizeof(Smem), stream>>>(d_in, (long long)in_len, (uint8_t*)b_log.p, ctrl,
+                                                             (unsigned int*)(base + off_s1), rec_pos, rec_size, rec_lines, (int)n_tiles);
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeEncode + 1], stream); ctx->ev_pending[kTimeEncode] = 1; }
+    ctx->launches += 1;
+    if ((rc = scan_exclusive_u64(ctx, (const uint64_t*)rec_size, (uint64_t*)off_b, n_tiles, (uint64_t*)&ctrl->total_bytes, &b_scr, stream))) return rc;
+    if ((rc = scan_exclusive_u64(ctx, (const uint64_t*)rec_lines, (uint64_t*)off_l, n_tiles, (uint64_t*)&ctrl->total_lines, &b_scr, stream))) return rc;
+    k_enc_totals<<<1, 1, 0, stream>>>(ctrl, (unsigned long long)out_cap);
+    k_gather_tiles<<<(unsigned)((n_tiles * 32 + 255) / 256), 256, 0, stream>>>((const uint8_t*)b_log.p, d_out, ctrl, rec_pos, rec_size,
+                                                                               rec_lines, off_b, off_l, line_offs, (int)n_tiles);
     unsigned pb = (unsigned)std::min<size_t>((lines_cap + 255) / 256, 148 * 8);
-    k_patch_headers<<<pb, 256, 0, stream>>>(d_out, (const unsigned long long*)(base + off_lines), ctrl, d_line_out_offsets,
-                                            (unsigned long long)line_cap, d_result);
+    k_patch_headers<<<pb, 256, 0, stream>>>(d_out, line_offs, ctrl, d_line_out_offsets, (unsigned long long)line_cap, d_result);
     k_finish_line2big<<<1, 1, 0, stream>>>(ctrl, d_result);
-    ctx->launches += 3;
+    ctx->launches += 4;
     VCFC_CUDA(ctx, cudaGetLastError());
     return VCFC_OK;
 }
