@@ -33,13 +33,13 @@ constexpr int kHalo = 1024;
 constexpr int kPad = 32;                // zeroed bytes in front of / behind the window
 constexpr int kMaxReq = kHalo - 64;     // longest required section taken by this path
 constexpr int kWin = kTile + 2 * kHalo + 2 * kPad;
-constexpr int kStage = 12288;           // smem staging; tiles that expand beyond it store straight to HBM
+constexpr int kStage = 8192;            // smem staging; tiles that expand beyond it store straight to HBM
 constexpr int kMaxNl = 30;              // newlines per tile taken by this path (lines >= ~0.5 KB)
 constexpr int kMaxSeg = kMaxNl + 2;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxItems = 2 * kThreads; // two items per thread, held in registers
-constexpr int kCtasPerSm = 4;
+constexpr int kCtasPerSm = 5;
 
 enum { kCutLine = 0, kCutSample = 1, kCutSampleFirst = 2, kCutEnd = 3, kCutBad = 4 };
 constexpr int kNone = 7;                // "no open run" class
@@ -81,7 +81,7 @@ struct Smem {
     unsigned long long excl_bytes, excl_lines;
     int skip_write;
 };
-static_assert(sizeof(Smem) <= 53 * 1024, "4 CTAs per SM need <= ~56 KB each");
+static_assert(sizeof(Smem) <= 44 * 1024, "5 CTAs per SM need <= ~44.4 KB each");
 
 __device__ __forceinline__ bool is_sep(uint32_t c) { return c == '\t' || c == '\n'; }
 
