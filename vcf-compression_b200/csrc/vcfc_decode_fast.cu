@@ -339,10 +339,12 @@ struct Writer {
         *wp++ = acc | (P << (8 * fill));
         const uint32_t Q = __funnelshift_r(P, P, 8 * ((4 - fill) & 3));  // the stream, re-aligned to image words
         int m = nw - 1;
-        while (m > 0 && (reinterpret_cast<uintptr_t>(wp) & 15)) { *wp++ = Q; m--; }
-        const uint4 Q4 = make_uint4(Q, Q, Q, Q);
-        while (m >= 4) { *reinterpret_cast<uint4*>(wp) = Q4; wp += 4; m -= 4; }
-        while (m > 0) { *wp++ = Q; m--; }
+        if (m > 0) {
+            while (m > 0 && (reinterpret_cast<uintptr_t>(wp) & 15)) { *wp++ = Q; m--; }
+            const uint4 Q4 = make_uint4(Q, Q, Q, Q);
+            while (m >= 4) { *reinterpret_cast<uint4*>(wp) = Q4; wp += 4; m -= 4; }
+            while (m > 0) { *wp++ = Q; m--; }
+        }
         acc = rem ? (Q & ((1u << (8 * rem)) - 1u)) : 0u;
         fill = rem;
     }
@@ -469,25 +471,38 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
                 while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)(tab[mid] >> 1) <= x) lo = mid; else hi = mid; }
                 int ci = lo << 4, cur = (int)(tab[lo] >> 1);
                 bool payload = (tab[lo] & 1u) != 0;
-                while (x < x_end) {
+                // skip what lies before x inside the chunk (tight loop), then emit
+                for (;;) {
                     const uint32_t c = lp[tb + ci];
                     if (payload) {
-                        if (cur == x) { wr.byte(c); x++; }
+                        if (cur == x) break;
                         cur++; ci++;
                         if (c == 9u || c == 10u) payload = false;
                     } else if (c >= 0xE0u) {
                         payload = true; ci++;
                     } else {
                         const int len = 4 * (int)(c < 0x80u ? c : (c & 0x1Fu));
-                        if (cur + len > x) {
-                            const int stop = min(cur + len, x_end);
-                            const bool nl = stop > x_nl;               // this run carries the line's final byte
-                            wr.run(sample_word(c), (x - cur) & 3, stop - x - (nl ? 1 : 0));
-                            if (nl) wr.byte('\n');
-                            x = stop;
-                            if (stop < cur + len) break;
-                        }
+                        if (cur + len > x) break;
                         cur += len; ci++;
+                    }
+                }
+                while (x < x_end) {
+                    const uint32_t c = lp[tb + ci];
+                    if (payload) {
+                        wr.byte(c); x++;
+                        ci++;
+                        if (c == 9u || c == 10u) payload = false;
+                        cur = x;
+                    } else if (c >= 0xE0u) {
+                        payload = true; ci++;
+                    } else {
+                        const int len = 4 * (int)(c < 0x80u ? c : (c & 0x1Fu));
+                        const int stop = min(cur + len, x_end);
+                        const bool nl = stop > x_nl;                   // this run carries the line's final byte
+                        wr.run(sample_word(c), (x - cur) & 3, stop - x - (nl ? 1 : 0));
+                        if (nl) wr.byte('\n');
+                        x = stop;
+                        cur += len; ci++;                              // (a run cut by x_end also ends the loop)
                     }
                 }
             }
