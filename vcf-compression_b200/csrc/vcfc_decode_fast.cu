@@ -25,7 +25,7 @@
 namespace vcfc {
 namespace dec {
 
-constexpr int kSeg = 16384;             // D1 segment (compressed bytes)
+constexpr int kSeg = 2048;              // D1 segment (compressed bytes): one thread each, so keep the serial walk short
 constexpr int kTile = 16384;            // D4 output tile
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
@@ -243,18 +243,28 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
             int nb = (int)(tn - off);
             nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
             uint8_t b[16];
+            if (nb > 0) {       // five aligned 32-bit loads instead of sixteen byte loads; bytes past the line are never used
+                const uintptr_t ga = reinterpret_cast<uintptr_t>(p + tb + off);
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
+                const int sh = 8 * (int)(ga & 3);
+                const int nwd = (nb + (int)(ga & 3) + 3) >> 2;          // aligned words that hold the chunk's nb bytes
+                uint32_t w0 = wp[0], w1 = nwd > 1 ? wp[1] : 0u, w2 = nwd > 2 ? wp[2] : 0u, w3 = nwd > 3 ? wp[3] : 0u,
+                         w4 = nwd > 4 ? wp[4] : 0u;
+                const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                                       __funnelshift_r(w3, w4, sh)};
 #pragma unroll
-            for (int i = 0; i < 16; i++) b[i] = i < nb ? p[tb + off + i] : 0;
-            const int kind = last_setter_kind(b, nb);
+                for (int i = 0; i < 16; i++) b[i] = (uint8_t)(v[i >> 2] >> (8 * (i & 3)));
+            }
+            const int kind = nb > 0 ? last_setter_kind(b, nb) : 0;
             // state at chunk start: last setter of the nearest lower lane that has one, else the carry
             const unsigned has = __ballot_sync(0xffffffffu, kind != 0);
             const unsigned below = has & ((1u << lane) - 1u);
             const int src = below ? 31 - __clz(below) : 0;
             const int k_src = __shfl_sync(0xffffffffu, kind, src);
             const int k_in = below ? k_src : carry_kind;
-            unsigned o, ns;
-            int e;
-            chunk_measure(b, nb, k_in == 1, off + nb == tn && nb > 0, &o, &ns, &e);
+            unsigned o = 0, ns = 0;
+            int e = 0;
+            if (nb > 0) chunk_measure(b, nb, k_in == 1, off + nb == tn, &o, &ns, &e);
             err_any |= e;
             // chunk table (text offset << 1 | payload state at the chunk's first byte), consumed by k_dec_expand;
             // line k owns the slots [(ls >> 4) + k, ...): disjoint between lines, <= clen / 16 + 1 of them
