@@ -72,7 +72,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         if self.nv:

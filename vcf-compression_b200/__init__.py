@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
         "vcfc_last_kernel_ms": (C.c_float, [vp, i]),
         "vcfc_launch_count": (u64, [vp]),
         "vcfc_last_path": (i, [vp]),
+        "vcfc_last_reject_reason": (i, [vp]),
         "vcfc_force_generic": (i, [vp, i]),
     }
     for name, (res, args) in sig.items():
@@ -101,6 +102,15 @@ def _ptr(b):
     if isinstance(b, bytearray):
         return C.cast((C.c_char * len(b)).from_buffer(b), C.c_void_p)
     return C.c_void_p(b.ctypes.data)     # numpy
+
+
+def _stream(handle):
+    """cudaStream_t for the ABI: None -> the context's own stream (NULL); 0 -> the legacy default stream, which is what
+    torch.cuda.current_stream().cuda_stream reports for torch's default stream (cudaStreamLegacy = 1 names it explicitly,
+    because a NULL stream argument means "the context's stream" in this ABI); anything else is passed through."""
+    if handle is None:
+        return C.c_void_p(None)
+    return C.c_void_p(1 if handle == 0 else handle)
 
 
 class Codec:
@@ -138,6 +148,10 @@ class Codec:
     @property
     def launches(self) -> int:
         return lib().vcfc_launch_count(self._ctx)
+
+    @property
+    def last_reject_reason(self) -> int:
+        return lib().vcfc_last_reject_reason(self._ctx)
 
     def force_generic(self, on: bool):
         lib().vcfc_force_generic(self._ctx, int(on))
@@ -201,28 +215,28 @@ class Codec:
                    d_offsets: int = 0, line_cap: int = 0):
         rc = lib().vcfc_encode_block_dev(self._ctx, C.c_void_p(d_in), in_len, C.c_void_p(d_out), out_cap,
                                          C.c_void_p(d_offsets or None), line_cap, C.c_void_p(d_result),
-                                         C.c_void_p(stream or None))
+                                         _stream(stream))
         if rc != OK:
             raise VcfcError(rc, self.cuda_error() if rc == E_CUDA else strerror(rc))
 
     def decode_dev(self, d_in: int, in_len: int, sample_count: int, d_out: int, out_cap: int, d_result: int,
                    stream: int = 0):
         rc = lib().vcfc_decode_block_dev(self._ctx, C.c_void_p(d_in), in_len, sample_count, C.c_void_p(d_out), out_cap,
-                                         C.c_void_p(d_result), C.c_void_p(stream or None))
+                                         C.c_void_p(d_result), _stream(stream))
         if rc != OK:
             raise VcfcError(rc, self.cuda_error() if rc == E_CUDA else strerror(rc))
 
     def decode_size_dev(self, d_in: int, in_len: int, sample_count: int, stream: int = 0) -> Result:
         r = Result()
         rc = lib().vcfc_decode_size_dev(self._ctx, C.c_void_p(d_in), in_len, sample_count, C.byref(r),
-                                        C.c_void_p(stream or None))
+                                        _stream(stream))
         if rc != OK:
             raise VcfcError(rc, self.cuda_error() if rc == E_CUDA else strerror(rc))
         return r
 
     def fetch_result(self, d_result: int, stream: int = 0) -> Result:
         r = Result()
-        rc = lib().vcfc_fetch_result(self._ctx, C.c_void_p(d_result), C.byref(r), C.c_void_p(stream or None))
+        rc = lib().vcfc_fetch_result(self._ctx, C.c_void_p(d_result), C.byref(r), _stream(stream))
         if rc != OK:
             raise VcfcError(rc, self.cuda_error())
         return r

@@ -136,6 +136,7 @@ float vcfc_last_kernel_ms(vcfc_ctx* ctx, int which) {
 }
 uint64_t vcfc_launch_count(const vcfc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int vcfc_last_path(const vcfc_ctx* ctx) { return ctx ? ctx->last_path : 0; }
+int vcfc_last_reject_reason(const vcfc_ctx* ctx) { return ctx ? ctx->last_reject : 0; }
 int vcfc_force_generic(vcfc_ctx* ctx, int on) {
     if (!ctx) return VCFC_E_ARG;
     ctx->force_generic = on;
@@ -156,6 +157,7 @@ static int peek_status(vcfc_ctx* ctx, const vcfc_result* d_result, cudaStream_t 
     VCFC_CUDA(ctx, cudaMemcpyAsync(ctx->h_result + 2, d_result, sizeof(vcfc_result), cudaMemcpyDeviceToHost, st));
     VCFC_CUDA(ctx, cudaStreamSynchronize(st));
     *status = ctx->h_result[2].status;
+    if (*status == kStatusIrregular) ctx->last_reject = ctx->h_result[2].reserved;
     return VCFC_OK;
 }
 

@@ -218,7 +218,7 @@ __device__ __forceinline__ void chunk_measure(const uint8_t* b, int nb, bool pay
 // ---- D2: per-line validation and text size (one warp per line) ----------------------------------------------
 __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ line_start,
                             unsigned long long n_lines, unsigned long long sample_count, unsigned long long* __restrict__ sizes,
-                            unsigned* __restrict__ ctab, Ctrl* __restrict__ ctrl) {
+                            unsigned* __restrict__ ctab, unsigned* __restrict__ rq_arr, Ctrl* __restrict__ ctrl) {
     const unsigned long long k = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (k >= n_lines) return;
@@ -226,7 +226,8 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
     const uint8_t* p = in + ls;
     const long long clen = (long long)(le - ls);
     const long long rq = hdr_len(p + 4);
-    bool bad = clen > kCmax || rq < 1 || rq + 9 > clen + 0;
+    bool bad = rq < 1 || rq + 9 > clen || clen > 0x7fffffffll;
+    if (lane == 0) rq_arr[k] = (unsigned)(bad ? 0 : rq);
     // required section: exactly 9 tabs (compress.cpp:820-828; the 8-tab form means no samples -> generic path)
     unsigned tabs = 0;
     if (!bad) for (long long i = lane; i < rq; i += 32) tabs += (p[8 + i] == '\t');
@@ -289,14 +290,33 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
     }
 }
 
-// first line of every output tile: line k covers text bytes [off[k], off[k+1])
+// First line of every output tile (line k covers text bytes [off[k], off[k+1])) and, when the tile starts inside
+// that line's sample text, the chunk that holds the tile's first byte: a long line is then staged from that chunk
+// on instead of from its start (kWholeLine otherwise).
+constexpr unsigned kWholeLine = 0xFFFFFFFFu;
 __global__ void k_dec_tilemap(const unsigned long long* __restrict__ off, unsigned long long n_lines, unsigned long long total,
-                              unsigned int* __restrict__ first_line) {
+                              const unsigned long long* __restrict__ line_start, const unsigned* __restrict__ rq_arr,
+                              const unsigned* __restrict__ gtab, unsigned int* __restrict__ first_line,
+                              unsigned int* __restrict__ first_chunk) {
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_lines) return;
     const unsigned long long a = off[k], b = k + 1 < n_lines ? off[k + 1] : total;
     if (b == a) return;
-    for (unsigned long long t = (a + kTile - 1) / kTile; t * kTile < b; t++) first_line[t] = (unsigned int)k;
+    const unsigned long long ls = line_start[k];
+    const long long rq = rq_arr[k];
+    const int nch = (int)(((long long)(line_start[k + 1] - ls) - 8 - rq + 15) >> 4);
+    const unsigned* tab = gtab + (ls >> 4) + k;
+    for (unsigned long long t = (a + kTile - 1) / kTile; t * kTile < b; t++) {
+        first_line[t] = (unsigned int)k;
+        const long long xs = (long long)(t * kTile - a) - rq;          // text offset of the tile start inside the sample text
+        unsigned fc = kWholeLine;
+        if (xs >= 0) {
+            int lo = 0, hi = nch;
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((long long)(tab[mid] >> 1) <= xs) lo = mid; else hi = mid; }
+            fc = (unsigned)lo;
+        }
+        first_chunk[t] = fc;
+    }
 }
 
 // ---- D4: expansion, one CTA per output tile --------------------------------------------------------------------
@@ -319,6 +339,9 @@ struct Smem {
     int l_coff[kMaxL + 2];                   // offset of its compressed bytes in cbuf
     int l_ctab[kMaxL + 1];                   // its first chunk table slot
     int n_batch, more;
+    int staged;                              // compressed bytes of the batch held in cbuf
+    int c_first, rq0;                        // first line staged from chunk c_first of its token region (-1: from its start)
+    unsigned long long c_lo;                 // block offset of cbuf's first staged byte
 };
 
 __device__ __forceinline__ uint32_t sample_word(uint32_t tok) {      // token byte -> "x|y\t" little-endian
@@ -368,7 +391,8 @@ struct Writer {
 __global__ void __launch_bounds__(kThreads, 4)
 k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ line_start,
              const unsigned long long* __restrict__ off, unsigned long long n_lines, unsigned long long total,
-             const unsigned int* __restrict__ first_line, const unsigned* __restrict__ gtab, uint8_t* __restrict__ out,
+             const unsigned int* __restrict__ first_line, const unsigned int* __restrict__ first_chunk,
+             const unsigned* __restrict__ rq_arr, const unsigned* __restrict__ gtab, uint8_t* __restrict__ out,
              const Ctrl* __restrict__ ctrl) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -379,6 +403,7 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
     const unsigned long long T1 = T0 + (unsigned long long)tile_len;
     const int s_lo = tid * kSpan, s_hi = min(s_lo + kSpan, tile_len);   // this thread's span of the tile image
     unsigned long long k0 = first_line[blockIdx.x];
+    unsigned fc_tile = first_chunk[blockIdx.x];         // applies to the first batch's first line only
     Writer wr;
     wr.wp = reinterpret_cast<uint32_t*>(sm.stage + s_lo);
     wr.acc = 0;
@@ -386,17 +411,21 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
 
     for (;;) {
         // (1) line table entries of the next batch: lines k0 .. k0 + nb - 1 overlap the tile
-        unsigned long long c_lo = 0;
         if (warp == 0) {
             const unsigned long long kk = k0 + (unsigned long long)lane;
             const unsigned long long o = kk < n_lines ? off[kk] : total;
             const unsigned long long ls = kk <= n_lines ? line_start[kk] : 0ull;
-            c_lo = __shfl_sync(0xffffffffu, ls, 0);
+            const unsigned long long ls0 = __shfl_sync(0xffffffffu, ls, 0);
+            // a long first line whose text began before the tile is staged from the chunk that holds the tile's first byte
+            unsigned long long s0 = ls0;
+            int rq0 = 0;
+            if (fc_tile != kWholeLine) { rq0 = (int)rq_arr[k0]; s0 = ls0 + 8ull + (unsigned long long)rq0 + 16ull * fc_tile; }
             const bool overlaps = kk < n_lines && o < T1;
             unsigned m = __ballot_sync(0xffffffffu, overlaps) & 0x7fffffffu;         // lane 31 only supplies the end of line 30
             int nb = __popc(m);                                                        // off[] is monotone: a prefix of the lanes
-            // the batch's compressed bytes must fit in cbuf (a single line always does, k_dec_sizes checked it)
-            const unsigned fits = __ballot_sync(0xffffffffu, ls - c_lo <= (unsigned long long)kCmax);
+            // later lines are staged whole, so they must fit behind the first; the first may be cut at kCmax
+            // (kCmax compressed bytes always expand to at least a tile of text)
+            const unsigned fits = __ballot_sync(0xffffffffu, ls >= s0 && ls - s0 <= (unsigned long long)kCmax);
             while (nb > 1 && !((fits >> nb) & 1u)) nb--;
             const unsigned long long o_next = __shfl_down_sync(0xffffffffu, o, 1);
             const unsigned long long ls_next = __shfl_down_sync(0xffffffffu, ls, 1);
@@ -404,57 +433,47 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
                 sm.l_pos[lane] = (int)((long long)o - (long long)T0);
                 sm.l_end[lane] = (int)(o_next < T1 ? o_next - T0 : (unsigned long long)tile_len);
                 sm.l_last[lane] = (int)min((long long)o_next - 1 - (long long)T0, (long long)(1 << 30));
-                sm.l_coff[lane] = (int)(ls - c_lo);
-                if (lane == nb - 1) sm.l_coff[nb] = (int)(ls_next - c_lo);
+                sm.l_coff[lane] = lane == 0 ? 0 : (int)(ls - s0);
+                if (lane == nb - 1) sm.l_coff[nb] = (int)min(ls_next - s0, (unsigned long long)0x7fffffff);
             }
             const unsigned long long o_after = __shfl_sync(0xffffffffu, o, nb);       // nb <= 31
             if (lane == 0) {
                 sm.n_batch = nb;
                 sm.more = (nb > 0 && k0 + (unsigned long long)nb < n_lines && o_after < T1) ? 1 : 0;   // another batch follows
+                sm.c_lo = s0;
+                sm.c_first = fc_tile != kWholeLine ? (int)fc_tile : -1;
+                sm.rq0 = rq0;
             }
         }
         __syncthreads();
         const int nb = sm.n_batch;
         if (nb == 0) break;
-        c_lo = line_start[k0];
+        const unsigned long long c_lo = sm.c_lo;
+        const int c_first = sm.c_first;
         // (2) stage the batch's compressed bytes; cbuf keeps the source's 16-byte phase so both sides are aligned
         const int phase = (int)(reinterpret_cast<uintptr_t>(in + c_lo) & 15);
+        const int staged = min(sm.l_coff[nb], kCmax);
         {
-            const int clen = sm.l_coff[nb];
             const uint8_t* src = in + c_lo;
-            const int head = min((16 - phase) & 15, clen);
+            const int head = min((16 - phase) & 15, staged);
             if (tid < head) sm.cbuf[phase + tid] = src[tid];
-            const int n16 = (clen - head) >> 4;
+            const int n16 = (staged - head) >> 4;
             const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
             uint4* d4 = reinterpret_cast<uint4*>(sm.cbuf + phase + head);
             for (int i = tid; i < n16; i += kThreads) d4[i] = s4[i];
             const int t0 = head + 16 * n16;
-            if (tid < clen - t0) sm.cbuf[phase + t0 + tid] = src[t0 + tid];
+            if (tid < staged - t0) sm.cbuf[phase + t0 + tid] = src[t0 + tid];
         }
-        __syncthreads();
-        // chunk table slots per line (tiny: nb <= 31)
-        if (warp == 0) {
-            int nch = 0;
-            if (lane < nb) {
-                const uint8_t* lp = sm.cbuf + phase + sm.l_coff[lane];
-                const int rq = (int)hdr_len(lp + 4);
-                nch = ((sm.l_coff[lane + 1] - sm.l_coff[lane]) - 8 - rq + 15) >> 4;
-            }
-            int inc = nch;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-            if (lane < nb) sm.l_ctab[lane] = inc - nch;
-        }
-        __syncthreads();
-        // (3) chunk tables of the batch's lines, built once per line by k_dec_sizes: copy them in
+        // (3) chunk tables of the batch's lines (built once per line by k_dec_sizes): copy the staged part.
+        //     Line li's entries go to slot (l_coff >> 4) + li, the global table's rule relative to the batch.
         for (int li = warp; li < nb; li += kWarps) {
-            const uint8_t* lp = sm.cbuf + phase + sm.l_coff[li];
-            const int clen = sm.l_coff[li + 1] - sm.l_coff[li];
-            const int rq = (int)hdr_len(lp + 4);
-            const int nch = (clen - 8 - rq + 15) >> 4;
-            const unsigned* src = gtab + ((c_lo + (unsigned long long)sm.l_coff[li]) >> 4) + (k0 + (unsigned long long)li);
-            unsigned* tab = sm.ctab + sm.l_ctab[li];
-            for (int i = lane; i < nch; i += 32) tab[i] = src[i];
+            const int coff = sm.l_coff[li];
+            const int avail = min(sm.l_coff[li + 1], staged) - coff;          // staged bytes of this line
+            const int nslots = (avail >> 4) + 1;
+            const unsigned long long lsk = li == 0 ? line_start[k0] : c_lo + (unsigned long long)coff;
+            const unsigned* src = gtab + (lsk >> 4) + (k0 + (unsigned long long)li) + (li == 0 && c_first >= 0 ? c_first : 0);
+            unsigned* tab = sm.ctab + (coff >> 4) + li;
+            for (int i = lane; i < nslots; i += 32) tab[i] = src[i];
         }
         __syncthreads();
         // (4) generate: the lines of the batch that intersect this thread's span, strictly left to right
@@ -464,20 +483,25 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
             if (lpos >= s_hi) break;
             const int g_lo = max(s_lo, max(lpos, 0)), g_hi = min(s_hi, lend);
             if (g_lo >= g_hi) continue;
-            const uint8_t* lp = sm.cbuf + phase + sm.l_coff[li];
-            const int clen = sm.l_coff[li + 1] - sm.l_coff[li];
-            const int rq = (int)hdr_len(lp + 4);
-            const int tb = 8 + rq, tn = clen - tb;
+            const int coff = sm.l_coff[li];
+            const bool cont = li == 0 && c_first >= 0;                // the line is staged from chunk c_first of its tokens
+            const uint8_t* lp = sm.cbuf + phase + coff;               // whole-line mode: the line's first byte
+            const int rq = cont ? sm.rq0 : (int)hdr_len(lp + 4);
+            const int tb = cont ? -16 * c_first : 8 + rq;             // lp[tb + ci] = token byte ci of the line
+            const int avail = min(sm.l_coff[li + 1], staged) - coff;  // staged bytes of this line
             const int tpos = lpos + rq;                               // tile position of the first sample's text
             int sp = g_lo;
             // required section passes through (compress.cpp:788-807)
             for (; sp < g_hi && sp < tpos; sp++) wr.byte(lp[8 + (sp - lpos)]);
             if (sp < g_hi) {
-                const unsigned* tab = sm.ctab + sm.l_ctab[li];
+                const int cbase = cont ? c_first : 0;                 // first chunk whose table entry is in smem
+                const unsigned* tab = sm.ctab + (coff >> 4) + li - cbase;
                 int x = sp - tpos;                                    // text offset inside the sample text
                 const int x_end = g_hi - tpos;
                 const int x_nl = sm.l_last[li] - tpos;                // the line's last text byte: '\n' instead of the tab
-                int lo = 0, hi = (tn + 15) >> 4;                      // chunk whose start offset is the last one <= x
+                // chunk whose start offset is the last one <= x, among the staged chunks
+                int lo = cbase, hi = cbase + ((avail - (cont ? 0 : 8 + rq) + 15) >> 4);
+                if (hi <= lo) hi = lo + 1;
                 while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((int)(tab[mid] >> 1) <= x) lo = mid; else hi = mid; }
                 int ci = lo << 4, cur = (int)(tab[lo] >> 1);
                 bool payload = (tab[lo] & 1u) != 0;
@@ -521,6 +545,7 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
         __syncthreads();
         if (!more) break;
         k0 += (unsigned long long)nb;
+        fc_tile = kWholeLine;
     }
 
     if (wr.fill) wr.flush_tail();
@@ -571,7 +596,7 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
     int rc;
     const long long n = (long long)in_len, n_seg = (n + kSeg - 1) / kSeg;
     DevBuf &b_ctrl = ctx->ws[2], &b_seg = ctx->ws[0], &b_scr = ctx->ws[1], &b_ls = ctx->ws[3], &b_sizes = ctx->ws[4],
-           &b_offs = ctx->ws[7], &b_tiles = ctx->ws[5], &b_tab = ctx->ws[8];
+           &b_offs = ctx->ws[7], &b_tiles = ctx->ws[5], &b_tab = ctx->ws[8], &b_rq = ctx->ws[6];
     if ((rc = dev_reserve(ctx, &b_ctrl, sizeof(Ctrl) + 64))) return rc;
     if ((rc = dev_reserve(ctx, &b_seg, (size_t)n_seg * 8 * 4 + 64))) return rc;
     Ctrl* ctrl = (Ctrl*)b_ctrl.p;
@@ -601,10 +626,11 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
     if ((rc = dev_reserve(ctx, &b_sizes, (n_lines + 1) * 8))) return rc;
     if ((rc = dev_reserve(ctx, &b_offs, (n_lines + 1) * 8))) return rc;
     if ((rc = dev_reserve(ctx, &b_tab, ((size_t)in_len / 16 + n_lines + 8) * 4))) return rc;
+    if ((rc = dev_reserve(ctx, &b_rq, (n_lines + 2) * 4))) return rc;
     unsigned long long* line_start = (unsigned long long*)b_ls.p;
     k_dec_fill<<<gs, 128, 0, stream>>>(d_in, n, n_seg, cand, base, line_start, n_lines, ctrl);
     k_dec_sizes<<<(unsigned)((n_lines * 32 + 127) / 128), 128, 0, stream>>>(d_in, line_start, n_lines, sample_count,
-                                                                             (unsigned long long*)b_sizes.p, (unsigned*)b_tab.p, ctrl);
+                                                                             (unsigned long long*)b_sizes.p, (unsigned*)b_tab.p, (unsigned*)b_rq.p, ctrl);
     ctx->launches += 2;
     if ((rc = scan_exclusive_u64(ctx, (uint64_t*)b_sizes.p, (uint64_t*)b_offs.p, (size_t)n_lines, (uint64_t*)&ctrl->total_out, &b_scr, stream)))
         return rc;
@@ -623,12 +649,14 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
         return VCFC_OK;
     }
     const unsigned long long n_tiles = (total + kTile - 1) / kTile;
-    if ((rc = dev_reserve(ctx, &b_tiles, n_tiles * 4 + 64))) return rc;
-    k_dec_tilemap<<<(unsigned)((n_lines + 255) / 256), 256, 0, stream>>>((unsigned long long*)b_offs.p, n_lines, total,
-                                                                          (unsigned int*)b_tiles.p);
+    if ((rc = dev_reserve(ctx, &b_tiles, n_tiles * 8 + 64))) return rc;
+    unsigned int* first_chunk = (unsigned int*)b_tiles.p + n_tiles;
+    k_dec_tilemap<<<(unsigned)((n_lines + 255) / 256), 256, 0, stream>>>((unsigned long long*)b_offs.p, n_lines, total, line_start,
+                                                                          (const unsigned*)b_rq.p, (const unsigned*)b_tab.p,
+                                                                          (unsigned int*)b_tiles.p, first_chunk);
     if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeDecodeExpand], stream);
     k_dec_expand<<<(unsigned)n_tiles, kThreads, sizeof(Smem), stream>>>(d_in, line_start, (unsigned long long*)b_offs.p, n_lines,
-                                                                        total, (unsigned int*)b_tiles.p, (const unsigned*)b_tab.p, d_out, ctrl);
+                                                                        total, (unsigned int*)b_tiles.p, first_chunk, (const unsigned*)b_rq.p, (const unsigned*)b_tab.p, d_out, ctrl);
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeDecodeExpand + 1], stream); ctx->ev_pending[kTimeDecodeExpand] = 1; }
     k_dec_result<<<1, 1, 0, stream>>>(d_result, ctrl, VCFC_OK, total, n_lines);
     ctx->launches += 3;

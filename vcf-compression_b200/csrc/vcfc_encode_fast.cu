@@ -262,7 +262,12 @@ __device__ __forceinline__ void item_classify(Smem& sm, const uint8_t* __restric
         }
     }
     if (kend >= 0 && ((V >> kend) & 1u) && win[base + 4 * kend + 3] != '\n') irr = true;
-    if (irr) sm.irregular = 1;
+    if (irr) sm.irregular = 6;                               // a sample column that is not 3 bytes + separator
+#ifdef VCFC_DEBUG
+    if (irr) printf("REJECT6 tile=%d item=%d seg=%d a=%d e=%d flags=%d blk=%d phase=%d V=%02x Craw=%02x kend=%d n_seg=%d n_items=%d cs=%d ce=%d bytes=%02x %02x %02x %02x %02x %02x %02x %02x\n",
+                    sm.tile, item, si, a, e, flags, blk, phase, V, Craw, kend, sm.n_seg, sm.n_items, sm.cs, sm.ce,
+                    win[base], win[base+1], win[base+2], win[base+3], win[base+4], win[base+5], win[base+6], win[base+7]);
+#endif
     const uint32_t Hd = V & (F | ~(Craw & Q));
     const uint32_t PC = (((Craw << 1) | pc_all) & 0xFFu) & ~F;     // the previous word is a coded sample of this line
     it.V = V; it.C = Craw & V; it.L = L; it.Hd = Hd; it.CL = Hd & PC;
@@ -371,6 +376,7 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
         const int tile_next = tile + G;
         if (tid == 0) {
             sm.irregular = *((volatile int*)&ctrl->irregular);
+            sm.tile = tile;
             sm.n_nl = 0;
             sm.skip_write = 0;
             sm.tile_last_head = kNoHead;
@@ -399,7 +405,7 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
         if (sm.irregular || !was_issued) {     // some tile already gave up: keep the look-back chains alive and move on
             if (tid == 0) {
                 s1[tile] = (2u << 30) | ((unsigned)kNone << 8);
-                atomicExch(&ctrl->irregular, 1);
+                atomicCAS(&ctrl->irregular, 0, 9);
             }
             buf ^= 1;
             __syncthreads();
@@ -416,7 +422,7 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
             if (lane == 0) {
                 if (warp == 0) { sm.cs = (int)(c - wbase); sm.cs_kind = kind; sm.cs_s0 = s0c; }
                 else           { sm.ce = (int)(c - wbase); sm.ce_kind = kind; }
-                if (kind == kCutBad) sm.irregular = 1;
+                if (kind == kCutBad) sm.irregular = 2;
             }
         }
         {
@@ -454,7 +460,7 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
         const int first_partial = (cs_kind == kCutSample || cs_kind == kCutSampleFirst) && cs < ce ? 1 : 0;
         if (warp == 0 && !sm.irregular) {
             int n_nl = sm.n_nl;
-            if (n_nl > kMaxNl) { if (lane == 0) sm.irregular = 1; n_nl = 0; }
+            if (n_nl > kMaxNl) { if (lane == 0) sm.irregular = 3; n_nl = 0; }
             // sort: lane j ends up holding the j-th smallest newline position (and its first-sample offset)
             int q = lane < n_nl ? sm.nlpos[lane] : 0x3fffffff, qs0 = lane < n_nl ? sm.nls0[lane] : -2, rank = 0;
             for (int j = 0; j < n_nl; j++) rank += (__shfl_sync(0xffffffffu, q, j) < q);
@@ -498,7 +504,12 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
                 sg.a = a; sg.e = e; sg.ls = ls; sg.s0 = s0; sg.flags = flags; sg.item0 = inc - nitems; sg.out0 = 0;
             }
             if (lane == 0) {
-                if (irr) sm.irregular = 1;
+                if (irr) sm.irregular = (items > kMaxItems || n_seg > kMaxSeg) ? 5 : 4;
+#ifdef VCFC_DEBUG
+                if (irr) printf("REJECT45 tile=%d n_nl=%d n_seg=%d items=%d cs=%d(k%d) ce=%d(k%d) cs_s0=%d idx_lo=%d n_in=%d n_start=%d nl0=%d s0_0=%d nl1=%d s0_1=%d nl2=%d\n",
+                                sm.tile, sm.n_nl, n_seg, items, cs, cs_kind, ce, sm.ce_kind, sm.cs_s0, idx_lo, n_in, n_start, sm.nlpos[0], sm.nls0[0],
+                                sm.nlpos[1], sm.nls0[1], sm.nlpos[2]);
+#endif
                 else { sm.n_seg = n_seg; sm.n_lines = n_lines; sm.n_items = items; }
             }
         }
@@ -567,7 +578,7 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
                 *((volatile unsigned*)&s1[tile]) = (2u << 30) | ((unsigned)kNone << 8);          // nothing carried out
             }
 #ifdef VCFC_DEBUG
-            printf("tile %d cs=%d(k%d) ce=%d(k%d) bad=%d n_items=%d n_seg=%d tl=%d s1=%08x ein=%d wbase=%lld\n", tile, cs, cs_kind, ce,
+            if (bad) printf("tile %d cs=%d(k%d) ce=%d(k%d) bad=%d n_items=%d n_seg=%d tl=%d s1=%08x ein=%d wbase=%lld\n", tile, cs, cs_kind, ce,
                    sm.ce_kind, (int)bad, sm.n_items, sm.n_seg, tl, s1[tile], ein, wbase);
 #endif
             sm.ein_virtual = ein;
@@ -604,7 +615,7 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
         }
         if (bad) total = 0;
         const bool staged = total <= kStage;                           // else: store straight to HBM once the offset is known
-        if (bad && tid == 0) atomicExch(&ctrl->irregular, 1);
+        if (bad && tid == 0 && atomicCAS(&ctrl->irregular, 0, sm.irregular ? sm.irregular : 9) == 0) ctrl->total_lines = (unsigned long long)tile;   // (diagnostics: first rejecting tile)
 
         // ---- 7. emit into staging; reserve the tile's place in the log with one atomic (no scan chain: the final
         //         positions come from a device scan over the tile records, k_gather_tiles moves the bytes) -----------
@@ -667,7 +678,7 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
 // Final totals from the tile-record scans; decides capacity before any byte reaches the caller's buffer.
 __global__ void k_enc_totals(Ctrl* __restrict__ ctrl, unsigned long long out_cap) {
     if (ctrl->total_bytes > out_cap) ctrl->cap_exceeded = 1;
-    if (ctrl->total_lines > ctrl->line_cap) ctrl->irregular = 1;
+    if (ctrl->total_lines > ctrl->line_cap && !ctrl->irregular) ctrl->irregular = 8;
 }
 
 // One warp per tile: log[pos .. pos + size) -> out[off ..], line offsets rebased from the tile's trailer.
@@ -719,7 +730,7 @@ __global__ void k_patch_headers(uint8_t* __restrict__ out, const unsigned long l
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         res->reserved = 0;
         res->err_line = 0;
-        if (irregular) { res->status = kStatusIrregular; res->out_len = 0; res->n_lines = 0; }
+        if (irregular) { res->status = kStatusIrregular; res->reserved = irregular; res->out_len = 0; res->n_lines = 0; res->err_line = nl; }
         else if (cap)  { res->status = VCFC_E_CAP; res->out_len = total; res->n_lines = 0; }
         else           { res->status = VCFC_OK; res->out_len = total; res->n_lines = nl; }
     }

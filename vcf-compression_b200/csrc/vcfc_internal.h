@@ -45,6 +45,7 @@ struct vcfc_ctx {
     int          ev_pending[vcfc::kTimeSlots] = {0, 0, 0};
     uint64_t     launches    = 0;
     int          last_path   = 0;
+    int          last_reject = 0;     // why the tile kernels last handed a block to the generic kernels
     int          force_generic = 0;
     char         cuda_err[256] = {0};
 };
