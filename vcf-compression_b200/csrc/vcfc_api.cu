@@ -303,9 +303,9 @@ int vcfc_decode_block(vcfc_ctx* ctx, const uint8_t* in, size_t in_len, uint64_t 
     VCFC_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t chunk = env_size("VCFC_DCHUNK_MB", 32) << 20;
     size_t pos = 0, o = 0, lines = 0;
-    int status = VCFC_OK, rc = VCFC_OK;
+    int status = VCFC_OK, rc = VCFC_OK, i = 0;
     uint64_t eline = 0;
-    cudaStream_t st = ctx->copy_stream[0];
+    // Two slots on two streams: while slot s copies its decoded text to the host, slot s^1 uploads and decodes the next chunk.
     while (status == VCFC_OK) {
         // chunk end = last line boundary within `chunk` bytes: walk the 4-byte line-length headers
         // (compress.cpp:270-330); a broken header ends the walk and the device reports it.
@@ -326,30 +326,35 @@ int vcfc_decode_block(vcfc_ctx* ctx, const uint8_t* in, size_t in_len, uint64_t 
         } else if (in_len - end < 8) {
             end = in_len;
         }
+        const int s = i & 1;
+        cudaStream_t st = ctx->copy_stream[s];
+        VCFC_CUDA(ctx, cudaStreamSynchronize(st));      // slot s: its previous D2H has finished
         size_t len = end - pos;
-        if ((rc = dev_reserve(ctx, &ctx->d_in[0], len + 64))) break;
-        VCFC_CUDA(ctx, cudaMemcpyAsync(ctx->d_in[0].p, in + pos, len, cudaMemcpyHostToDevice, st));
-        size_t want = std::min(out_cap - o, std::max<size_t>(len * 10, 1 << 20));
+        if ((rc = dev_reserve(ctx, &ctx->d_in[s], len + 64))) break;
+        VCFC_CUDA(ctx, cudaMemcpyAsync(ctx->d_in[s].p, in + pos, len, cudaMemcpyHostToDevice, st));
+        size_t want = std::min(out_cap - o, std::max<size_t>(len * 20, (size_t)1 << 20));
         vcfc_result r;
+        memset(&r, 0, sizeof(r));
         for (int attempt = 0; attempt < 2; attempt++) {
-            if ((rc = dev_reserve(ctx, &ctx->d_out[0], want + 64))) break;
-            if ((rc = vcfc_decode_block_dev(ctx, (const uint8_t*)ctx->d_in[0].p, len, sample_count, (uint8_t*)ctx->d_out[0].p,
-                                            want, ctx->d_result, st)))
+            if ((rc = dev_reserve(ctx, &ctx->d_out[s], want + 64))) break;
+            if ((rc = vcfc_decode_block_dev(ctx, (const uint8_t*)ctx->d_in[s].p, len, sample_count, (uint8_t*)ctx->d_out[s].p,
+                                            want, ctx->d_result + s, st)))
                 break;
-            if ((rc = vcfc_fetch_result(ctx, ctx->d_result, &r, st))) break;
+            if ((rc = vcfc_fetch_result(ctx, ctx->d_result + s, &r, st))) break;
             if (r.status != VCFC_E_CAP || r.out_len > out_cap - o) break;
             want = r.out_len;                  // the device told us the exact size: retry once
         }
         if (rc) break;
         if (r.status == VCFC_E_CAP) { status = VCFC_E_CAP; break; }
-        if (r.out_len) VCFC_CUDA(ctx, cudaMemcpyAsync(out + o, ctx->d_out[0].p, r.out_len, cudaMemcpyDeviceToHost, st));
-        VCFC_CUDA(ctx, cudaStreamSynchronize(st));
+        if (r.out_len) VCFC_CUDA(ctx, cudaMemcpyAsync(out + o, ctx->d_out[s].p, r.out_len, cudaMemcpyDeviceToHost, st));
         if (r.status != VCFC_OK) { status = r.status; eline = lines + r.err_line; }
         o += r.out_len;
         lines += r.n_lines;
         pos = end;
+        i++;
         if (pos >= in_len) break;
     }
+    for (int s = 0; s < 2; s++) cudaStreamSynchronize(ctx->copy_stream[s]);
     *out_len = o;
     if (n_lines) *n_lines = lines;
     if (err_line) *err_line = eline;

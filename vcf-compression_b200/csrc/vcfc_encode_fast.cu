@@ -793,8 +793,15 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
     }
     const unsigned grid = (unsigned)std::min<size_t>(n_tiles, (size_t)resident);
     if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeEncode], stream);
-    k_encode_tiles<<<grid, kThreads, sizeof(Smem), stream>>>(d_in, (long long)in_len, (uint8_t*)b_log.p, ctrl,
-                                                             (unsigned int*)(base + off_s1), rec_pos, rec_size, rec_lines, (int)n_tiles);
+    {   // cooperative launch: every CTA is resident, which look-back #1 (a CTA spins on its neighbour's tile) relies on
+        const uint8_t* a_in = d_in;
+        long long a_n = (long long)in_len;
+        uint8_t* a_log = (uint8_t*)b_log.p;
+        unsigned int* a_s1 = (unsigned int*)(base + off_s1);
+        int a_tiles = (int)n_tiles;
+        void* args[] = {&a_in, &a_n, &a_log, &ctrl, &a_s1, &rec_pos, &rec_size, &rec_lines, &a_tiles};
+        VCFC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_encode_tiles, dim3(grid), dim3(kThreads), args, sizeof(Smem), stream));
+    }
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeEncode + 1], stream); ctx->ev_pending[kTimeEncode] = 1; }
     ctx->launches += 1;
     if ((rc = scan_exclusive_u64(ctx, (const uint64_t*)rec_size, (uint64_t*)off_b, n_tiles, (uint64_t*)&ctrl->total_bytes, &b_scr, stream))) return rc;
