@@ -327,21 +327,32 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
 
-    def roofline(kms, alg_bytes, step_ms, name):
+    # DRAM traffic per launch: measured once per round with `ncu --set full` on a 100k-line run of this same
+    # workload (profiles/traffic_r1.json: dram__bytes_read.sum + dram__bytes_write.sum next to that run's
+    # algorithmic bytes) and scaled by the algorithmic bytes of this launch; null when the file is absent.
+    try:
+        traffic_ref = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+    except Exception:  # noqa: BLE001
+        traffic_ref = {}
+
+    def roofline(kms, alg_bytes, step_ms, name, which):
         k = [x for x in kms if x and x > 0]
         kern_ms = statistics.mean(k) if k else step_ms
         ach = alg_bytes / (kern_ms * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        tr = traffic_ref.get(which)
+        traffic = alg_bytes * tr["dram_bytes"] / tr["algorithmic_bytes"] if tr and name.startswith("k_") else None
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": (tr or {}).get("source") if traffic else None,
                 "kernel": name, "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / step_ms if step_ms else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
 
-    enc_kernel = "k_encode_tiles (single pass)" if enc_path == pkg.PATH_FAST else "generic line-serial kernels (whole step)"
+    enc_kernel = "k_encode_tiles (single pass over the input)" if enc_path == pkg.PATH_FAST else "generic line-serial kernels (whole step)"
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": enc_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": enc_launches,
            "compression_ratio": tot_in / tot_out, "path": {"encode": enc_path, "decode": dec_path},
            "parity": f"{checked} lines byte-identical to the oracle; full-size device round trip identical",
-           "roofline": roofline(enc_kms, n_in + n_out, enc_ms, enc_kernel)}
+           "roofline": roofline(enc_kms, n_in + n_out, enc_ms, enc_kernel, "encode")}
 
     if not args.no_decode:
         dec_ms, dec_kms, dec_launches, dclocks = timed(
@@ -349,7 +360,7 @@ def main():
         dec_kernel = "k_decode_expand" if dec_path == pkg.PATH_FAST else "generic line-serial kernels (whole step)"
         out["decode"] = {"metric": "uncompressed-VCF GB/s decode", "value": tot_in / (dec_ms * 1e-3) / 1e9, "unit": UNIT,
                          "ms_per_step": dec_ms, "gpu_launches": dec_launches, "clocks": dclocks,
-                         "roofline": roofline(dec_kms, n_in + n_out, dec_ms, dec_kernel)}
+                         "roofline": roofline(dec_kms, n_in + n_out, dec_ms, dec_kernel, "decode")}
         del d_txt
 
     # ---- end to end through the host-pointer C ABI: pinned host buffers, H2D + kernels + D2H timed ----
