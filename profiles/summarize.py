@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Turns gpurun_out/ captures into the small, tracked summaries under profiles/.
 
-    python profiles/summarize.py <round-tag> <launches.csv> <full.ncu-rep> [bench.json]
+    python profiles/summarize.py <round-tag> <launches.csv> <bench.json> <full.ncu-rep> [<full.ncu-rep> ...]
 
 * launches: `ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ ...` over bench.py
   -> per-kernel launch count, total time and SHARE of the step (cold-cache, serialised: shares, not absolutes)
@@ -54,12 +54,13 @@ def full(path):
 
 
 if __name__ == "__main__":
-    tag, lpath, fpath = sys.argv[1:4]
+    tag, lpath, bpath = sys.argv[1:4]
     md = [f"# ncu summaries, {tag}\n"]
     t, n = launches(lpath)
     md.append(f"## Launch list ({n} launches; `--metrics gpu__time_duration.sum --clock-control none`)\n\n{t}\n")
-    md.append(f"## `--set full` capture of the dominant kernels\n{full(fpath)}\n")
-    if len(sys.argv) > 4:
-        md.append("## bench.py line of the same build\n\n```json\n" + json.dumps(json.load(open(sys.argv[4])), indent=1) + "\n```\n")
+    md.append("## `--set full` captures of the dominant kernels (100k-line run of the bench workload)")
+    for fpath in sys.argv[4:]:
+        md.append(full(fpath))
+    md.append("\n## bench.py line of the same build\n\n```json\n" + json.dumps(json.load(open(bpath)), indent=1) + "\n```\n")
     open(f"profiles/{tag}_ncu_summary.md", "w").write("\n".join(md))
     print(f"profiles/{tag}_ncu_summary.md")
