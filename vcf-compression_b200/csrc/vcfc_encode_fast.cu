@@ -28,18 +28,24 @@
 namespace vcfc {
 namespace enc {
 
-constexpr int kTile = 14336;            // nominal input bytes per tile (448 blocks of 32)
+#ifndef VCFC_ENC_TILE
+#define VCFC_ENC_TILE 14336
+#define VCFC_ENC_THREADS 256
+#define VCFC_ENC_STAGE 8192
+#define VCFC_ENC_CTAS 5
+#endif
+constexpr int kTile = VCFC_ENC_TILE;    // nominal input bytes per tile (224 blocks of 64)
 constexpr int kHalo = 1024;
 constexpr int kPad = 32;                // zeroed bytes in front of / behind the window
 constexpr int kMaxReq = kHalo - 64;     // longest required section taken by this path
 constexpr int kWin = kTile + 2 * kHalo + 2 * kPad;
-constexpr int kStage = 8192;            // smem staging; tiles that expand beyond it store straight to HBM
+constexpr int kStage = VCFC_ENC_STAGE;            // smem staging; tiles that expand beyond it store straight to HBM
 constexpr int kMaxNl = 30;              // newlines per tile taken by this path (lines >= ~0.5 KB)
 constexpr int kMaxSeg = kMaxNl + 2;
-constexpr int kThreads = 256;
+constexpr int kThreads = VCFC_ENC_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxItems = 2 * kThreads; // two items per thread, held in registers
-constexpr int kCtasPerSm = 5;
+constexpr int kMaxItems = kThreads;     // one item per thread, held in registers
+constexpr int kCtasPerSm = VCFC_ENC_CTAS;
 
 enum { kCutLine = 0, kCutSample = 1, kCutSampleFirst = 2, kCutEnd = 3, kCutBad = 4 };
 constexpr int kNone = 7;                // "no open run" class
@@ -81,7 +87,8 @@ struct Smem {
     unsigned long long excl_bytes, excl_lines;
     int skip_write;
 };
-static_assert(sizeof(Smem) <= 44 * 1024, "5 CTAs per SM need <= ~44.4 KB each");
+static_assert(sizeof(Smem) * kCtasPerSm <= 226 * 1024, "resident CTAs must fit the SM's shared memory");
+static_assert(kTile / 64 + kMaxSeg <= kMaxItems && kTile % 64 == 0, "one item per thread");
 
 __device__ __forceinline__ bool is_sep(uint32_t c) { return c == '\t' || c == '\n'; }
 
@@ -190,59 +197,60 @@ __device__ __forceinline__ int gt_class3(const uint8_t* p) {
 __device__ __forceinline__ uint32_t cls_flag(int c) { return (0x80C0A000u >> (8 * c)) & 0xFFu; }   // utils.hpp:44-55
 __device__ __forceinline__ int mod_chunk(int x, bool m127) { return m127 ? x % 127 : x % 31; }
 
-struct Item {                  // one 32-byte block of up to 8 samples of one line; lives in registers
-    int blk;                   // window offset of the block (multiple of 32)
-    int phase;                 // sample k sits at blk + phase + 4k
-    uint32_t V, C, L, Hd, CL;  // 8-bit masks: valid, coded, literal, run head, closing token before the sample
+struct Item {                  // one 64-byte block of up to 16 samples of one line; lives in registers
+    int base;                  // window offset of sample 0 (block start + the line's phase); sample k sits at base + 4k
+    uint32_t V, C, L, Hd, CL;  // 16-bit masks: valid, coded, literal, run head, closing token before the sample
+    uint32_t Ap, Bp;           // 17-bit masks: bit k = low bit of the first / second allele of sample k-1
     int kend;                  // index of the sample that ends the line, or -1
     int pcoded;                // the sample before the first valid one is a coded sample of the same line
     int hdr;                   // 8 + required length if this item carries a line start, else 0
     int seg;
 };
 
-__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long a, unsigned long long b) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
-}
-__device__ __forceinline__ void ld_status(const unsigned long long* p, unsigned long long* a, unsigned long long* b) {
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(*a), "=l"(*b) : "l"(p) : "memory");
-}
-
 // ---- classify one item ------------------------------------------------------------------------------------
 __device__ __forceinline__ void item_classify(Smem& sm, const uint8_t* __restrict__ win, int item, Item& it, int* lasthead) {
-    it.blk = 0; it.V = it.C = it.L = it.Hd = it.CL = 0; it.kend = -1; it.pcoded = 0; it.hdr = 0; it.phase = 0; it.seg = 0;
+    it.base = 0; it.V = it.C = it.L = it.Hd = it.CL = 0; it.Ap = it.Bp = 0; it.kend = -1; it.pcoded = 0; it.hdr = 0; it.seg = 0;
     *lasthead = kNoHead;
     if (item >= sm.n_items) return;
     int si = 0;
     for (int j = 1; j < sm.n_seg; j++) si += (sm.seg[j].item0 <= item);
-    const int a = sm.seg[si].a, e = sm.seg[si].e, flags = sm.seg[si].flags, item0 = sm.seg[si].item0;
-    const int blk = ((a >> 5) + (item - item0)) << 5, phase = a & 3;
-    it.blk = blk; it.phase = phase; it.seg = si;
-    if (item == item0 && sm.seg[si].ls >= 0) it.hdr = 8 + sm.seg[si].s0 - sm.seg[si].ls;
+    const Seg sg = sm.seg[si];
+    const int a = sg.a, e = sg.e, flags = sg.flags;
+    const int blk = ((a >> 6) + (item - sg.item0)) << 6, phase = a & 3;
+    it.seg = si;
+    if (item == sg.item0 && sg.ls >= 0) it.hdr = 8 + sg.s0 - sg.ls;
     const int base = blk + phase;
+    it.base = base;
     // valid samples: those that start in [a, e)
     const int rel_a = a - base, rel_e = e - base;
-    const int klo = rel_a > 0 ? rel_a >> 2 : 0, khi = rel_e >= 32 ? 8 : (rel_e > 0 ? rel_e >> 2 : 0);
+    const int klo = rel_a > 0 ? rel_a >> 2 : 0, khi = rel_e >= 64 ? 16 : (rel_e > 0 ? rel_e >> 2 : 0);
     const uint32_t V = khi > klo ? (((1u << khi) - 1u) & ~((1u << klo) - 1u)) : 0u;
     if (!V) return;
     const uint32_t F = ((flags & 2) && rel_a >= 0) ? (1u << klo) : 0u;
     int kend = -1;
-    if (flags & 1) { int r = e - 4 - base; if (r >= 0 && r < 32) kend = r >> 2; }
-    // the 10 words around the block; sample k = bytes base + 4k .. base + 4k + 3
+    if (flags & 1) { int r = e - 4 - base; if (r >= 0 && r < 64) kend = r >> 2; }
+    // the 18 words around the block; sample k = bytes base + 4k .. base + 4k + 3
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(win + blk);
-    uint32_t W[10];
+    uint32_t W[18];
     W[0] = wp[-1];
-    uint4 v0 = *reinterpret_cast<const uint4*>(wp), v1 = *reinterpret_cast<const uint4*>(wp + 4);
-    W[1] = v0.x; W[2] = v0.y; W[3] = v0.z; W[4] = v0.w; W[5] = v1.x; W[6] = v1.y; W[7] = v1.z; W[8] = v1.w;
-    W[9] = wp[8];
-    uint32_t Craw = 0, Q = 0, sp = __funnelshift_r(W[0], W[1], 8 * phase);
-    const uint32_t pc_all = ((sp & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u ? 1u : 0u;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        uint32_t s = __funnelshift_r(W[k + 1], W[k + 2], 8 * phase);
-        Craw |= (((s & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u ? 1u : 0u) << k;   // "x|y\t" with x, y in {0,1}
-        Q |= (s == sp ? 1u : 0u) << k;                                         // same bytes as the previous word
-        sp = s;
+    for (int q = 0; q < 4; q++) {
+        const uint4 v = *reinterpret_cast<const uint4*>(wp + 4 * q);
+        W[4 * q + 1] = v.x; W[4 * q + 2] = v.y; W[4 * q + 3] = v.z; W[4 * q + 4] = v.w;
     }
+    W[17] = wp[16];
+    const int sh = 8 * phase;
+    const uint32_t sp = __funnelshift_r(W[0], W[1], sh);
+    const uint32_t pc_all = ((sp & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u ? 1u : 0u;
+    uint32_t Craw = 0, accA = sp << 31, accB = (sp >> 16) << 31;   // allele bits are shifted in from the top
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const uint32_t s = __funnelshift_r(W[k + 1], W[k + 2], sh);
+        if (((s & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u) Craw |= 1u << k;          // "x|y\t" with x, y in {0,1}
+        accA = __funnelshift_r(accA, s, 1);
+        accB = __funnelshift_r(accB, s >> 16, 1);
+    }
+    const uint32_t Ap = accA >> 15, Bp = accB >> 15;                              // bit 0: the word before the block
     // everything valid that is not "x|y\t": literals, and the sample that carries the line's '\n'
     uint32_t L = 0, N = V & ~Craw;
     bool irr = false;
@@ -254,8 +262,6 @@ __device__ __forceinline__ void item_classify(Smem& sm, const uint8_t* __restric
         if (k == kend ? (b3 != '\n') : (b3 != '\t')) irr = true;
         if (gt_class3(p) < 4) {            // coded sample terminated by the line's newline
             Craw |= 1u << k;
-            const bool prev_coded = k > 0 ? ((Craw >> (k - 1)) & 1u) : pc_all;
-            if (prev_coded && p[-4] == p[0] && p[-2] == p[2]) Q |= 1u << k; else Q &= ~(1u << k);
         } else {
             if (p[0] == '\t' || p[1] == '\t' || p[2] == '\t') irr = true;
             L |= 1u << k;
@@ -263,76 +269,71 @@ __device__ __forceinline__ void item_classify(Smem& sm, const uint8_t* __restric
     }
     if (kend >= 0 && ((V >> kend) & 1u) && win[base + 4 * kend + 3] != '\n') irr = true;
     if (irr) sm.irregular = 6;                               // a sample column that is not 3 bytes + separator
-#ifdef VCFC_DEBUG
-    if (irr) printf("REJECT6 tile=%d item=%d seg=%d a=%d e=%d flags=%d blk=%d phase=%d V=%02x Craw=%02x kend=%d n_seg=%d n_items=%d cs=%d ce=%d bytes=%02x %02x %02x %02x %02x %02x %02x %02x\n",
-                    sm.tile, item, si, a, e, flags, blk, phase, V, Craw, kend, sm.n_seg, sm.n_items, sm.cs, sm.ce,
-                    win[base], win[base+1], win[base+2], win[base+3], win[base+4], win[base+5], win[base+6], win[base+7]);
-#endif
-    const uint32_t Hd = V & (F | ~(Craw & Q));
-    const uint32_t PC = (((Craw << 1) | pc_all) & 0xFFu) & ~F;     // the previous word is a coded sample of this line
+    const uint32_t Cprev = (Craw << 1) | pc_all;
+    const uint32_t same = ~(((Ap >> 1) ^ Ap) | ((Bp >> 1) ^ Bp));              // same genotype bits as the previous word
+    const uint32_t Hd = V & (F | ~(Craw & Cprev & same));
+    const uint32_t PC = (Cprev & 0xFFFFu) & ~F;              // the previous word is a coded sample of this line
     it.V = V; it.C = Craw & V; it.L = L; it.Hd = Hd; it.CL = Hd & PC;
+    it.Ap = Ap; it.Bp = Bp;
     it.kend = (kend >= 0 && ((V >> kend) & 1u)) ? kend : -1;
     it.pcoded = (int)((PC >> klo) & 1u);
     if (Hd) *lasthead = base + 4 * (31 - __clz(Hd));
 }
 
 // bytes the item emits (tokens, literals, line end) -- compress.cpp:124-190 in closed form.
-// ein = address of the last run head before the item.  cnt_prev = chunk count (1..M) of the coded sample
-// just before the first valid one; cfbit = the sample before which the entering chunk fills up.
-__device__ __forceinline__ int item_count(const uint8_t* __restrict__ win, const Item& it, int ein, uint32_t* cfbit, int* cnt_prev, bool* m127) {
-    *cfbit = 0; *cnt_prev = 0; *m127 = true;
+// ein = address of the last run head before the item.  *h = sample index (may be negative) at which the chunk that is
+// open at the first valid sample began; *cfbit = the sample before which that chunk fills up (127 / 31 samples).
+__device__ __forceinline__ int item_count(const Item& it, int ein, uint32_t* cfbit, int* h) {
+    *cfbit = 0; *h = 0;
     if (!it.V) return it.hdr;
     const int k0 = __ffs(it.V) - 1;
+    *h = k0;
     int n = it.hdr + __popc(it.CL) + 5 * __popc(it.L);
     if (it.pcoded) {
-        const int paddr = it.blk + it.phase + 4 * k0 - 4;        // the previous sample
-        *m127 = ((win[paddr] | win[paddr + 2]) & 1u) == 0;  // 0|0 chunks by 127, the others by 31
-        *cnt_prev = mod_chunk((paddr - ein) >> 2, *m127) + 1;
-        const uint32_t t = (~it.Hd & it.V) >> k0;                 // leading samples that continue the entering run
+        const bool m127 = (((it.Ap | it.Bp) >> k0) & 1u) == 0;   // 0|0 chunks by 127, the others by 31
+        const int dist = (it.base + 4 * k0 - 4 - ein) >> 2;      // samples between the run's head and the previous sample
+        const int hh = k0 - 1 - mod_chunk(dist, m127);
+        *h = hh;
+        const uint32_t t = (~it.Hd & it.V) >> k0;                // leading samples that continue the entering run
         const int nlead = __ffs(~t) - 1;
-        const int j = (*m127 ? 127 : 31) - *cnt_prev;             // the chunk is full before lead sample j
-        if (j < nlead) { *cfbit = 1u << (k0 + j); n++; }
+        const int kf = hh + (m127 ? 127 : 31);                   // a new chunk starts at sample kf if the run reaches it
+        if (kf < k0 + nlead) { *cfbit = 1u << kf; n++; }
     }
     if (it.kend >= 0) n += ((it.L >> it.kend) & 1u) ? 0 : 2;      // literal: its tab becomes the '\n'; coded: token + '\n'
     return n;
 }
 
-__device__ __forceinline__ void item_emit(const uint8_t* __restrict__ win, const Item& it, uint32_t cfbit, int cnt_prev, bool m127,
+__device__ __forceinline__ void item_emit(const uint8_t* __restrict__ win, const Item& it, uint32_t cfbit, int h,
                                           uint8_t* __restrict__ dst) {
     if (!it.V) return;
-    const int k0 = __ffs(it.V) - 1;
-    const int base = it.blk + it.phase;
-    uint32_t ev = it.CL | cfbit | it.L | (it.kend >= 0 ? (1u << it.kend) : 0u);
+    const uint32_t tok = it.CL | cfbit;
+    const uint32_t kendbit = it.kend >= 0 ? (1u << it.kend) : 0u;
+    uint32_t ev = tok | it.L | kendbit;
     int o = 0;
     while (ev) {
         const int k = __ffs(ev) - 1;
         ev &= ev - 1;
-        const uint8_t* p = win + base + 4 * k;
-        if (((it.CL | cfbit) >> k) & 1u) {                        // token closing the chunk that ends at sample k-1
-            const int c = (int)(((p[-4] & 1u) << 1) | (p[-2] & 1u));
-            const uint32_t hb = it.Hd & ((1u << k) - 1u);
-            int cnt;
-            if ((cfbit >> k) & 1u) cnt = m127 ? 127 : 31;
-            else if (hb) cnt = k - (31 - __clz(hb));
-            else cnt = mod_chunk(cnt_prev - 1 + (k - k0), m127) + 1;
-            dst[o++] = (uint8_t)(cls_flag(c) | (uint32_t)cnt);
+        if ((tok >> k) & 1u) {                                    // token closing the chunk that ends at sample k-1
+            const uint32_t c = (((it.Ap >> k) & 1u) << 1) | ((it.Bp >> k) & 1u);
+            dst[o++] = (uint8_t)(cls_flag((int)c) | (uint32_t)(k - h));
+            h = k;
         }
-        if ((it.L >> k) & 1u) {                                   // literal escape (compress.cpp:171-185)
-            dst[o] = (uint8_t)(kTokLit | 1u);
-            dst[o + 1] = p[0]; dst[o + 2] = p[1]; dst[o + 3] = p[2];
-            o += 4;
-            if (k != it.kend) dst[o++] = '\t';
-        }
-        if (k == it.kend) {
-            if ((it.C >> k) & 1u) {                               // the open run ends with the line
-                const int c = (int)(((p[0] & 1u) << 1) | (p[2] & 1u));
-                const uint32_t hb = it.Hd & ((2u << k) - 1u);
-                int cnt;
-                if (hb) cnt = k - (31 - __clz(hb)) + 1;
-                else cnt = mod_chunk(cnt_prev + (k - k0), c == 0) + 1;
-                dst[o++] = (uint8_t)(cls_flag(c) | (uint32_t)cnt);
+        if ((it.L | kendbit) >> k & 1u) {
+            const uint8_t* p = win + it.base + 4 * k;
+            if ((it.L >> k) & 1u) {                               // literal escape (compress.cpp:171-185)
+                dst[o] = (uint8_t)(kTokLit | 1u);
+                dst[o + 1] = p[0]; dst[o + 2] = p[1]; dst[o + 3] = p[2];
+                o += 4;
+                if (k != it.kend) dst[o++] = '\t';
+                h = k + 1;
             }
-            dst[o++] = '\n';
+            if (k == it.kend) {
+                if ((it.C >> k) & 1u) {                           // the open run ends with the line
+                    const uint32_t c = (((it.Ap >> (k + 1)) & 1u) << 1) | ((it.Bp >> (k + 1)) & 1u);
+                    dst[o++] = (uint8_t)(cls_flag((int)c) | (uint32_t)(k - h + 1));
+                }
+                dst[o++] = '\n';
+            }
         }
     }
 }
@@ -492,7 +493,7 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
                 }
                 if (((e - a) & 3) != 0) irr = true;
                 // blocks are indexed by where a sample word STARTS; a line start with no sample here still needs an item
-                nitems = e > a ? ((e - 4) >> 5) - (a >> 5) + 1 : 1;
+                nitems = e > a ? ((e - 4) >> 6) - (a >> 6) + 1 : 1;
             }
             int inc = nitems;
 #pragma unroll
@@ -515,25 +516,19 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
         }
         __syncthreads();
 
-        // ---- 4. classify: two items per thread (lane l of warp w: items 64w + l and 64w + 32 + l) ------------------
-        Item it0, it1;
-        int lh0, lh1;
-        item_classify(sm, win, warp * 64 + lane, it0, &lh0);
-        item_classify(sm, win, warp * 64 + 32 + lane, it1, &lh1);
+        // ---- 4. classify: one item (64-byte block, 16 samples) per thread ----------------------------------------------
+        Item it;
+        int lh;
+        item_classify(sm, win, tid, it, &lh);
         // last run head before each item, inside the warp: nearest lower lane that has a head
-        int ein0, ein1;
+        int ein;
         {
-            const unsigned hm0 = __ballot_sync(0xffffffffu, lh0 != kNoHead), hm1 = __ballot_sync(0xffffffffu, lh1 != kNoHead);
-            const unsigned below = (1u << lane) - 1u;
-            const int src0 = (hm0 & below) ? 31 - __clz(hm0 & below) : 0, src1 = (hm1 & below) ? 31 - __clz(hm1 & below) : 0;
-            const int g0 = __shfl_sync(0xffffffffu, lh0, src0), g1 = __shfl_sync(0xffffffffu, lh1, src1);
-            const int last0 = __shfl_sync(0xffffffffu, lh0, hm0 ? 31 - __clz(hm0) : 0);
-            const int last1 = __shfl_sync(0xffffffffu, lh1, hm1 ? 31 - __clz(hm1) : 0);
-            const int tot0 = hm0 ? last0 : kNoHead, tot1 = hm1 ? last1 : kNoHead;
-            ein0 = (hm0 & below) ? g0 : kNoHead;
-            ein1 = (hm1 & below) ? g1 : tot0;
-            const int warp_last = hm1 ? tot1 : tot0;
-            if (lane == 0) { sm.warp_h[warp] = warp_last; if (warp_last != kNoHead) atomicMax(&sm.tile_last_head, warp_last); }
+            const unsigned hm = __ballot_sync(0xffffffffu, lh != kNoHead);
+            const unsigned below = hm & ((1u << lane) - 1u);
+            const int g = __shfl_sync(0xffffffffu, lh, below ? 31 - __clz(below) : 0);
+            ein = below ? g : kNoHead;
+            const int last = __shfl_sync(0xffffffffu, lh, hm ? 31 - __clz(hm) : 0);
+            if (lane == 0) { const int wl = hm ? last : kNoHead; sm.warp_h[warp] = wl; if (hm) atomicMax(&sm.tile_last_head, wl); }
         }
         __syncthreads();
         bool bad = sm.irregular != 0;
@@ -550,16 +545,14 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
                 const int pc0 = need_in ? gt_class3(win + cs - 4) : kNone;
                 const bool uniform = tl == kNoHead;                   // no run head in the tile: the entering run covers it
                 const int nsamp = (ce - cs) >> 2;                      // only used when uniform (one partial segment)
-                const int Ml = lc == 0 ? 127 : 31;
                 if (!uniform) {
-                    unsigned cnt = lc < 4 ? (unsigned)((((ce - tl) >> 2) - 1) % Ml) + 1u : 0u;
+                    unsigned cnt = lc < 4 ? (unsigned)mod_chunk(((ce - tl) >> 2) - 1, lc == 0) + 1u : 0u;
                     *((volatile unsigned*)&s1[tile]) = (2u << 30) | ((unsigned)lc << 8) | cnt;    // absolute: publish before waiting
                 } else if (lc < 4) {
-                    *((volatile unsigned*)&s1[tile]) = (1u << 30) | ((unsigned)lc << 8) | (unsigned)(nsamp % Ml);   // relative
+                    *((volatile unsigned*)&s1[tile]) = (1u << 30) | ((unsigned)lc << 8) | (unsigned)mod_chunk(nsamp, lc == 0);   // relative
                 }
                 int cnt_in = 0;
                 if (need_in && pc0 < 4 && tile > 0) {
-                    const int M = pc0 == 0 ? 127 : 31;
                     int acc = 0;
                     for (int j = tile - 1; j >= 0; j--) {
                         unsigned v;
@@ -567,11 +560,11 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
                         acc += (int)(v & 0xFFu);
                         if ((v >> 30) == 2u) break;
                     }
-                    cnt_in = ((acc - 1) % M + M) % M + 1;              // open chunk count before the tile, 1..M
+                    cnt_in = mod_chunk(acc - 1 + 127 * 31, pc0 == 0) + 1;              // open chunk count before the tile, 1..M
                     ein = cs - 4 * cnt_in;
                 }
                 if (uniform) {
-                    unsigned cnt = lc < 4 ? (unsigned)((cnt_in + nsamp - 1) % Ml) + 1u : 0u;
+                    unsigned cnt = lc < 4 ? (unsigned)mod_chunk(cnt_in + nsamp - 1, lc == 0) + 1u : 0u;
                     *((volatile unsigned*)&s1[tile]) = (2u << 30) | ((unsigned)lc << 8) | cnt;
                 }
             } else {
@@ -589,28 +582,21 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
         {
             int pre = sm.ein_virtual;                                  // heads of earlier warps (addresses grow with the item index)
             for (int w = 0; w < warp; w++) pre = max(pre, sm.warp_h[w]);
-            ein0 = max(ein0, pre);
-            ein1 = max(ein1, pre);
+            ein = max(ein, pre);
         }
-        uint32_t cf0 = 0, cf1 = 0;
-        int cp0 = 0, cp1 = 0;
-        bool m0 = true, m1 = true;
-        const int n0 = bad ? 0 : item_count(win, it0, ein0, &cf0, &cp0, &m0);
-        const int n1 = bad ? 0 : item_count(win, it1, ein1, &cf1, &cp1, &m1);
-        int off0, off1, total;
+        uint32_t cf = 0;
+        int h0 = 0;
+        const int n0 = bad ? 0 : item_count(it, ein, &cf, &h0);
+        int off0, total;
         {
-            // both sub-rounds in one scan: low half = items 64w + lane, high half = items 64w + 32 + lane
-            unsigned inc = (unsigned)n0 | ((unsigned)n1 << 16);
+            int inc = n0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-            const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
-            const int tot0 = (int)(tot & 0xFFFFu), tot1 = (int)(tot >> 16);
-            if (lane == 0) sm.warp_s[warp] = tot0 + tot1;
+            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            if (lane == 31) sm.warp_s[warp] = inc;
             __syncthreads();
             int pre = 0, all = 0;
             for (int w = 0; w < kWarps; w++) { int v = sm.warp_s[w]; all += v; if (w < warp) pre += v; }
-            off0 = pre + (int)(inc & 0xFFFFu) - n0;
-            off1 = pre + tot0 + (int)(inc >> 16) - n1;
+            off0 = pre + inc - n0;
             total = all;
         }
         if (bad) total = 0;
@@ -621,12 +607,8 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
         //         positions come from a device scan over the tile records, k_gather_tiles moves the bytes) -----------
         const int nl = bad ? 0 : sm.n_lines;
         if (!bad) {
-            if (it0.hdr) sm.seg[it0.seg].out0 = off0;
-            if (it1.hdr) sm.seg[it1.seg].out0 = off1;
-            if (staged) {
-                item_emit(win, it0, cf0, cp0, m0, sm.stage + off0 + it0.hdr);
-                item_emit(win, it1, cf1, cp1, m1, sm.stage + off1 + it1.hdr);
-            }
+            if (it.hdr) sm.seg[it.seg].out0 = off0;
+            if (staged) item_emit(win, it, cf, h0, sm.stage + off0 + it.hdr);
         }
         if (tid == 0) {
             const unsigned long long need = (unsigned long long)total + 2ull * (unsigned long long)nl;   // bytes + u16 line offsets
@@ -639,10 +621,7 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
         if (!bad && !sm.skip_write && total > 0) {
             uint8_t* const dst = log + sm.excl_bytes;
             uint8_t* const image = staged ? sm.stage : dst;            // where the tile's output bytes are assembled
-            if (!staged) {
-                item_emit(win, it0, cf0, cp0, m0, image + off0 + it0.hdr);
-                item_emit(win, it1, cf1, cp1, m1, image + off1 + it1.hdr);
-            }
+            if (!staged) item_emit(win, it, cf, h0, image + off0 + it.hdr);
             // ---- 8. line starts: two length headers + required section; the line's offset goes to the trailer -------
             for (int l = warp; l < nl; l += kWarps) {
                 const int si = first_partial + l;
