@@ -79,12 +79,10 @@ struct Smem {
     int n_nl, n_seg, n_items, n_lines;
     int tile, next_tile, issued[2], irregular;
     int cs, cs_kind, ce, ce_kind, cs_s0;
-    int tile_last_head;
+    int lb_uniform, lb_lc, lb_nsamp;        // look-back #1: the tile has no run head (its record is relative until resolved)
     int ein_virtual;
     int warp_h[kWarps], warp_s[kWarps];
-    int lb_has[kWarps];
-    unsigned long long lb_a[kWarps], lb_b[kWarps];
-    unsigned long long excl_bytes, excl_lines;
+    unsigned long long excl_bytes;
     int skip_write;
 };
 static_assert(sizeof(Smem) * kCtasPerSm <= 226 * 1024, "resident CTAs must fit the SM's shared memory");
@@ -176,8 +174,12 @@ __device__ int line_scan(const uint8_t* __restrict__ win, int ls, int vhi_w, int
             unsigned upto = j == 31 ? 0xffffffffu : ((1u << (j + 1)) - 1u);
             if (nlm & upto) return -1;
             if ((tabm & ((tabm << 1) | carry)) & upto) return -1;   // empty field in the required section
-            int s0 = base + j + 1;
-            return (s0 - ls) <= kMaxReq ? s0 : -1;
+            const int s0 = base + j + 1;
+            if ((s0 - ls) > kMaxReq) return -1;
+            // a FORMAT column spelled like a genotype ("0|1") would make the first sample look like a run continuation
+            const uint32_t* wq = reinterpret_cast<const uint32_t*>(win + ((s0 - 4) & ~3));
+            const uint32_t wl = __funnelshift_r(wq[0], wq[1], 8 * ((s0 - 4) & 3));
+            return ((wl & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u ? -1 : s0;
         }
         if (nlm) return -1;                          // fewer than 10 columns
         if (tabm & ((tabm << 1) | carry)) return -1;
@@ -354,7 +356,7 @@ __device__ __forceinline__ void issue_window_load(Smem& sm, int buf, const uint8
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
                unsigned int* __restrict__ s1, unsigned long long* __restrict__ rec_pos, unsigned long long* __restrict__ rec_size,
-               unsigned long long* __restrict__ rec_lines, int n_tiles) {
+               unsigned long long* __restrict__ rec_lines, int n_tiles, unsigned long long log_cap) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -372,15 +374,16 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
     __syncthreads();
     int buf = 0;
     unsigned par[2] = {0u, 0u};
+    int irr_seen = 0;                       // thread 0: ctrl->irregular as of one tile ago (the load stays off the critical path)
 
     for (int tile = (int)blockIdx.x; tile < n_tiles; tile += G) {
         const int tile_next = tile + G;
         if (tid == 0) {
-            sm.irregular = *((volatile int*)&ctrl->irregular);
+            sm.irregular = irr_seen;
+            irr_seen = *((volatile int*)&ctrl->irregular);
             sm.tile = tile;
             sm.n_nl = 0;
             sm.skip_write = 0;
-            sm.tile_last_head = kNoHead;
             sm.n_items = 0; sm.n_seg = 0; sm.n_lines = 0;
             sm.issued[buf ^ 1] = 0;
             if (tile_next < n_tiles && !sm.irregular) { issue_window_load(sm, buf ^ 1, in, n, tile_next); sm.issued[buf ^ 1] = 1; }
@@ -424,6 +427,46 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
                 if (warp == 0) { sm.cs = (int)(c - wbase); sm.cs_kind = kind; sm.cs_s0 = s0c; }
                 else           { sm.ce = (int)(c - wbase); sm.ce_kind = kind; }
                 if (kind == kCutBad) sm.irregular = 2;
+            }
+            // ---- look-back #1, published as early as possible (warp 1): what the run that leaves the tile looks like.
+            //      A sample is a run head unless it and the word before it are the same coded genotype (line_scan
+            //      guarantees that a line's first sample never passes this test), so the last head is found from the
+            //      bytes alone, scanning back from the end cut.
+            if (warp == 1) {
+                unsigned word = (2u << 30) | ((unsigned)kNone << 8);            // nothing carried out
+                int uniform = 0, lcv = kNone, nsamp = 0;
+                if (kind == kCutSample) {
+                    const int ce_w = (int)(c - wbase), lo = kHalo + kPad;        // sample starts below lo belong to the previous tile
+                    const int lc = gt_class3(win + ce_w - 4);
+                    lcv = lc;
+                    word = (2u << 30) | ((unsigned)lc << 8);
+                    if (lc < 4) {
+                        int found = -1;
+                        for (int top = ce_w - 4; top >= lo && found < 0; top -= 128) {
+                            const int p = top - 4 * lane;
+                            bool head = false;
+                            if (p >= lo) {
+                                const uint32_t* wq = reinterpret_cast<const uint32_t*>(win + (p & ~3));
+                                const int shq = 8 * (p & 3);
+                                const uint32_t w1 = __funnelshift_r(wq[0], wq[1], shq), w0 = __funnelshift_r(wq[-1], wq[0], shq);
+                                head = !((((w1 & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u) && w1 == w0);
+                            }
+                            const unsigned hm = __ballot_sync(0xffffffffu, head);
+                            if (hm) found = top - 4 * (__ffs(hm) - 1);
+                        }
+                        if (found >= 0) {
+                            word |= (unsigned)mod_chunk(((ce_w - found) >> 2) - 1, lc == 0) + 1u;
+                        } else {                                                 // the entering run covers the whole tile
+                            uniform = 1;
+                            nsamp = (ce_w - lo) >> 2;
+                            word = (1u << 30) | ((unsigned)lc << 8) | (unsigned)mod_chunk(nsamp, lc == 0);   // relative
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    *((volatile unsigned*)&s1[tile]) = word;
+                    sm.lb_uniform = uniform; sm.lb_lc = lcv; sm.lb_nsamp = nsamp;
+                }
             }
         }
         {
@@ -517,6 +560,8 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
         __syncthreads();
 
         // ---- 4. classify: one item (64-byte block, 16 samples) per thread ----------------------------------------------
+        unsigned lb_pref = 0;
+        if (tid == 0 && tile > 0) lb_pref = *((volatile unsigned*)&s1[tile - 1]);   // consumed after the classification
         Item it;
         int lh;
         item_classify(sm, win, tid, it, &lh);
@@ -528,55 +573,37 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
             const int g = __shfl_sync(0xffffffffu, lh, below ? 31 - __clz(below) : 0);
             ein = below ? g : kNoHead;
             const int last = __shfl_sync(0xffffffffu, lh, hm ? 31 - __clz(hm) : 0);
-            if (lane == 0) { const int wl = hm ? last : kNoHead; sm.warp_h[warp] = wl; if (hm) atomicMax(&sm.tile_last_head, wl); }
+            if (lane == 0) sm.warp_h[warp] = hm ? last : kNoHead;
+        }
+        // ---- 5. look-back #1 (thread 0): chunk count of the run that enters the tile -- chunks are counted from the
+        //         run's head (compress.cpp:129-170), which can lie many tiles back ---------------------------------------
+        if (tid == 0) {
+            int einv = kNoHead;
+            if (first_partial && cs_kind == kCutSample && tile > 0) {              // the first sample continues a line
+                const int pc0 = gt_class3(win + cs - 4);
+                if (pc0 < 4) {
+                    int acc = 0;
+                    unsigned v = lb_pref;
+                    for (int j = tile - 1;;) {
+                        while ((v >> 30) == 0) v = *((volatile unsigned*)&s1[j]);
+                        acc += (int)(v & 0xFFu);
+                        if ((v >> 30) == 2u || j == 0) break;
+                        j--;
+                        v = *((volatile unsigned*)&s1[j]);
+                    }
+                    const int cnt_in = mod_chunk(acc - 1 + 127 * 31, pc0 == 0) + 1;  // open chunk count before the tile, 1..M
+                    einv = cs - 4 * cnt_in;
+                    if (sm.lb_uniform) {                                          // now absolute: shortens the successors' chains
+                        const int lc = sm.lb_lc;
+                        *((volatile unsigned*)&s1[tile]) =
+                            (2u << 30) | ((unsigned)lc << 8) | ((unsigned)mod_chunk(cnt_in + sm.lb_nsamp - 1, lc == 0) + 1u);
+                    }
+                }
+            }
+            sm.ein_virtual = einv;
         }
         __syncthreads();
         bool bad = sm.irregular != 0;
-
-        // ---- 5. look-back #1 (thread 0): chunk count of the run that enters the tile ----------------------------------
-        if (tid == 0) {
-            const int tl = sm.tile_last_head;
-            int ein = kNoHead;
-            if (!bad && cs < ce) {
-                // class of the tile's last sample (kNone when the tile ends with a line end or a required section)
-                int lc = kNone;
-                if (sm.ce_kind == kCutSample) lc = gt_class3(win + ce - 4);
-                const bool need_in = first_partial && cs_kind == kCutSample;      // the first sample continues a line
-                const int pc0 = need_in ? gt_class3(win + cs - 4) : kNone;
-                const bool uniform = tl == kNoHead;                   // no run head in the tile: the entering run covers it
-                const int nsamp = (ce - cs) >> 2;                      // only used when uniform (one partial segment)
-                if (!uniform) {
-                    unsigned cnt = lc < 4 ? (unsigned)mod_chunk(((ce - tl) >> 2) - 1, lc == 0) + 1u : 0u;
-                    *((volatile unsigned*)&s1[tile]) = (2u << 30) | ((unsigned)lc << 8) | cnt;    // absolute: publish before waiting
-                } else if (lc < 4) {
-                    *((volatile unsigned*)&s1[tile]) = (1u << 30) | ((unsigned)lc << 8) | (unsigned)mod_chunk(nsamp, lc == 0);   // relative
-                }
-                int cnt_in = 0;
-                if (need_in && pc0 < 4 && tile > 0) {
-                    int acc = 0;
-                    for (int j = tile - 1; j >= 0; j--) {
-                        unsigned v;
-                        do { v = *((volatile unsigned*)&s1[j]); } while ((v >> 30) == 0);
-                        acc += (int)(v & 0xFFu);
-                        if ((v >> 30) == 2u) break;
-                    }
-                    cnt_in = mod_chunk(acc - 1 + 127 * 31, pc0 == 0) + 1;              // open chunk count before the tile, 1..M
-                    ein = cs - 4 * cnt_in;
-                }
-                if (uniform) {
-                    unsigned cnt = lc < 4 ? (unsigned)mod_chunk(cnt_in + nsamp - 1, lc == 0) + 1u : 0u;
-                    *((volatile unsigned*)&s1[tile]) = (2u << 30) | ((unsigned)lc << 8) | cnt;
-                }
-            } else {
-                *((volatile unsigned*)&s1[tile]) = (2u << 30) | ((unsigned)kNone << 8);          // nothing carried out
-            }
-#ifdef VCFC_DEBUG
-            if (bad) printf("tile %d cs=%d(k%d) ce=%d(k%d) bad=%d n_items=%d n_seg=%d tl=%d s1=%08x ein=%d wbase=%lld\n", tile, cs, cs_kind, ce,
-                   sm.ce_kind, (int)bad, sm.n_items, sm.n_seg, tl, s1[tile], ein, wbase);
-#endif
-            sm.ein_virtual = ein;
-        }
-        __syncthreads();
 
         // ---- 6. byte counts and their exclusive scan ----------------------------------------------------------------------
         {
@@ -606,15 +633,16 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
         // ---- 7. emit into staging; reserve the tile's place in the log with one atomic (no scan chain: the final
         //         positions come from a device scan over the tile records, k_gather_tiles moves the bytes) -----------
         const int nl = bad ? 0 : sm.n_lines;
+        const unsigned long long need = (unsigned long long)total + 2ull * (unsigned long long)nl;       // bytes + u16 line offsets
+        unsigned long long pos = 0ull;
+        if (tid == 0 && need) pos = atomicAdd(&ctrl->log_cursor, need);   // issued before the emission, consumed after it
         if (!bad) {
             if (it.hdr) sm.seg[it.seg].out0 = off0;
             if (staged) item_emit(win, it, cf, h0, sm.stage + off0 + it.hdr);
         }
         if (tid == 0) {
-            const unsigned long long need = (unsigned long long)total + 2ull * (unsigned long long)nl;   // bytes + u16 line offsets
-            const unsigned long long pos = need ? atomicAdd(&ctrl->log_cursor, need) : 0ull;
             rec_pos[tile] = pos; rec_size[tile] = (unsigned long long)total; rec_lines[tile] = (unsigned long long)nl;
-            if (pos + need > ctrl->log_cap) { sm.skip_write = 1; atomicExch(&ctrl->cap_exceeded, 1); }
+            if (pos + need > log_cap) { sm.skip_write = 1; atomicExch(&ctrl->cap_exceeded, 1); }
             sm.excl_bytes = pos;
         }
         __syncthreads();
@@ -778,7 +806,8 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         uint8_t* a_log = (uint8_t*)b_log.p;
         unsigned int* a_s1 = (unsigned int*)(base + off_s1);
         int a_tiles = (int)n_tiles;
-        void* args[] = {&a_in, &a_n, &a_log, &ctrl, &a_s1, &rec_pos, &rec_size, &rec_lines, &a_tiles};
+        unsigned long long a_cap = (unsigned long long)log_cap;
+        void* args[] = {&a_in, &a_n, &a_log, &ctrl, &a_s1, &rec_pos, &rec_size, &rec_lines, &a_tiles, &a_cap};
         VCFC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_encode_tiles, dim3(grid), dim3(kThreads), args, sizeof(Smem), stream));
     }
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeEncode + 1], stream); ctx->ev_pending[kTimeEncode] = 1; }
