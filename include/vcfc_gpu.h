@@ -137,7 +137,8 @@ int vcfc_last_path(const vcfc_ctx *ctx);
  * sample region not a multiple of 4 bytes), 5 too many segments, 6 a sample column that is not 3 bytes wide,
  * 8 line table overflow, 9 follow-up of another tile's reject. */
 int vcfc_last_reject_reason(const vcfc_ctx *ctx);
-/* Testing aid: route every block through the generic kernels. */
+/* Testing aid: on = 1 routes every block through the generic kernels; on = 2 keeps the tile kernels but makes the
+ * decoder use its span-walking expansion kernel even when the fill-and-patch kernel applies; 0 = automatic. */
 int vcfc_force_generic(vcfc_ctx *ctx, int on);
 
 #ifdef __cplusplus

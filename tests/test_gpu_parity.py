@@ -28,10 +28,10 @@ def codec():
     c.close()
 
 
-@pytest.fixture(params=["auto", "generic"])
+@pytest.fixture(params=["auto", "walk", "generic"])
 def any_path(request, codec):
-    """Run a test through the default dispatch and through the generic kernels."""
-    codec.force_generic(request.param == "generic")
+    """Run a test through the default dispatch, with the span-walking decode kernel, and through the generic kernels."""
+    codec.force_generic({"auto": 0, "generic": 1, "walk": 2}[request.param])
     yield codec
     codec.force_generic(False)
 

@@ -153,7 +153,8 @@ class Codec:
     def last_reject_reason(self) -> int:
         return lib().vcfc_last_reject_reason(self._ctx)
 
-    def force_generic(self, on: bool):
+    def force_generic(self, on):
+        """0/False automatic, 1/True generic kernels only, 2 tile kernels with the span-walking decoder."""
         lib().vcfc_force_generic(self._ctx, int(on))
 
     def set_timing(self, on: bool):

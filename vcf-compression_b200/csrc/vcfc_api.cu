@@ -166,7 +166,7 @@ int vcfc_encode_block_dev(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uin
     if (!ctx || !d_result || (in_len && (!d_in || !d_out))) return VCFC_E_ARG;
     VCFC_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    if (!ctx->force_generic) {
+    if (ctx->force_generic != 1) {
         int rc = encode_fast(ctx, d_in, in_len, d_out, out_cap, d_line_out_offsets, line_cap, d_result, st);
         if (rc != VCFC_OK) return rc;
         int status = 0;
@@ -184,7 +184,7 @@ static int decode_dev_common(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, 
     if (!ctx || !d_result || (in_len && !d_in) || (!size_only && in_len && !d_out)) return VCFC_E_ARG;
     VCFC_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    if (!ctx->force_generic) {
+    if (ctx->force_generic != 1) {
         int rc = decode_fast(ctx, d_in, in_len, sample_count, d_out, out_cap, d_result, size_only, st);
         if (rc != VCFC_OK) return rc;
         int status = 0;

@@ -37,6 +37,7 @@ struct Ctrl {
     int irregular;
     int n_fix;                                    // segments whose first plausible line start is not on the chain
     unsigned long long n_lines, end_pos, total_out;
+    int not_grid, pad;                            // some sample text is not 4 bytes wide (or a required section < 16 bytes)
     int fix[kMaxFix];
 };
 
@@ -185,9 +186,10 @@ __device__ __forceinline__ int last_setter_kind(const uint8_t* b, int nb) {
 
 // Walks nb token-region bytes starting in `payload` state; accumulates text bytes and samples.
 // is_last: the chunk ends with the line's final '\n'.  err bits: 1 = malformed for this path.
+// *tres: bit r set = a literal ended (its terminator included) at chunk-relative text offset == r (mod 4).
 __device__ __forceinline__ void chunk_measure(const uint8_t* b, int nb, bool payload, bool is_last, unsigned* out_len,
-                                              unsigned* samples, int* err) {
-    unsigned o = 0, ns = 0;
+                                              unsigned* samples, int* err, unsigned* tres) {
+    unsigned o = 0, ns = 0, tr = 0;
     int e = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -196,8 +198,8 @@ __device__ __forceinline__ void chunk_measure(const uint8_t* b, int nb, bool pay
         if (i >= nb) {
         } else if (payload) {
             o++;
-            if (c == 9u) { payload = false; ns++; }
-            else if (c == 10u) { payload = false; ns++; if (!line_end) e = 1; }     // '\n' inside a payload: compress.cpp:875-884
+            if (c == 9u) { payload = false; ns++; tr |= 1u << (o & 3u); }
+            else if (c == 10u) { payload = false; ns++; tr |= 1u << (o & 3u); if (!line_end) e = 1; }     // '\n' inside a payload: compress.cpp:875-884
         } else if (line_end) {
             // the newline after a run: it replaces the run's last tab, no text of its own
         } else if (c < 0x80u) {
@@ -212,7 +214,7 @@ __device__ __forceinline__ void chunk_measure(const uint8_t* b, int nb, bool pay
             payload = true;
         }
     }
-    *out_len = o; *samples = ns; *err = e;
+    *out_len = o; *samples = ns; *err = e; *tres = tr;
 }
 
 // ---- D2: per-line validation and text size (one warp per line) ----------------------------------------------
@@ -238,7 +240,7 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
     if (!bad) {
         const long long tb = 8 + rq, tn = clen - tb;            // token region, its last byte is the line's '\n'
         int carry_kind = 0;                                     // last setter seen so far (0 = none: token state)
-        int err_any = 0;
+        int err_any = 0, off_grid = rq < 16 ? 1 : 0;
         for (long long base = 0; base < tn; base += 512) {
             const long long off = base + 16ll * lane;
             int nb = (int)(tn - off);
@@ -263,9 +265,9 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
             const int src = below ? 31 - __clz(below) : 0;
             const int k_src = __shfl_sync(0xffffffffu, kind, src);
             const int k_in = below ? k_src : carry_kind;
-            unsigned o = 0, ns = 0;
+            unsigned o = 0, ns = 0, tres = 0;
             int e = 0;
-            if (nb > 0) chunk_measure(b, nb, k_in == 1, off + nb == tn, &o, &ns, &e);
+            if (nb > 0) chunk_measure(b, nb, k_in == 1, off + nb == tn, &o, &ns, &e, &tres);
             err_any |= e;
             // chunk table (text offset << 1 | payload state at the chunk's first byte), consumed by k_dec_expand;
             // line k owns the slots [(ls >> 4) + k, ...): disjoint between lines, <= clen / 16 + 1 of them
@@ -276,11 +278,14 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
                 if (lane >= d) { inc += t; n32 += u; }
             }
             if (nb > 0) ctab[(ls >> 4) + k + (unsigned long long)(off >> 4)] = (((unsigned)total + inc - o) << 1) | (k_in == 1 ? 1u : 0u);
+            // every literal must end on the 4-byte sample grid for the fill-and-patch kernel (k_dec_expand_grid)
+            if (tres & ~(1u << ((4u - ((unsigned)total + inc - o)) & 3u))) off_grid = 1;
             total += __shfl_sync(0xffffffffu, inc, 31);
             ns_total += __shfl_sync(0xffffffffu, n32, 31);
             if (has) carry_kind = __shfl_sync(0xffffffffu, kind, 31 - __clz(has));
         }
         err_any = __any_sync(0xffffffffu, err_any);
+        if (__any_sync(0xffffffffu, off_grid) && lane == 0) atomicExch(&ctrl->not_grid, 1);
         if (err_any || ns_total != sample_count) bad = true;
         total += (unsigned long long)rq;
     }
@@ -325,7 +330,12 @@ __global__ void k_dec_tilemap(const unsigned long long* __restrict__ off, unsign
 // compressed bytes (contiguous in the block) are staged in smem with 16-byte copies, (3) one warp per line builds
 // a chunk table (text offset + token/payload state at every 16th token byte) with warp scans only, (4) each
 // thread binary-searches the table for its span, walks to the token that covers it and generates its bytes.
-constexpr int kSpan = kTile / kThreads;     // 64
+#ifndef VCFC_DEC_XTHREADS
+#define VCFC_DEC_XTHREADS 256
+#define VCFC_DEC_XCTAS 4
+#endif
+constexpr int kXThreads = VCFC_DEC_XTHREADS, kXWarps = kXThreads / 32;   // D4 block size
+constexpr int kSpan = kTile / kXThreads;    // 64
 constexpr int kChunks = kCmax / 16 + 2 * 32;
 constexpr int kMaxL = 31;                   // lines per batch
 
@@ -388,7 +398,7 @@ struct Writer {
     }
 };
 
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kXThreads, VCFC_DEC_XCTAS)
 k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ line_start,
              const unsigned long long* __restrict__ off, unsigned long long n_lines, unsigned long long total,
              const unsigned int* __restrict__ first_line, const unsigned int* __restrict__ first_chunk,
@@ -460,13 +470,13 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
             const int n16 = (staged - head) >> 4;
             const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
             uint4* d4 = reinterpret_cast<uint4*>(sm.cbuf + phase + head);
-            for (int i = tid; i < n16; i += kThreads) d4[i] = s4[i];
+            for (int i = tid; i < n16; i += kXThreads) d4[i] = s4[i];
             const int t0 = head + 16 * n16;
             if (tid < staged - t0) sm.cbuf[phase + t0 + tid] = src[t0 + tid];
         }
         // (3) chunk tables of the batch's lines (built once per line by k_dec_sizes): copy the staged part.
         //     Line li's entries go to slot (l_coff >> 4) + li, the global table's rule relative to the batch.
-        for (int li = warp; li < nb; li += kWarps) {
+        for (int li = warp; li < nb; li += kXWarps) {
             const int coff = sm.l_coff[li];
             const int avail = min(sm.l_coff[li + 1], staged) - coff;          // staged bytes of this line
             const int nslots = (avail >> 4) + 1;
@@ -557,10 +567,223 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
             const int n16 = tile_len >> 4;
             const uint4* s4 = reinterpret_cast<const uint4*>(sm.stage);
             uint4* d4 = reinterpret_cast<uint4*>(dst);
-            for (int i = tid; i < n16; i += kThreads) d4[i] = s4[i];
-            for (int i = (n16 << 4) + tid; i < tile_len; i += kThreads) dst[i] = sm.stage[i];
+            for (int i = tid; i < n16; i += kXThreads) d4[i] = s4[i];
+            for (int i = (n16 << 4) + tid; i < tile_len; i += kXThreads) dst[i] = sm.stage[i];
         } else {
-            for (int i = tid; i < tile_len; i += kThreads) dst[i] = sm.stage[i];
+            for (int i = tid; i < tile_len; i += kXThreads) dst[i] = sm.stage[i];
+        }
+    }
+}
+
+// ---- D4', sample text on the 4-byte grid (every sample column is 3 bytes wide): fill and patch -------------------------
+// Almost all of the text is the default genotype, so the tile image is first FILLED with "0|0\t" in each line's phase
+// (16-byte stores, no parsing) and then PATCHED: one thread per 16 token bytes walks its chunk from the chunk table's
+// text offset and writes only what differs -- a '1' for the allele bytes of 0|1 / 1|0 / 1|1 runs, literal payloads --
+// plus the required sections and the line ends.  Work is proportional to the COMPRESSED size of the tile.
+struct SmemG {
+    alignas(16) uint8_t stage[kTile];
+    alignas(16) uint8_t cbuf[kCmax + 32];
+    unsigned ctab[kChunks];
+    int l_pos[kMaxL + 1], l_end[kMaxL + 1], l_last[kMaxL + 1], l_coff[kMaxL + 2];
+    int l_rq[kMaxL + 1];                     // required length
+    int l_c0[kMaxL + 2];                     // first flat chunk index of the line (exclusive prefix of the chunk counts)
+    int l_wb[kMaxL + 1];                     // token bytes of the line to walk (the line's final '\n' excluded)
+    int n_batch, more, staged, c_first;
+    unsigned long long c_lo;
+};
+
+__global__ void __launch_bounds__(kXThreads, VCFC_DEC_XCTAS)
+k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ line_start,
+                  const unsigned long long* __restrict__ off, unsigned long long n_lines, unsigned long long total,
+                  const unsigned int* __restrict__ first_line, const unsigned int* __restrict__ first_chunk,
+                  const unsigned* __restrict__ rq_arr, const unsigned* __restrict__ gtab, uint8_t* __restrict__ out,
+                  const Ctrl* __restrict__ ctrl) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    SmemG& sm = *reinterpret_cast<SmemG*>(smem_raw);
+    if (ctrl->irregular) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long T0 = (unsigned long long)blockIdx.x * kTile;
+    const int tile_len = (int)(total - T0 < (unsigned long long)kTile ? total - T0 : (unsigned long long)kTile);
+    const unsigned long long T1 = T0 + (unsigned long long)tile_len;
+    unsigned long long k0 = first_line[blockIdx.x];
+    unsigned fc_tile = first_chunk[blockIdx.x];         // applies to the first batch's first line only
+
+    for (;;) {
+        // (1) line table entries of the next batch: lines k0 .. k0 + nb - 1 overlap the tile
+        if (warp == 0) {
+            const unsigned long long kk = k0 + (unsigned long long)lane;
+            const unsigned long long o = kk < n_lines ? off[kk] : total;
+            const unsigned long long ls = kk <= n_lines ? line_start[kk] : 0ull;
+            int rq = kk < n_lines ? (int)rq_arr[kk] : 0;
+            const unsigned long long ls0 = __shfl_sync(0xffffffffu, ls, 0);
+            const int rq0 = __shfl_sync(0xffffffffu, rq, 0);
+            // a long first line whose text began before the tile is staged from the chunk that holds the tile's first byte
+            unsigned long long s0 = ls0;
+            const bool cont = fc_tile != kWholeLine;
+            if (cont) s0 = ls0 + 8ull + (unsigned long long)rq0 + 16ull * fc_tile;
+            const bool overlaps = kk < n_lines && o < T1;
+            unsigned m = __ballot_sync(0xffffffffu, overlaps) & 0x7fffffffu;         // lane 31 only supplies the end of line 30
+            int nb = __popc(m);                                                        // off[] is monotone: a prefix of the lanes
+            // later lines are staged whole, so they must fit behind the first; the first may be cut at kCmax
+            // (kCmax compressed bytes always expand to at least a tile of text)
+            const unsigned fits = __ballot_sync(0xffffffffu, ls >= s0 && ls - s0 <= (unsigned long long)kCmax);
+            while (nb > 1 && !((fits >> nb) & 1u)) nb--;
+            const unsigned long long o_next = __shfl_down_sync(0xffffffffu, o, 1);
+            const unsigned long long ls_next = __shfl_down_sync(0xffffffffu, ls, 1);
+            const unsigned long long ls_after = __shfl_sync(0xffffffffu, ls, nb);     // nb <= 31
+            const int staged = (int)min(ls_after - s0, (unsigned long long)kCmax);
+            // token bytes to walk and their 16-byte chunks
+            const int coff = lane == 0 ? 0 : (int)(ls - s0);
+            const int cend = (int)min(ls_next - s0, (unsigned long long)0x7fffffff);
+            const bool whole = cend <= staged;                                         // the line's final '\n' is staged
+            const int hdrb = (lane == 0 && cont) ? 0 : 8 + rq;
+            int wb = lane < nb ? min(cend, staged) - coff - hdrb - (whole ? 1 : 0) : 0;
+            if (wb < 0) wb = 0;
+            int nch = (wb + 15) >> 4, inc = nch;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            if (lane <= nb) sm.l_c0[lane] = inc - nch;
+            if (lane < nb) {
+                sm.l_pos[lane] = (int)((long long)o - (long long)T0);
+                sm.l_end[lane] = (int)(o_next < T1 ? o_next - T0 : (unsigned long long)tile_len);
+                sm.l_last[lane] = (int)min((long long)o_next - 1 - (long long)T0, (long long)(1 << 30));
+                sm.l_coff[lane] = coff;
+                sm.l_rq[lane] = rq;
+                sm.l_wb[lane] = wb;
+                if (lane == nb - 1) sm.l_coff[nb] = cend;
+            }
+            const unsigned long long o_after = __shfl_sync(0xffffffffu, o, nb);
+            if (lane == 0) {
+                sm.n_batch = nb;
+                sm.more = (nb > 0 && k0 + (unsigned long long)nb < n_lines && o_after < T1) ? 1 : 0;   // another batch follows
+                sm.c_lo = s0;
+                sm.c_first = cont ? (int)fc_tile : -1;
+                sm.staged = staged;
+            }
+        }
+        __syncthreads();
+        const int nb = sm.n_batch;
+        if (nb == 0) break;
+        const unsigned long long c_lo = sm.c_lo;
+        const int c_first = sm.c_first;
+        // (2) stage the batch's compressed bytes; cbuf keeps the source's 16-byte phase so both sides are aligned
+        const int phase = (int)(reinterpret_cast<uintptr_t>(in + c_lo) & 15);
+        const int staged = sm.staged;
+        {
+            const uint8_t* src = in + c_lo;
+            const int head = min((16 - phase) & 15, staged);
+            if (tid < head) sm.cbuf[phase + tid] = src[tid];
+            const int n16 = (staged - head) >> 4;
+            const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+            uint4* d4 = reinterpret_cast<uint4*>(sm.cbuf + phase + head);
+            for (int i = tid; i < n16; i += kXThreads) d4[i] = s4[i];
+            const int t0 = head + 16 * n16;
+            if (tid < staged - t0) sm.cbuf[phase + t0 + tid] = src[t0 + tid];
+        }
+        // (3) chunk tables of the batch's lines (built once per line by k_dec_sizes): line li's entries go to slot
+        //     (l_coff >> 4) + li, the global table's rule relative to the batch
+        for (int li = warp; li < nb; li += kXWarps) {
+            const int coff = sm.l_coff[li];
+            const int nslots = ((min(sm.l_coff[li + 1], staged) - coff) >> 4) + 1;
+            const unsigned long long lsk = li == 0 ? line_start[k0] : c_lo + (unsigned long long)coff;
+            const unsigned* src = gtab + (lsk >> 4) + (k0 + (unsigned long long)li) + (li == 0 && c_first >= 0 ? c_first : 0);
+            unsigned* tab = sm.ctab + (coff >> 4) + li;
+            for (int i = lane; i < nslots; i += 32) tab[i] = src[i];
+        }
+        // (4) fill: every 16-byte unit that starts inside the batch's lines gets "0|0\t" in the phase of its line
+        {
+            const int f_lo = sm.l_pos[0] <= 0 ? 0 : (sm.l_pos[0] + 15) >> 4, f_hi = (sm.l_end[nb - 1] + 15) >> 4;
+            for (int u = f_lo + tid; u < f_hi; u += kXThreads) {
+                const int pos = u << 4;
+                int li = 0;
+                for (int j = 1; j < nb; j++) li += (sm.l_pos[j] <= pos);
+                const int ph = (pos - sm.l_pos[li] - sm.l_rq[li]) & 3;
+                const uint32_t P = __funnelshift_r(0x09307C30u, 0x09307C30u, 8 * ph);
+                *reinterpret_cast<uint4*>(sm.stage + pos) = make_uint4(P, P, P, P);
+            }
+        }
+        __syncthreads();
+        // (5) patch: required sections and line ends (one warp per line) ...
+        for (int li = warp; li < nb; li += kXWarps) {
+            const int lpos = sm.l_pos[li], rq = sm.l_rq[li];
+            if (!(li == 0 && c_first >= 0)) {
+                const uint8_t* lp = sm.cbuf + phase + sm.l_coff[li];
+                const int i_lo = lpos < 0 ? -lpos : 0, i_hi = min(rq, tile_len - lpos);
+                for (int i = i_lo + lane; i < i_hi; i += 32) sm.stage[lpos + i] = lp[8 + i];
+            }
+            const int last = sm.l_last[li];
+            if (lane == 0 && last >= 0 && last < tile_len) sm.stage[last] = '\n';
+        }
+        // ... and the token chunks: only what is not the default genotype is written
+        {
+            const int n_chunks = sm.l_c0[nb];
+            for (int idx = tid; idx < n_chunks; idx += kXThreads) {
+                int li = 0;
+                for (int j = 1; j < nb; j++) li += (sm.l_c0[j] <= idx);
+                const int c = idx - sm.l_c0[li];
+                const int coff = sm.l_coff[li];
+                const bool cont = li == 0 && c_first >= 0;
+                const int rq = sm.l_rq[li];
+                const unsigned* tab = sm.ctab + (coff >> 4) + li;
+                const unsigned t0 = tab[c];
+                const int tpos = sm.l_pos[li] + rq;                  // tile position of the first sample's text
+                int pos = tpos + (int)(t0 >> 1);                     // tile position of the chunk's first text byte
+                if (pos >= tile_len) continue;
+                const int wb = sm.l_wb[li];
+                if (16 * (c + 1) < wb && tpos + (int)(tab[c + 1] >> 1) <= 0) continue;     // ends before the tile
+                const int nby = min(16, wb - 16 * c);
+                // the chunk's bytes: aligned 32-bit loads, funnel-shifted
+                const uint8_t* bp = sm.cbuf + phase + coff + (cont ? 0 : 8 + rq) + 16 * c;
+                const uintptr_t ga = reinterpret_cast<uintptr_t>(bp);
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
+                const int sh = 8 * (int)(ga & 3);
+                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+                const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                                       __funnelshift_r(w3, w4, sh)};
+                bool payload = (t0 & 1u) != 0;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const uint32_t b = (v[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                    if (i < nby) {
+                        if (payload) {
+                            if ((unsigned)pos < (unsigned)tile_len) sm.stage[pos] = (uint8_t)b;
+                            pos++;
+                            if (b == 9u || b == 10u) payload = false;
+                        } else if (b >= 0xE0u) {
+                            payload = true;
+                        } else if (b < 0x80u) {
+                            pos += 4 * (int)b;                        // 0|0: already there
+                        } else {
+                            const uint32_t f = b & 0xE0u;
+                            const bool a1 = f != kTok01, b1 = f != kTok10;
+                            const int cnt = (int)(b & 0x1Fu);
+                            for (int q = 0; q < cnt; q++, pos += 4) {
+                                if (a1 && (unsigned)pos < (unsigned)tile_len) sm.stage[pos] = '1';
+                                if (b1 && (unsigned)(pos + 2) < (unsigned)tile_len) sm.stage[pos + 2] = '1';
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        const int more = sm.more;
+        __syncthreads();
+        if (!more) break;
+        k0 += (unsigned long long)nb;
+        fc_tile = kWholeLine;
+    }
+    __syncthreads();
+    // tile image -> HBM
+    {
+        uint8_t* dst = out + T0;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            const int n16 = tile_len >> 4;
+            const uint4* s4 = reinterpret_cast<const uint4*>(sm.stage);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            for (int i = tid; i < n16; i += kXThreads) d4[i] = s4[i];
+            for (int i = (n16 << 4) + tid; i < tile_len; i += kXThreads) dst[i] = sm.stage[i];
+        } else {
+            for (int i = tid; i < tile_len; i += kXThreads) dst[i] = sm.stage[i];
         }
     }
 }
@@ -591,6 +814,7 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
     static bool attr_set = false;
     if (!attr_set) {
         VCFC_CUDA(ctx, cudaFuncSetAttribute(k_dec_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        VCFC_CUDA(ctx, cudaFuncSetAttribute(k_dec_expand_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemG)));
         attr_set = true;
     }
     int rc;
@@ -613,7 +837,7 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
     k_dec_verify<<<gs, 128, 0, stream>>>(n, n_seg, cand, endp, ctrl, 1);
     ctx->launches += 4;
     if ((rc = scan_exclusive_u64(ctx, (const uint64_t*)cnt, (uint64_t*)base, (size_t)n_seg, (uint64_t*)&ctrl->n_lines, &b_scr, stream))) return rc;
-    struct { int irregular, n_fix; unsigned long long n_lines, end_pos, total_out; } h;
+    struct { int irregular, n_fix; unsigned long long n_lines, end_pos, total_out; int not_grid, pad; } h;
     VCFC_CUDA(ctx, cudaMemcpyAsync(&h, ctrl, sizeof(h), cudaMemcpyDeviceToHost, stream));
     VCFC_CUDA(ctx, cudaStreamSynchronize(stream));
     if (h.irregular || h.n_lines == 0 || h.n_lines >= (1ull << 32)) {
@@ -655,8 +879,12 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
                                                                           (const unsigned*)b_rq.p, (const unsigned*)b_tab.p,
                                                                           (unsigned int*)b_tiles.p, first_chunk);
     if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeDecodeExpand], stream);
-    k_dec_expand<<<(unsigned)n_tiles, kThreads, sizeof(Smem), stream>>>(d_in, line_start, (unsigned long long*)b_offs.p, n_lines,
-                                                                        total, (unsigned int*)b_tiles.p, first_chunk, (const unsigned*)b_rq.p, (const unsigned*)b_tab.p, d_out, ctrl);
+    if (h.not_grid || ctx->force_generic == 2)
+        k_dec_expand<<<(unsigned)n_tiles, kXThreads, sizeof(Smem), stream>>>(d_in, line_start, (unsigned long long*)b_offs.p, n_lines,
+                                                                            total, (unsigned int*)b_tiles.p, first_chunk, (const unsigned*)b_rq.p, (const unsigned*)b_tab.p, d_out, ctrl);
+    else
+        k_dec_expand_grid<<<(unsigned)n_tiles, kXThreads, sizeof(SmemG), stream>>>(d_in, line_start, (unsigned long long*)b_offs.p, n_lines,
+                                                                                  total, (unsigned int*)b_tiles.p, first_chunk, (const unsigned*)b_rq.p, (const unsigned*)b_tab.p, d_out, ctrl);
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeDecodeExpand + 1], stream); ctx->ev_pending[kTimeDecodeExpand] = 1; }
     k_dec_result<<<1, 1, 0, stream>>>(d_result, ctrl, VCFC_OK, total, n_lines);
     ctx->launches += 3;
