@@ -580,19 +580,30 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
 // (16-byte stores, no parsing) and then PATCHED: one thread per 16 token bytes walks its chunk from the chunk table's
 // text offset and writes only what differs -- a '1' for the allele bytes of 0|1 / 1|0 / 1|1 runs, literal payloads --
 // plus the required sections and the line ends.  Work is proportional to the COMPRESSED size of the tile.
+#ifndef VCFC_DEC_GTHREADS
+#define VCFC_DEC_GTHREADS 128
+#define VCFC_DEC_GCTAS 8
+#define VCFC_DEC_GCMAX 6144
+#endif
+constexpr int kGThreads = VCFC_DEC_GTHREADS, kGWarps = kGThreads / 32;
+constexpr int kCmaxG = VCFC_DEC_GCMAX;      // compressed bytes staged per batch; a line that does not fit is continued in the next batch
+constexpr int kChunksG = kCmaxG / 16 + 2 * 32;
+static_assert(kCmaxG >= 2048 && kCmaxG % 16 == 0, "a batch must at least hold a line start (8 + 960 bytes) and some chunks");
+
 struct SmemG {
     alignas(16) uint8_t stage[kTile];
-    alignas(16) uint8_t cbuf[kCmax + 32];
-    unsigned ctab[kChunks];
+    alignas(16) uint8_t cbuf[kCmaxG + 32];
+    unsigned ctab[kChunksG];
     int l_pos[kMaxL + 1], l_end[kMaxL + 1], l_last[kMaxL + 1], l_coff[kMaxL + 2];
     int l_rq[kMaxL + 1];                     // required length
     int l_c0[kMaxL + 2];                     // first flat chunk index of the line (exclusive prefix of the chunk counts)
     int l_wb[kMaxL + 1];                     // token bytes of the line to walk (the line's final '\n' excluded)
     int n_batch, more, staged, c_first;
+    int cut_next;                            // the batch's only line was cut: chunk to continue from (else -1)
     unsigned long long c_lo;
 };
 
-__global__ void __launch_bounds__(kXThreads, VCFC_DEC_XCTAS)
+__global__ void __launch_bounds__(kGThreads, VCFC_DEC_GCTAS)
 k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ line_start,
                   const unsigned long long* __restrict__ off, unsigned long long n_lines, unsigned long long total,
                   const unsigned int* __restrict__ first_line, const unsigned int* __restrict__ first_chunk,
@@ -606,7 +617,8 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
     const int tile_len = (int)(total - T0 < (unsigned long long)kTile ? total - T0 : (unsigned long long)kTile);
     const unsigned long long T1 = T0 + (unsigned long long)tile_len;
     unsigned long long k0 = first_line[blockIdx.x];
-    unsigned fc_tile = first_chunk[blockIdx.x];         // applies to the first batch's first line only
+    unsigned fc_tile = first_chunk[blockIdx.x];         // chunk the batch's first line is staged from (kWholeLine: from its header)
+    bool contd = false;                                  // that line was begun by an earlier batch of this tile
 
     for (;;) {
         // (1) line table entries of the next batch: lines k0 .. k0 + nb - 1 overlap the tile
@@ -624,14 +636,14 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
             const bool overlaps = kk < n_lines && o < T1;
             unsigned m = __ballot_sync(0xffffffffu, overlaps) & 0x7fffffffu;         // lane 31 only supplies the end of line 30
             int nb = __popc(m);                                                        // off[] is monotone: a prefix of the lanes
-            // later lines are staged whole, so they must fit behind the first; the first may be cut at kCmax
-            // (kCmax compressed bytes always expand to at least a tile of text)
-            const unsigned fits = __ballot_sync(0xffffffffu, ls >= s0 && ls - s0 <= (unsigned long long)kCmax);
+            // later lines are staged whole, so they must fit behind the first; a first line that does not fit is cut at a
+            // chunk boundary and continued by the next batch
+            const unsigned fits = __ballot_sync(0xffffffffu, ls >= s0 && ls - s0 <= (unsigned long long)kCmaxG);
             while (nb > 1 && !((fits >> nb) & 1u)) nb--;
             const unsigned long long o_next = __shfl_down_sync(0xffffffffu, o, 1);
             const unsigned long long ls_next = __shfl_down_sync(0xffffffffu, ls, 1);
             const unsigned long long ls_after = __shfl_sync(0xffffffffu, ls, nb);     // nb <= 31
-            const int staged = (int)min(ls_after - s0, (unsigned long long)kCmax);
+            const int staged = (int)min(ls_after - s0, (unsigned long long)kCmaxG);
             // token bytes to walk and their 16-byte chunks
             const int coff = lane == 0 ? 0 : (int)(ls - s0);
             const int cend = (int)min(ls_next - s0, (unsigned long long)0x7fffffff);
@@ -639,6 +651,7 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
             const int hdrb = (lane == 0 && cont) ? 0 : 8 + rq;
             int wb = lane < nb ? min(cend, staged) - coff - hdrb - (whole ? 1 : 0) : 0;
             if (wb < 0) wb = 0;
+            if (!whole) wb &= ~15;                                                     // a cut line is resumed at a chunk boundary
             int nch = (wb + 15) >> 4, inc = nch;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
@@ -659,6 +672,7 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
                 sm.c_lo = s0;
                 sm.c_first = cont ? (int)fc_tile : -1;
                 sm.staged = staged;
+                sm.cut_next = (nb == 1 && !whole) ? (cont ? (int)fc_tile : 0) + (wb >> 4) : -1;
             }
         }
         __syncthreads();
@@ -676,13 +690,13 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
             const int n16 = (staged - head) >> 4;
             const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
             uint4* d4 = reinterpret_cast<uint4*>(sm.cbuf + phase + head);
-            for (int i = tid; i < n16; i += kXThreads) d4[i] = s4[i];
+            for (int i = tid; i < n16; i += kGThreads) d4[i] = s4[i];
             const int t0 = head + 16 * n16;
             if (tid < staged - t0) sm.cbuf[phase + t0 + tid] = src[t0 + tid];
         }
         // (3) chunk tables of the batch's lines (built once per line by k_dec_sizes): line li's entries go to slot
         //     (l_coff >> 4) + li, the global table's rule relative to the batch
-        for (int li = warp; li < nb; li += kXWarps) {
+        for (int li = warp; li < nb; li += kGWarps) {
             const int coff = sm.l_coff[li];
             const int nslots = ((min(sm.l_coff[li + 1], staged) - coff) >> 4) + 1;
             const unsigned long long lsk = li == 0 ? line_start[k0] : c_lo + (unsigned long long)coff;
@@ -692,8 +706,9 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
         }
         // (4) fill: every 16-byte unit that starts inside the batch's lines gets "0|0\t" in the phase of its line
         {
-            const int f_lo = sm.l_pos[0] <= 0 ? 0 : (sm.l_pos[0] + 15) >> 4, f_hi = (sm.l_end[nb - 1] + 15) >> 4;
-            for (int u = f_lo + tid; u < f_hi; u += kXThreads) {
+            const int f_first = contd ? (nb > 1 ? sm.l_pos[1] : sm.l_end[0]) : sm.l_pos[0];   // a continued line is already filled
+            const int f_lo = f_first <= 0 ? 0 : (f_first + 15) >> 4, f_hi = (sm.l_end[nb - 1] + 15) >> 4;
+            for (int u = f_lo + tid; u < f_hi; u += kGThreads) {
                 const int pos = u << 4;
                 int li = 0;
                 for (int j = 1; j < nb; j++) li += (sm.l_pos[j] <= pos);
@@ -704,7 +719,7 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
         }
         __syncthreads();
         // (5) patch: required sections and line ends (one warp per line) ...
-        for (int li = warp; li < nb; li += kXWarps) {
+        for (int li = warp; li < nb; li += kGWarps) {
             const int lpos = sm.l_pos[li], rq = sm.l_rq[li];
             if (!(li == 0 && c_first >= 0)) {
                 const uint8_t* lp = sm.cbuf + phase + sm.l_coff[li];
@@ -717,7 +732,7 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
         // ... and the token chunks: only what is not the default genotype is written
         {
             const int n_chunks = sm.l_c0[nb];
-            for (int idx = tid; idx < n_chunks; idx += kXThreads) {
+            for (int idx = tid; idx < n_chunks; idx += kGThreads) {
                 int li = 0;
                 for (int j = 1; j < nb; j++) li += (sm.l_c0[j] <= idx);
                 const int c = idx - sm.l_c0[li];
@@ -766,11 +781,17 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
                 }
             }
         }
-        const int more = sm.more;
+        // a cut line goes on in the next batch unless what is left of it lies behind the tile
+        const int cut_next = sm.cut_next;
+        int more = sm.more;
+        if (cut_next >= 0) {
+            const unsigned* tab = sm.ctab + (c_first >= 0 ? -c_first : 0);       // line 0: slot 0 holds chunk max(c_first, 0)
+            more = sm.l_pos[0] + sm.l_rq[0] + (int)(tab[cut_next] >> 1) < tile_len ? 1 : 0;
+        }
         __syncthreads();
         if (!more) break;
-        k0 += (unsigned long long)nb;
-        fc_tile = kWholeLine;
+        if (cut_next >= 0) { fc_tile = (unsigned)cut_next; contd = true; }
+        else { k0 += (unsigned long long)nb; fc_tile = kWholeLine; contd = false; }
     }
     __syncthreads();
     // tile image -> HBM
@@ -780,10 +801,10 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
             const int n16 = tile_len >> 4;
             const uint4* s4 = reinterpret_cast<const uint4*>(sm.stage);
             uint4* d4 = reinterpret_cast<uint4*>(dst);
-            for (int i = tid; i < n16; i += kXThreads) d4[i] = s4[i];
-            for (int i = (n16 << 4) + tid; i < tile_len; i += kXThreads) dst[i] = sm.stage[i];
+            for (int i = tid; i < n16; i += kGThreads) d4[i] = s4[i];
+            for (int i = (n16 << 4) + tid; i < tile_len; i += kGThreads) dst[i] = sm.stage[i];
         } else {
-            for (int i = tid; i < tile_len; i += kXThreads) dst[i] = sm.stage[i];
+            for (int i = tid; i < tile_len; i += kGThreads) dst[i] = sm.stage[i];
         }
     }
 }
@@ -883,7 +904,7 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
         k_dec_expand<<<(unsigned)n_tiles, kXThreads, sizeof(Smem), stream>>>(d_in, line_start, (unsigned long long*)b_offs.p, n_lines,
                                                                             total, (unsigned int*)b_tiles.p, first_chunk, (const unsigned*)b_rq.p, (const unsigned*)b_tab.p, d_out, ctrl);
     else
-        k_dec_expand_grid<<<(unsigned)n_tiles, kXThreads, sizeof(SmemG), stream>>>(d_in, line_start, (unsigned long long*)b_offs.p, n_lines,
+        k_dec_expand_grid<<<(unsigned)n_tiles, kGThreads, sizeof(SmemG), stream>>>(d_in, line_start, (unsigned long long*)b_offs.p, n_lines,
                                                                                   total, (unsigned int*)b_tiles.p, first_chunk, (const unsigned*)b_rq.p, (const unsigned*)b_tab.p, d_out, ctrl);
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeDecodeExpand + 1], stream); ctx->ev_pending[kTimeDecodeExpand] = 1; }
     k_dec_result<<<1, 1, 0, stream>>>(d_result, ctrl, VCFC_OK, total, n_lines);
