@@ -60,15 +60,37 @@ __device__ __forceinline__ bool plausible_line(const uint8_t* __restrict__ in, l
 // ---- D1: speculative line table ---------------------------------------------------------------------
 __global__ void k_dec_walk(const uint8_t* __restrict__ in, long long n, long long n_seg, long long* __restrict__ cand,
                            long long* __restrict__ endp, unsigned long long* __restrict__ cnt) {
-    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per segment: the lanes look for the first plausible line start 128 bytes at a time, then the warp
+    // follows the length headers (uniform loads) to the end of the segment
+    const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (s >= n_seg) return;
     const long long lo = s * kSeg, hi = lo + kSeg < n ? lo + kSeg : n;
     long long c = kNoCand, ll = 0;
-    for (long long p = lo; p < hi; p++) {
-        if (p != 0 && in[p - 1] != '\n') continue;
-        if (plausible_line(in, n, p, &ll)) { c = p; break; }
-        if (p == 0) break;                                   // offset 0 must be a line start
+    for (long long base = lo; base < hi && c == kNoCand; base += 128) {
+        unsigned hit[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const long long p = base + 32 * u + lane;
+            bool h = false;
+            if (p < hi && n - p >= 8) {
+                const bool after_nl = p == 0 || in[p - 1] == '\n';
+                h = after_nl && (in[p] >> 6) == 3 && (in[p + 4] >> 6) == 3;      // both length tags present
+            }
+            hit[u] = __ballot_sync(0xffffffffu, h);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            unsigned m = hit[u];
+            while (m && c == kNoCand) {
+                const long long p = base + 32 * u + (__ffs(m) - 1);
+                m &= m - 1;
+                if (plausible_line(in, n, p, &ll)) c = p;
+            }
+        }
+        if (lo == 0 && c != 0) break;                        // offset 0 must be a line start
     }
+    if (lo == 0 && c != 0) c = kNoCand;
     unsigned long long k = 0;
     long long p = c;
     if (c >= 0) {
@@ -80,9 +102,11 @@ __global__ void k_dec_walk(const uint8_t* __restrict__ in, long long n, long lon
             if (!plausible_line(in, n, p, &ll)) { p = kBroken; break; }
         }
     }
-    cand[s] = c;
-    endp[s] = p;
-    cnt[s] = k;
+    if (lane == 0) {
+        cand[s] = c;
+        endp[s] = p;
+        cnt[s] = k;
+    }
 }
 
 // Chain check, by induction from offset 0: a segment's first line start must be where the previous chain
@@ -232,7 +256,17 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
     if (lane == 0) rq_arr[k] = (unsigned)(bad ? 0 : rq);
     // required section: exactly 9 tabs (compress.cpp:820-828; the 8-tab form means no samples -> generic path)
     unsigned tabs = 0;
-    if (!bad) for (long long i = lane; i < rq; i += 32) tabs += (p[8 + i] == '\t');
+    if (!bad) {
+        for (long long o4 = 4ll * lane; o4 < rq; o4 += 128) {          // four bytes per lane: aligned loads, funnel-shifted
+            const uintptr_t ga = reinterpret_cast<uintptr_t>(p + 8 + o4);
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
+            const int nv = (int)(rq - o4 < 4 ? rq - o4 : 4);
+            const uint32_t w0 = wp[0], w1 = (nv + (int)(ga & 3) > 4) ? wp[1] : 0u;
+            const uint32_t v = __funnelshift_r(w0, w1, 8 * (int)(ga & 3));
+            const uint32_t bm = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
+            tabs += __popc(zero_bytes((v ^ 0x09090909u) | ~bm));
+        }
+    }
 #pragma unroll
     for (int d = 16; d; d >>= 1) tabs += __shfl_xor_sync(0xffffffffu, tabs, d);
     if (tabs != 9) bad = true;
@@ -246,6 +280,7 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
             int nb = (int)(tn - off);
             nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
             uint8_t b[16];
+            uint32_t lit_any = 0, set_any = 0, run_sum = 0, run_zero = 0;
             if (nb > 0) {       // five aligned 32-bit loads instead of sixteen byte loads; bytes past the line are never used
                 const uintptr_t ga = reinterpret_cast<uintptr_t>(p + tb + off);
                 const uint32_t* wp = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
@@ -257,8 +292,25 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
                                        __funnelshift_r(w3, w4, sh)};
 #pragma unroll
                 for (int i = 0; i < 16; i++) b[i] = (uint8_t)(v[i >> 2] >> (8 * (i & 3)));
+                // word-parallel view of the chunk: is there any literal marker (>= 0xE0) or tab / newline among its bytes,
+                // and what the bytes add up to when every one of them is a run token
+                const bool is_last = off + nb == tn;
+                const int nbv = nb - (is_last ? 1 : 0);                  // the line's final '\n' carries no text
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int nj = nb - 4 * j, njv = nbv - 4 * j;
+                    const uint32_t bm = nj >= 4 ? 0xFFFFFFFFu : (nj <= 0 ? 0u : ((1u << (8 * nj)) - 1u));
+                    const uint32_t bmv = njv >= 4 ? 0xFFFFFFFFu : (njv <= 0 ? 0u : ((1u << (8 * njv)) - 1u));
+                    const uint32_t w = v[j];
+                    lit_any |= w & (w << 1) & (w << 2) & 0x80808080u & bm;
+                    set_any |= (zero_bytes(w ^ 0x09090909u) | zero_bytes(w ^ 0x0A0A0A0Au)) & bm;
+                    const uint32_t cv = w & (0x7F7F7F7Fu ^ (((w >> 7) & 0x01010101u) * 0x60u)) & bmv;     // run lengths
+                    run_sum = __dp4a(cv, 0x01010101u, run_sum);
+                    run_zero |= zero_bytes(cv | ~bmv);
+                }
             }
-            const int kind = nb > 0 ? last_setter_kind(b, nb) : 0;
+            set_any |= lit_any;
+            const int kind = (nb > 0 && set_any) ? last_setter_kind(b, nb) : 0;
             // state at chunk start: last setter of the nearest lower lane that has one, else the carry
             const unsigned has = __ballot_sync(0xffffffffu, kind != 0);
             const unsigned below = has & ((1u << lane) - 1u);
@@ -267,7 +319,10 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
             const int k_in = below ? k_src : carry_kind;
             unsigned o = 0, ns = 0, tres = 0;
             int e = 0;
-            if (nb > 0) chunk_measure(b, nb, k_in == 1, off + nb == tn, &o, &ns, &e, &tres);
+            if (nb > 0) {
+                if (k_in != 1 && !lit_any) { o = 4u * run_sum; ns = run_sum; e = run_zero ? 1 : 0; }   // run tokens only
+                else chunk_measure(b, nb, k_in == 1, off + nb == tn, &o, &ns, &e, &tres);
+            }
             err_any |= e;
             // chunk table (text offset << 1 | payload state at the chunk's first byte), consumed by k_dec_expand;
             // line k owns the slots [(ls >> 4) + k, ...): disjoint between lines, <= clen / 16 + 1 of them
@@ -852,7 +907,7 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
     VCFC_CUDA(ctx, cudaMemsetAsync(ctrl, 0, sizeof(Ctrl), stream));
     const unsigned gs = (unsigned)((n_seg + 127) / 128);
     if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeDecodeScan], stream);
-    k_dec_walk<<<gs, 128, 0, stream>>>(d_in, n, n_seg, cand, endp, cnt);
+    k_dec_walk<<<(unsigned)((n_seg * 32 + 127) / 128), 128, 0, stream>>>(d_in, n, n_seg, cand, endp, cnt);
     k_dec_verify<<<gs, 128, 0, stream>>>(n, n_seg, cand, endp, ctrl, 0);
     k_dec_repair<<<1, 1, 0, stream>>>(d_in, n, n_seg, cand, endp, cnt, ctrl);
     k_dec_verify<<<gs, 128, 0, stream>>>(n, n_seg, cand, endp, ctrl, 1);
