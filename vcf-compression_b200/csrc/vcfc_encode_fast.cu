@@ -682,6 +682,301 @@ k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict_
     }
 }
 
+// =====================================================================================================================
+// Streaming encoder: ONE WARP per tile, no CTA barriers.  The warp walks its tile line by line in steps of up to 2 KB
+// (one 64-byte block = 16 samples per lane, loaded straight from global memory into registers), carrying the line /
+// run state in registers; tokens go to a per-warp staging area in shared memory and from there to the tile log.
+// Same ownership rule (cut points), look-back #1 records, tile log, records and gather pass as above.
+// =====================================================================================================================
+#ifndef VCFC_ENC_STILE
+#define VCFC_ENC_STILE 16384
+#define VCFC_ENC_SWARPS 4
+#define VCFC_ENC_SCTAS 8
+#define VCFC_ENC_SSTAGE 3072
+#endif
+constexpr int kSTile = VCFC_ENC_STILE;          // nominal input bytes per tile
+constexpr int kSWarps = VCFC_ENC_SWARPS;        // warps per CTA (independent of each other)
+constexpr int kSCtas = VCFC_ENC_SCTAS;
+constexpr int kSStage = VCFC_ENC_SSTAGE;        // per-warp staging; a tile that expands beyond it is emitted in a second pass
+constexpr int kStep = 2048;                     // bytes per step: 32 lanes x 64
+static_assert(kSTile % 64 == 0, "tiles start on block boundaries");
+
+struct SmemS {
+    alignas(16) uint8_t stage[kSWarps][kSStage + 16];
+};
+
+// byte / word of the input at tile-relative offset r (win = in + gb); outside [0, n) reads as 0
+__device__ __forceinline__ uint32_t ldb(const uint8_t* __restrict__ win, int r, int r_lo, int r_hi) {
+    return (r >= r_lo && r < r_hi) ? win[r] : 0u;
+}
+__device__ __forceinline__ uint32_t ldw(const uint8_t* __restrict__ win, int r, int r_lo, int r_hi) {   // r multiple of 4
+    if (r >= r_lo && r + 4 <= r_hi) return *reinterpret_cast<const uint32_t*>(win + r);
+    return ldb(win, r, r_lo, r_hi) | (ldb(win, r + 1, r_lo, r_hi) << 8) | (ldb(win, r + 2, r_lo, r_hi) << 16) |
+           (ldb(win, r + 3, r_lo, r_hi) << 24);
+}
+
+__global__ void __launch_bounds__(32 * kSWarps, kSCtas)
+k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
+                unsigned int* __restrict__ s1, unsigned long long* __restrict__ rec_pos, unsigned long long* __restrict__ rec_size,
+                unsigned long long* __restrict__ rec_lines, int n_tiles, unsigned long long log_cap) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    SmemS& sm = *reinterpret_cast<SmemS*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* const stage = sm.stage[warp];
+    const int gw = (int)blockIdx.x * kSWarps + warp, nw = (int)gridDim.x * kSWarps;
+    int irr_seen = 0;                       // ctrl->irregular as of one tile ago (the load stays off the critical path)
+
+    for (int tile = gw; tile < n_tiles; tile += nw) {
+        const int irr_now = irr_seen;
+        irr_seen = *((volatile int*)&ctrl->irregular);
+        if (irr_now) {                      // some tile already gave up: keep the look-back chains alive and move on
+            if (lane == 0) s1[tile] = (2u << 30) | ((unsigned)kNone << 8);
+            continue;
+        }
+        const long long t0 = (long long)tile * kSTile;
+        const long long gb = t0 - 64;                                   // tile-relative offsets: r = g - gb (a multiple of 64 apart)
+        const uint8_t* const win = in + gb;
+        const int r_lo = gb < 0 ? 64 : 0;                               // valid relative range [r_lo, r_hi)
+        const int r_hi = (int)(n - gb < (long long)(1 << 24) ? n - gb : (long long)(1 << 24));
+        int irregular = 0;
+        if (t0 + kSTile >= n && in[n - 1] != '\n') irregular = 1;        // no final newline: generic path
+        // ---- cut points ------------------------------------------------------------------------------------------------
+        int ks, ke;
+        int cs, ce;
+        {
+            const long long vlo_s = t0 - kHalo > 0 ? t0 - kHalo : 0, vhi_s = t0 + kHalo < n ? t0 + kHalo : n;
+            cs = (int)(cut_find(in, 0, vlo_s, vhi_s, n, t0, lane, &ks) - gb);
+            const long long t1 = t0 + kSTile;
+            const long long vlo_e = t1 - kHalo > 0 ? t1 - kHalo : 0, vhi_e = t1 + kHalo < n ? t1 + kHalo : n;
+            ce = (int)(cut_find(in, 0, vlo_e, vhi_e, n, t1, lane, &ke) - gb);
+            if (ks == kCutBad || ke == kCutBad) irregular = 2;
+        }
+        // ---- look-back #1, published first: what the run that leaves the tile looks like (see prep above) ----------------
+        int lb_uniform = 0, lb_lc = kNone, lb_nsamp = 0;
+        {
+            unsigned word = (2u << 30) | ((unsigned)kNone << 8);
+            if (ke == kCutSample && !irregular) {
+                const int lo = 64 > r_lo + 4 ? 64 : r_lo + 4;             // sample starts below t0 belong to the previous tile
+                const int lc = gt_class3(win + ce - 4);
+                lb_lc = lc;
+                word = (2u << 30) | ((unsigned)lc << 8);
+                if (lc < 4) {
+                    int found = -1;
+                    for (int top = ce - 4; top >= lo && found < 0; top -= 128) {
+                        const int p = top - 4 * lane;
+                        bool head = false;
+                        if (p >= lo) {
+                            const int pa = p & ~3, shq = 8 * (p & 3);
+                            const uint32_t wa = ldw(win, pa - 4, r_lo, r_hi), wb = ldw(win, pa, r_lo, r_hi), wc = ldw(win, pa + 4, r_lo, r_hi);
+                            const uint32_t w1 = __funnelshift_r(wb, wc, shq), w0 = __funnelshift_r(wa, wb, shq);
+                            head = !((((w1 & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u) && w1 == w0);
+                        }
+                        const unsigned hm = __ballot_sync(0xffffffffu, head);
+                        if (hm) found = top - 4 * (__ffs(hm) - 1);
+                    }
+                    if (found >= 0) {
+                        word |= (unsigned)mod_chunk(((ce - found) >> 2) - 1, lc == 0) + 1u;
+                    } else {
+                        lb_uniform = 1;
+                        lb_nsamp = (ce - 64) >> 2;
+                        word = (1u << 30) | ((unsigned)lc << 8) | (unsigned)mod_chunk(lb_nsamp, lc == 0);   // relative
+                    }
+                }
+            }
+            if (lane == 0) *((volatile unsigned*)&s1[tile]) = word;
+        }
+        // ---- look-back #1, read: chunk count of the run that enters the tile ---------------------------------------------
+        int ein0 = kNoHead;
+        if (ks == kCutSample && tile > 0 && cs < ce && !irregular) {
+            const int pc0 = gt_class3(win + cs - 4);
+            if (pc0 < 4) {
+                int cnt_in = 0;
+                if (lane == 0) {
+                    int acc = 0;
+                    for (int j = tile - 1;; j--) {
+                        unsigned v;
+                        do { v = *((volatile unsigned*)&s1[j]); } while ((v >> 30) == 0);
+                        acc += (int)(v & 0xFFu);
+                        if ((v >> 30) == 2u || j == 0) break;
+                    }
+                    cnt_in = mod_chunk(acc - 1 + 127 * 31, pc0 == 0) + 1;            // open chunk count before the tile, 1..M
+                    if (lb_uniform)
+                        *((volatile unsigned*)&s1[tile]) =
+                            (2u << 30) | ((unsigned)lb_lc << 8) | ((unsigned)mod_chunk(cnt_in + lb_nsamp - 1, lb_lc == 0) + 1u);
+                }
+                cnt_in = __shfl_sync(0xffffffffu, cnt_in, 0);
+                ein0 = cs - 4 * cnt_in;
+            }
+        }
+        // ---- the tile, line by line; pass 0 emits into the staging area while the output fits, pass 1 (rare) straight
+        //      into the log once the size is known -------------------------------------------------------------------------
+        int total = 0, nl = 0, my_off = 0;
+        unsigned long long pos = 0ull;
+        bool overflow = false, skip_write = false;
+        for (int pass = 0; pass < 2; pass++) {
+            uint8_t* const image = pass == 0 ? stage : log + pos;
+            bool emit_on = !irregular;
+            int o = 0, cur = cs, ein_carry = ein0;
+            bool in_req = ks == kCutLine, first = ks == kCutSampleFirst;
+            nl = 0;
+            while (cur < ce && !irregular) {
+                if (in_req) {
+                    // ---- a line start: two length headers + the required section (compress.cpp:32-100) ----------------
+                    const int ls = cur;
+                    const int s0 = line_scan(win, ls, r_hi, lane);
+                    if (s0 < 0) { irregular = 4; break; }
+                    if (nl >= kMaxNl) { irregular = 3; break; }
+                    const int rq = s0 - ls;
+                    if (pass == 0 && o + 8 + rq > kSStage) { emit_on = false; overflow = true; }
+                    if (emit_on) {
+                        uint8_t* d = image + o;
+                        if (lane < 4) d[lane] = lane == 0 ? 0xC0 : 0;                       // line length: patched by k_patch_headers
+                        if (lane >= 4 && lane < 8) {
+                            const unsigned v = (unsigned)rq;
+                            d[lane] = lane == 4 ? (uint8_t)((v >> 24) | 0xC0) : (uint8_t)(v >> (8 * (7 - lane)));
+                        }
+                        for (int k = lane; k < rq; k += 32) d[8 + k] = win[ls + k];
+                    }
+                    if (lane == nl) my_off = o;
+                    nl++;
+                    o += 8 + rq;
+                    cur = s0;
+                    in_req = false; first = true; ein_carry = kNoHead;
+                    continue;
+                }
+                // ---- a step of samples: those that start in [cur, bound), up to the line's end ---------------------------
+                const int a = cur, wstart = a & ~63, blk = wstart + 64 * lane, phase = a & 3, base = blk + phase;
+                const int bound = min(ce, wstart + kStep);
+                uint32_t W[18];
+                if (blk >= r_lo && blk + 64 <= r_hi) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(win + blk + 16 * q);
+                        W[4 * q + 1] = v.x; W[4 * q + 2] = v.y; W[4 * q + 3] = v.z; W[4 * q + 4] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) W[q + 1] = ldw(win, blk + 4 * q, r_lo, r_hi);
+                }
+                W[0] = __shfl_up_sync(0xffffffffu, W[16], 1);
+                W[17] = __shfl_down_sync(0xffffffffu, W[1], 1);
+                if (lane == 0) W[0] = ldw(win, blk - 4, r_lo, r_hi);
+                if (lane == 31) W[17] = ldw(win, blk + 64, r_lo, r_hi);
+                const int sh = 8 * phase;
+                const uint32_t sp = __funnelshift_r(W[0], W[1], sh);
+                const uint32_t pc_all = ((sp & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u ? 1u : 0u;
+                uint32_t Craw = 0, accA = sp << 31, accB = (sp >> 16) << 31;   // allele bits are shifted in from the top
+#pragma unroll
+                for (int k = 0; k < 16; k++) {
+                    const uint32_t sw = __funnelshift_r(W[k + 1], W[k + 2], sh);
+                    if (((sw & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u) Craw |= 1u << k;      // "x|y\t" with x, y in {0,1}
+                    accA = __funnelshift_r(accA, sw, 1);
+                    accB = __funnelshift_r(accB, sw >> 16, 1);
+                }
+                Item it;
+                it.base = base; it.Ap = accA >> 15; it.Bp = accB >> 15; it.hdr = 0; it.seg = 0;
+                // samples that start in [a, bound)
+                const int rel_a = a - base, rel_b = bound - base;
+                const int klo = rel_a > 0 ? rel_a >> 2 : 0, khi = rel_b >= 64 ? 16 : (rel_b > 0 ? (rel_b + 3) >> 2 : 0);
+                uint32_t V = khi > klo ? (((1u << khi) - 1u) & ~((1u << klo) - 1u)) : 0u;
+                // the line's last sample carries the '\n': the first such sample ends the step
+                int kend = -1;
+                for (uint32_t t = V & ~Craw; t; t &= t - 1) {
+                    const int k = __ffs(t) - 1;
+                    if (ldb(win, base + 4 * k + 3, r_lo, r_hi) == '\n') { kend = k; break; }
+                }
+                const unsigned endm = __ballot_sync(0xffffffffu, kend >= 0);
+                const int le = endm ? __ffs(endm) - 1 : 32;
+                if (lane > le) V = 0;
+                if (lane == le) V &= (2u << kend) - 1u;
+                const int q_end = __shfl_sync(0xffffffffu, base + 4 * kend + 3, le & 31);   // the '\n' (valid when endm)
+                // everything valid that is not "x|y\t": literals, and the sample that ends the line
+                uint32_t L = 0;
+                bool irr = false;
+                for (uint32_t t = V & ~Craw; t; t &= t - 1) {
+                    const int k = __ffs(t) - 1;
+                    const uint8_t* p = win + base + 4 * k;
+                    const bool inside = base + 4 * k >= r_lo && base + 4 * k + 4 <= r_hi;
+                    const uint32_t b0 = inside ? p[0] : 0u, b1 = inside ? p[1] : 0u, b2 = inside ? p[2] : 0u, b3 = inside ? p[3] : 0u;
+                    if (k == kend ? (b3 != '\n') : (b3 != '\t')) irr = true;
+                    if (b1 == '|' && (b0 & 0xFEu) == 0x30u && (b2 & 0xFEu) == 0x30u) {
+                        Craw |= 1u << k;           // coded sample terminated by the line's newline
+                    } else {
+                        if (is_sep(b0) || is_sep(b1) || is_sep(b2)) irr = true;
+                        L |= 1u << k;
+                    }
+                }
+                if (__any_sync(0xffffffffu, irr)) { irregular = 6; break; }    // a sample column that is not 3 bytes + separator
+                const uint32_t F = (first && lane == 0) ? (1u << klo) : 0u;
+                const uint32_t Cprev = (Craw << 1) | pc_all;
+                const uint32_t same = ~(((it.Ap >> 1) ^ it.Ap) | ((it.Bp >> 1) ^ it.Bp));   // same genotype bits as the previous word
+                const uint32_t Hd = V & (F | ~(Craw & Cprev & same));
+                const uint32_t PC = (Cprev & 0xFFFFu) & ~F;
+                it.V = V; it.C = Craw & V; it.L = L; it.Hd = Hd; it.CL = Hd & PC;
+                it.kend = (lane == le) ? kend : -1;
+                it.pcoded = (int)((PC >> klo) & 1u);
+                const int lh = Hd ? base + 4 * (31 - __clz(Hd)) : kNoHead;
+                // last run head before each item: nearest lower lane that has one, else what the earlier steps left
+                int ein;
+                {
+                    const unsigned hm = __ballot_sync(0xffffffffu, lh != kNoHead);
+                    const unsigned below = hm & ((1u << lane) - 1u);
+                    const int g = __shfl_sync(0xffffffffu, lh, below ? 31 - __clz(below) : 0);
+                    ein = below ? g : ein_carry;
+                    const int last = __shfl_sync(0xffffffffu, lh, hm ? 31 - __clz(hm) : 0);
+                    if (hm) ein_carry = last;
+                }
+                uint32_t cf = 0;
+                int h0 = 0;
+                const int n0 = item_count(it, ein, &cf, &h0);
+                int inc = n0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+                const int step_total = __shfl_sync(0xffffffffu, inc, 31);
+                if (pass == 0 && o + step_total > kSStage) { emit_on = false; overflow = true; }
+                if (emit_on) item_emit(win, it, cf, h0, image + o + inc - n0);
+                o += step_total;
+                first = false;
+                if (endm) { cur = q_end + 1; in_req = true; }
+                else cur = a + 4 * ((bound - a + 3) >> 2);
+            }
+            if (pass == 1) break;
+            // ---- the tile's place in the log: one atomic; the final position comes from the scan over the tile records -------
+            if (irregular) {
+                if (lane == 0 && atomicCAS(&ctrl->irregular, 0, irregular) == 0) ctrl->total_lines = (unsigned long long)tile;   // (diagnostics)
+                o = 0; nl = 0;
+            }
+            total = o;
+            const unsigned long long need = (unsigned long long)total + 2ull * (unsigned long long)nl;   // bytes + u16 line offsets
+            if (lane == 0) {
+                pos = need ? atomicAdd(&ctrl->log_cursor, need) : 0ull;
+                rec_pos[tile] = pos; rec_size[tile] = (unsigned long long)total; rec_lines[tile] = (unsigned long long)nl;
+                if (pos + need > log_cap) atomicExch(&ctrl->cap_exceeded, 1);
+            }
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            skip_write = pos + need > log_cap;
+            if (irregular || skip_write || total == 0 || !overflow) break;
+        }
+        if (irregular || skip_write || total == 0) continue;
+        uint8_t* const dst = log + pos;
+        if (lane < nl) { dst[total + 2 * lane] = (uint8_t)my_off; dst[total + 2 * lane + 1] = (uint8_t)((unsigned)my_off >> 8); }
+        if (!overflow) {
+            // staging -> log: aligned 4-byte stores, source words funnel-shifted
+            __syncwarp();
+            const int mis = (int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);      // bytes until dst is 4-byte aligned
+            const int head = min(mis, total);
+            if (lane < head) dst[lane] = stage[lane];
+            const int nwords = (total - head) >> 2;
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage);
+            uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+            for (int k = lane; k < nwords; k += 32) dw[k] = __funnelshift_r(sw[k], sw[k + 1], 8 * head);
+            const int tail0 = head + 4 * nwords;
+            if (lane < total - tail0) dst[tail0 + lane] = stage[tail0 + lane];
+            __syncwarp();
+        }
+    }
+}
+
 // Final totals from the tile-record scans; decides capacity before any byte reaches the caller's buffer.
 __global__ void k_enc_totals(Ctrl* __restrict__ ctrl, unsigned long long out_cap) {
     if (ctrl->total_bytes > out_cap) ctrl->cap_exceeded = 1;
@@ -768,12 +1063,19 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         ctx->launches++;
         return VCFC_OK;
     }
+#ifndef VCFC_ENC_CTA_TILES
+    constexpr bool kStream = true;
+#else
+    constexpr bool kStream = false;
+#endif
     static bool attr_set = false;
     if (!attr_set) {
         VCFC_CUDA(ctx, cudaFuncSetAttribute(k_encode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        VCFC_CUDA(ctx, cudaFuncSetAttribute(k_encode_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
         attr_set = true;
     }
-    const size_t n_tiles = (in_len + kTile - 1) / kTile;
+    const size_t tile_bytes = kStream ? kSTile : kTile;
+    const size_t n_tiles = (in_len + tile_bytes - 1) / tile_bytes;
     const size_t lines_cap = in_len / 64 + 1024;
     DevBuf &ws = ctx->ws[10], &b_log = ctx->ws[11], &b_scr = ctx->ws[1];
     const size_t off_s1 = 256, off_rec = off_s1 + ((n_tiles * 4 + 255) & ~size_t(255));
@@ -795,10 +1097,11 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
     static int resident = 0;        // CTAs that are guaranteed to be co-resident (look-back #1 spins on its neighbour)
     if (!resident) {
         int per_sm = 0;
-        VCFC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_tiles, kThreads, sizeof(Smem)));
+        if (kStream) VCFC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_stream, 32 * kSWarps, sizeof(SmemS)));
+        else VCFC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_tiles, kThreads, sizeof(Smem)));
         resident = std::max(1, per_sm) * ctx->sm_count;
     }
-    const unsigned grid = (unsigned)std::min<size_t>(n_tiles, (size_t)resident);
+    const unsigned grid = (unsigned)std::min<size_t>(kStream ? (n_tiles + kSWarps - 1) / kSWarps : n_tiles, (size_t)resident);
     if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeEncode], stream);
     {   // cooperative launch: every CTA is resident, which look-back #1 (a CTA spins on its neighbour's tile) relies on
         const uint8_t* a_in = d_in;
@@ -808,7 +1111,10 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         int a_tiles = (int)n_tiles;
         unsigned long long a_cap = (unsigned long long)log_cap;
         void* args[] = {&a_in, &a_n, &a_log, &ctrl, &a_s1, &rec_pos, &rec_size, &rec_lines, &a_tiles, &a_cap};
-        VCFC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_encode_tiles, dim3(grid), dim3(kThreads), args, sizeof(Smem), stream));
+        if (kStream)
+            VCFC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_encode_stream, dim3(grid), dim3(32 * kSWarps), args, sizeof(SmemS), stream));
+        else
+            VCFC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_encode_tiles, dim3(grid), dim3(kThreads), args, sizeof(Smem), stream));
     }
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeEncode + 1], stream); ctx->ev_pending[kTimeEncode] = 1; }
     ctx->launches += 1;
