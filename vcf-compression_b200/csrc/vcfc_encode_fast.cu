@@ -715,6 +715,66 @@ __device__ __forceinline__ uint32_t ldw(const uint8_t* __restrict__ win, int r, 
            (ldb(win, r + 3, r_lo, r_hi) << 24);
 }
 
+// End of the required section of the line that starts at relative offset ls, 512 bytes per round trip (16 per lane):
+// returns the offset of the first sample (after the 9th tab) or -1 when irregular -- same rules as line_scan.
+__device__ int line_scan16(const uint8_t* __restrict__ win, int ls, int r_lo, int r_hi, int lane) {
+    if (is_sep(ldb(win, ls, r_lo, r_hi))) return -1;           // empty first column / empty line
+    int tabs = 0;
+    unsigned carry = 0;                                          // the byte before the round's first byte is a tab
+    for (int base16 = ls & ~15; base16 < ls + kMaxReq + 16; base16 += 512) {
+        const int g = base16 + 16 * lane;
+        uint32_t w[4];
+        if (g >= r_lo && g + 16 <= r_hi) {
+            const uint4 v = *reinterpret_cast<const uint4*>(win + g);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                w[q] = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int r = g + 4 * q + b;
+                    w[q] |= ((r >= r_lo && r < r_hi) ? (uint32_t)win[r] : (uint32_t)'\n') << (8 * b);   // past the end: a newline
+                }
+            }
+        }
+        unsigned tm = 0, nm = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            tm |= nibble_of(zero_bytes(w[q] ^ 0x09090909u)) << (4 * q);
+            nm |= nibble_of(zero_bytes(w[q] ^ 0x0A0A0A0Au)) << (4 * q);
+        }
+        if (g < ls) { const unsigned keep = ~((1u << (ls - g)) - 1u); tm &= keep; nm &= keep; }   // bytes before the line (g + 16 > ls here)
+        if (g + 16 <= ls) { tm = 0; nm = 0; }
+        const int cnt = __popc(tm);
+        int inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        const unsigned prev15 = __shfl_up_sync(0xffffffffu, tm >> 15, 1);
+        const unsigned tin = lane == 0 ? carry : (prev15 & 1u);  // the byte before this lane's first byte is a tab
+        const unsigned dbl = tm & ((tm << 1) | tin) & 0xFFFFu;   // a tab right after a tab: empty field
+        const unsigned hitm = __ballot_sync(0xffffffffu, tabs + inc >= 9);
+        if (hitm) {
+            const int j = __ffs(hitm) - 1;
+            const int before = __shfl_sync(0xffffffffu, tabs + inc - cnt, j);
+            const unsigned tmj = __shfl_sync(0xffffffffu, tm, j);
+            const int bit = __fns(tmj, 0, 9 - before);            // position of the 9th tab inside lane j's 16 bytes
+            const unsigned upto = (2u << bit) - 1u;
+            const unsigned badm = lane < j ? (nm | dbl) : (lane == j ? ((nm | dbl) & upto) : 0u);
+            if (__any_sync(0xffffffffu, badm != 0u)) return -1;
+            const int s0 = base16 + 16 * j + bit + 1;
+            if (s0 - ls > kMaxReq) return -1;
+            // a FORMAT column spelled like a genotype ("0|1") would make the first sample look like a run continuation
+            const uint32_t wl = __funnelshift_r(ldw(win, (s0 - 4) & ~3, r_lo, r_hi), ldw(win, ((s0 - 4) & ~3) + 4, r_lo, r_hi), 8 * ((s0 - 4) & 3));
+            return ((wl & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u ? -1 : s0;
+        }
+        if (__any_sync(0xffffffffu, (nm | dbl) != 0u)) return -1; // fewer than 10 columns / empty field
+        tabs += __shfl_sync(0xffffffffu, inc, 31);
+        carry = __shfl_sync(0xffffffffu, tm >> 15, 31) & 1u;
+    }
+    return -1;
+}
+
 __global__ void __launch_bounds__(32 * kSWarps, kSCtas)
 k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
                 unsigned int* __restrict__ s1, unsigned long long* __restrict__ rec_pos, unsigned long long* __restrict__ rec_size,
@@ -743,13 +803,11 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
         // ---- cut points ------------------------------------------------------------------------------------------------
         int ks, ke;
         int cs, ce;
-        {
-            const long long vlo_s = t0 - kHalo > 0 ? t0 - kHalo : 0, vhi_s = t0 + kHalo < n ? t0 + kHalo : n;
-            cs = (int)(cut_find(in, 0, vlo_s, vhi_s, n, t0, lane, &ks) - gb);
+        {   // the end cut first: the look-back record the next tile waits for depends on it alone
             const long long t1 = t0 + kSTile;
             const long long vlo_e = t1 - kHalo > 0 ? t1 - kHalo : 0, vhi_e = t1 + kHalo < n ? t1 + kHalo : n;
             ce = (int)(cut_find(in, 0, vlo_e, vhi_e, n, t1, lane, &ke) - gb);
-            if (ks == kCutBad || ke == kCutBad) irregular = 2;
+            if (ke == kCutBad) irregular = 2;
         }
         // ---- look-back #1, published first: what the run that leaves the tile looks like (see prep above) ----------------
         int lb_uniform = 0, lb_lc = kNone, lb_nsamp = 0;
@@ -785,29 +843,17 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
             }
             if (lane == 0) *((volatile unsigned*)&s1[tile]) = word;
         }
-        // ---- look-back #1, read: chunk count of the run that enters the tile ---------------------------------------------
-        int ein0 = kNoHead;
-        if (ks == kCutSample && tile > 0 && cs < ce && !irregular) {
-            const int pc0 = gt_class3(win + cs - 4);
-            if (pc0 < 4) {
-                int cnt_in = 0;
-                if (lane == 0) {
-                    int acc = 0;
-                    for (int j = tile - 1;; j--) {
-                        unsigned v;
-                        do { v = *((volatile unsigned*)&s1[j]); } while ((v >> 30) == 0);
-                        acc += (int)(v & 0xFFu);
-                        if ((v >> 30) == 2u || j == 0) break;
-                    }
-                    cnt_in = mod_chunk(acc - 1 + 127 * 31, pc0 == 0) + 1;            // open chunk count before the tile, 1..M
-                    if (lb_uniform)
-                        *((volatile unsigned*)&s1[tile]) =
-                            (2u << 30) | ((unsigned)lb_lc << 8) | ((unsigned)mod_chunk(cnt_in + lb_nsamp - 1, lb_lc == 0) + 1u);
-                }
-                cnt_in = __shfl_sync(0xffffffffu, cnt_in, 0);
-                ein0 = cs - 4 * cnt_in;
-            }
+        {
+            const long long vlo_s = t0 - kHalo > 0 ? t0 - kHalo : 0, vhi_s = t0 + kHalo < n ? t0 + kHalo : n;
+            cs = (int)(cut_find(in, 0, vlo_s, vhi_s, n, t0, lane, &ks) - gb);
+            if (ks == kCutBad) irregular = 2;
         }
+        // ---- look-back #1, read: chunk count of the run that enters the tile -- resolved as late as possible (just before
+        //      the first byte count), so the predecessor's record is normally there already -------------------------------
+        int ein0 = kNoHead;
+        int pc0 = kNone;
+        if (ks == kCutSample && tile > 0 && cs < ce && !irregular) pc0 = gt_class3(win + cs - 4);
+        bool need_lb = pc0 < 4;
         // ---- the tile, line by line; pass 0 emits into the staging area while the output fits, pass 1 (rare) straight
         //      into the log once the size is known -------------------------------------------------------------------------
         int total = 0, nl = 0, my_off = 0;
@@ -823,7 +869,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 if (in_req) {
                     // ---- a line start: two length headers + the required section (compress.cpp:32-100) ----------------
                     const int ls = cur;
-                    const int s0 = line_scan(win, ls, r_hi, lane);
+                    const int s0 = line_scan16(win, ls, r_lo, r_hi, lane);
                     if (s0 < 0) { irregular = 4; break; }
                     if (nl >= kMaxNl) { irregular = 3; break; }
                     const int rq = s0 - ls;
@@ -916,6 +962,26 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 it.kend = (lane == le) ? kend : -1;
                 it.pcoded = (int)((PC >> klo) & 1u);
                 const int lh = Hd ? base + 4 * (31 - __clz(Hd)) : kNoHead;
+                if (need_lb) {
+                    int cnt_in = 0;
+                    if (lane == 0) {
+                        int acc = 0;
+                        for (int j = tile - 1;; j--) {
+                            unsigned v = *((volatile unsigned*)&s1[j]);
+                            while ((v >> 30) == 0) { __nanosleep(64); v = *((volatile unsigned*)&s1[j]); }
+                            acc += (int)(v & 0xFFu);
+                            if ((v >> 30) == 2u || j == 0) break;
+                        }
+                        cnt_in = mod_chunk(acc - 1 + 127 * 31, pc0 == 0) + 1;        // open chunk count before the tile, 1..M
+                        if (lb_uniform)
+                            *((volatile unsigned*)&s1[tile]) =
+                                (2u << 30) | ((unsigned)lb_lc << 8) | ((unsigned)mod_chunk(cnt_in + lb_nsamp - 1, lb_lc == 0) + 1u);
+                    }
+                    cnt_in = __shfl_sync(0xffffffffu, cnt_in, 0);
+                    ein0 = cs - 4 * cnt_in;
+                    ein_carry = ein0;
+                    need_lb = false;
+                }
                 // last run head before each item: nearest lower lane that has one, else what the earlier steps left
                 int ein;
                 {
