@@ -346,7 +346,7 @@ def main():
                 "kernel": name, "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / step_ms if step_ms else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
 
-    enc_kernel = "k_encode_tiles (single pass over the input)" if enc_path == pkg.PATH_FAST else "generic line-serial kernels (whole step)"
+    enc_kernel = "k_encode_stream (single pass over the input)" if enc_path == pkg.PATH_FAST else "generic line-serial kernels (whole step)"
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": enc_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": enc_launches,
@@ -357,7 +357,7 @@ def main():
     if not args.no_decode:
         dec_ms, dec_kms, dec_launches, dclocks = timed(
             lambda: codec.decode_dev(d_out.data_ptr(), n_out, args.samples, d_txt.data_ptr(), d_txt.numel(), d_res.data_ptr(), stream), 2)
-        dec_kernel = "k_decode_expand" if dec_path == pkg.PATH_FAST else "generic line-serial kernels (whole step)"
+        dec_kernel = "k_dec_expand_grid (fill and patch; k_dec_expand when sample text is off the 4-byte grid)" if dec_path == pkg.PATH_FAST else "generic line-serial kernels (whole step)"
         out["decode"] = {"metric": "uncompressed-VCF GB/s decode", "value": tot_in / (dec_ms * 1e-3) / 1e9, "unit": UNIT,
                          "ms_per_step": dec_ms, "gpu_launches": dec_launches, "clocks": dclocks,
                          "roofline": roofline(dec_kms, n_in + n_out, dec_ms, dec_kernel, "decode")}

@@ -2,24 +2,27 @@
 //
 // "Regular" = what a GT-only VCF looks like: '\n'-terminated lines, single tabs, >= 10 columns,
 // every sample column exactly 3 bytes (a|b, a/b, ./. ...), required section (CHROM..FORMAT) of
-// at most kMaxReq bytes, lines of at least ~0.5 KB.  Anything else sets ctrl->irregular and the
-// caller reruns the block on the generic kernels (vcfc_generic.cu).  Output bytes are those of
-// compress_data_line (/root/reference/src/compress.cpp:5-203) for every line.
+// at most kMaxReq bytes, at most kMaxNl line starts per 16 KB tile.  Anything else sets
+// ctrl->irregular and the caller reruns the block on the generic kernels (vcfc_generic.cu).
+// Output bytes are those of compress_data_line (/root/reference/src/compress.cpp:5-203) for every line.
 //
-// One CTA = one tile of 14 KB of input; HBM traffic = input read once + output written once:
-//   1. bulk async copy (TMA engine: cp.async.bulk + mbarrier) of the tile and 1 KB halos into smem
-//   2. cut points: a tile owns the units (one sample column, or one whole required section) that
+// k_encode_stream: ONE WARP per tile of 16 KB, no CTA barriers; HBM traffic = input read once + output
+// written once (+ the tile log, see 6):
+//   1. cut points: a tile owns the units (one sample column, or one whole required section) that
 //      START in [cut(i*T), cut((i+1)*T)); both neighbours derive the shared cut from the same bytes
-//   3. newline list (16-byte AND-filter) -> line segments (9th tab by warp ballot/popc)
-//   4. items = 32-byte blocks of 8 phase-aligned sample words, two per thread, kept in registers as
-//      8-bit masks: valid / coded / literal / run head / closing token
-//   5. look-back #1 (one word per tile): how long the run that enters the tile already is -- chunks
-//      are 127 / 31 samples counted from the run's head (compress.cpp:129-170)
-//   6. byte counts -> packed warp scan -> look-back #2 (decoupled, 16-byte status words): output
-//      offset and line index of the tile
-//   7. tokens / literals / required sections are written to smem staging and stored to HBM
-// A second tiny kernel patches the 4-byte line-length headers (they need the NEXT line's offset)
-// and writes the result block.
+//   2. look-back #1 (one word per tile): how long the run that enters the tile already is -- chunks
+//      are 127 / 31 samples counted from the run's head (compress.cpp:129-170), which may lie many
+//      tiles back; a tile publishes its record before doing anything else
+//   3. the warp walks its tile line by line: a line start = 9th tab found 512 bytes per round trip,
+//      two length headers + the required section copied through
+//   4. samples in steps of 2 KB: every lane loads one 64-byte block (16 phase-aligned sample words)
+//      straight into registers and classifies it into 16-bit masks: valid / coded / literal / run head /
+//      closing token / allele bits; the line's '\n' ends the step
+//   5. closed-form byte count per lane -> warp scan -> tokens and literals into a per-warp staging area
+//   6. the tile's bytes are appended to a tile log at a position reserved with ONE atomicAdd (no scan
+//      chain); two device scans over the per-tile (bytes, lines) records give the final positions,
+//      k_gather_tiles moves the bytes and k_patch_headers fills in the 4-byte line-length headers
+//      (they need the NEXT line's offset) and the result block.
 #include <algorithm>
 
 #include "vcfc_common.cuh"
@@ -28,24 +31,9 @@
 namespace vcfc {
 namespace enc {
 
-#ifndef VCFC_ENC_TILE
-#define VCFC_ENC_TILE 14336
-#define VCFC_ENC_THREADS 256
-#define VCFC_ENC_STAGE 8192
-#define VCFC_ENC_CTAS 5
-#endif
-constexpr int kTile = VCFC_ENC_TILE;    // nominal input bytes per tile (224 blocks of 64)
-constexpr int kHalo = 1024;
-constexpr int kPad = 32;                // zeroed bytes in front of / behind the window
+constexpr int kHalo = 1024;             // how far around a nominal tile boundary a cut point is searched
 constexpr int kMaxReq = kHalo - 64;     // longest required section taken by this path
-constexpr int kWin = kTile + 2 * kHalo + 2 * kPad;
-constexpr int kStage = VCFC_ENC_STAGE;            // smem staging; tiles that expand beyond it store straight to HBM
-constexpr int kMaxNl = 30;              // newlines per tile taken by this path (lines >= ~0.5 KB)
-constexpr int kMaxSeg = kMaxNl + 2;
-constexpr int kThreads = VCFC_ENC_THREADS;
-constexpr int kWarps = kThreads / 32;
-constexpr int kMaxItems = kThreads;     // one item per thread, held in registers
-constexpr int kCtasPerSm = VCFC_ENC_CTAS;
+constexpr int kMaxNl = 30;              // line starts per tile taken by this path (one lane each keeps the line's offset)
 
 enum { kCutLine = 0, kCutSample = 1, kCutSampleFirst = 2, kCutEnd = 3, kCutBad = 4 };
 constexpr int kNone = 7;                // "no open run" class
@@ -60,33 +48,6 @@ struct Ctrl {                           // one per launch, zeroed by the host
     unsigned long long line_cap;
     unsigned long long log_cursor, log_cap;   // the tile log: tile outputs in arrival order, gathered by k_gather_tiles
 };
-
-struct Seg {                            // a run of sample words of one line inside the tile
-    int a, e;                           // sample bytes [a, e), window-relative
-    int ls, s0;                         // line start / first sample if the line starts in this tile, else ls = -1
-    int item0;                          // first item index
-    int flags;                          // bit0: span ends with the line's '\n'; bit1: first sample of span is first of line
-    int out0;                           // output offset (tile-relative) of the line start -- valid if ls >= 0
-    int pad;
-};
-
-struct Smem {
-    alignas(128) uint8_t win[2][kWin];  // double-buffered window: the next tile loads while this one is processed
-    alignas(16) uint8_t stage[kStage + 16];
-    alignas(8) uint64_t mbar[2];
-    Seg seg[kMaxSeg];
-    int nlpos[kMaxNl + 2], nls0[kMaxNl + 2];   // newline positions of the scanned range and the first sample after each
-    int n_nl, n_seg, n_items, n_lines;
-    int tile, next_tile, issued[2], irregular;
-    int cs, cs_kind, ce, ce_kind, cs_s0;
-    int lb_uniform, lb_lc, lb_nsamp;        // look-back #1: the tile has no run head (its record is relative until resolved)
-    int ein_virtual;
-    int warp_h[kWarps], warp_s[kWarps];
-    unsigned long long excl_bytes;
-    int skip_write;
-};
-static_assert(sizeof(Smem) * kCtasPerSm <= 226 * 1024, "resident CTAs must fit the SM's shared memory");
-static_assert(kTile / 64 + kMaxSeg <= kMaxItems && kTile % 64 == 0, "one item per thread");
 
 __device__ __forceinline__ bool is_sep(uint32_t c) { return c == '\t' || c == '\n'; }
 
@@ -156,39 +117,6 @@ __device__ long long cut_find(const uint8_t* __restrict__ win, long long wbase, 
     return b;
 }
 
-// ---- end of the required section of the line starting at window offset ls; warp-collective ------
-// Returns the window offset of the first sample (after the 9th tab) or -1 when irregular.
-__device__ int line_scan(const uint8_t* __restrict__ win, int ls, int vhi_w, int lane) {
-    uint32_t c0 = win[ls];
-    if (is_sep(c0)) return -1;                       // empty first column / empty line
-    int tabs = 0;
-    unsigned carry = 0;
-    for (int base = ls; base < ls + kMaxReq + 32; base += 32) {
-        int g = base + lane;
-        uint32_t c = g < vhi_w ? win[g] : (uint32_t)'\n';
-        unsigned tabm = __ballot_sync(0xffffffffu, c == '\t');
-        unsigned nlm = __ballot_sync(0xffffffffu, c == '\n');
-        int cnt = __popc(tabm);
-        if (tabs + cnt >= 9) {
-            int j = __fns(tabm, 0, 9 - tabs);
-            unsigned upto = j == 31 ? 0xffffffffu : ((1u << (j + 1)) - 1u);
-            if (nlm & upto) return -1;
-            if ((tabm & ((tabm << 1) | carry)) & upto) return -1;   // empty field in the required section
-            const int s0 = base + j + 1;
-            if ((s0 - ls) > kMaxReq) return -1;
-            // a FORMAT column spelled like a genotype ("0|1") would make the first sample look like a run continuation
-            const uint32_t* wq = reinterpret_cast<const uint32_t*>(win + ((s0 - 4) & ~3));
-            const uint32_t wl = __funnelshift_r(wq[0], wq[1], 8 * ((s0 - 4) & 3));
-            return ((wl & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u ? -1 : s0;
-        }
-        if (nlm) return -1;                          // fewer than 10 columns
-        if (tabm & ((tabm << 1) | carry)) return -1;
-        tabs += cnt;
-        carry = tabm >> 31;
-    }
-    return -1;
-}
-
 // ---- sample helpers -----------------------------------------------------------------------------------
 // class of the 3-byte genotype at p: 0..3 = 0|0 0|1 1|0 1|1, 4 = anything else (compress.cpp:129,145)
 __device__ __forceinline__ int gt_class3(const uint8_t* p) {
@@ -205,92 +133,17 @@ struct Item {                  // one 64-byte block of up to 16 samples of one l
     uint32_t Ap, Bp;           // 17-bit masks: bit k = low bit of the first / second allele of sample k-1
     int kend;                  // index of the sample that ends the line, or -1
     int pcoded;                // the sample before the first valid one is a coded sample of the same line
-    int hdr;                   // 8 + required length if this item carries a line start, else 0
-    int seg;
 };
-
-// ---- classify one item ------------------------------------------------------------------------------------
-__device__ __forceinline__ void item_classify(Smem& sm, const uint8_t* __restrict__ win, int item, Item& it, int* lasthead) {
-    it.base = 0; it.V = it.C = it.L = it.Hd = it.CL = 0; it.Ap = it.Bp = 0; it.kend = -1; it.pcoded = 0; it.hdr = 0; it.seg = 0;
-    *lasthead = kNoHead;
-    if (item >= sm.n_items) return;
-    int si = 0;
-    for (int j = 1; j < sm.n_seg; j++) si += (sm.seg[j].item0 <= item);
-    const Seg sg = sm.seg[si];
-    const int a = sg.a, e = sg.e, flags = sg.flags;
-    const int blk = ((a >> 6) + (item - sg.item0)) << 6, phase = a & 3;
-    it.seg = si;
-    if (item == sg.item0 && sg.ls >= 0) it.hdr = 8 + sg.s0 - sg.ls;
-    const int base = blk + phase;
-    it.base = base;
-    // valid samples: those that start in [a, e)
-    const int rel_a = a - base, rel_e = e - base;
-    const int klo = rel_a > 0 ? rel_a >> 2 : 0, khi = rel_e >= 64 ? 16 : (rel_e > 0 ? rel_e >> 2 : 0);
-    const uint32_t V = khi > klo ? (((1u << khi) - 1u) & ~((1u << klo) - 1u)) : 0u;
-    if (!V) return;
-    const uint32_t F = ((flags & 2) && rel_a >= 0) ? (1u << klo) : 0u;
-    int kend = -1;
-    if (flags & 1) { int r = e - 4 - base; if (r >= 0 && r < 64) kend = r >> 2; }
-    // the 18 words around the block; sample k = bytes base + 4k .. base + 4k + 3
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(win + blk);
-    uint32_t W[18];
-    W[0] = wp[-1];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const uint4 v = *reinterpret_cast<const uint4*>(wp + 4 * q);
-        W[4 * q + 1] = v.x; W[4 * q + 2] = v.y; W[4 * q + 3] = v.z; W[4 * q + 4] = v.w;
-    }
-    W[17] = wp[16];
-    const int sh = 8 * phase;
-    const uint32_t sp = __funnelshift_r(W[0], W[1], sh);
-    const uint32_t pc_all = ((sp & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u ? 1u : 0u;
-    uint32_t Craw = 0, accA = sp << 31, accB = (sp >> 16) << 31;   // allele bits are shifted in from the top
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const uint32_t s = __funnelshift_r(W[k + 1], W[k + 2], sh);
-        if (((s & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u) Craw |= 1u << k;          // "x|y\t" with x, y in {0,1}
-        accA = __funnelshift_r(accA, s, 1);
-        accB = __funnelshift_r(accB, s >> 16, 1);
-    }
-    const uint32_t Ap = accA >> 15, Bp = accB >> 15;                              // bit 0: the word before the block
-    // everything valid that is not "x|y\t": literals, and the sample that carries the line's '\n'
-    uint32_t L = 0, N = V & ~Craw;
-    bool irr = false;
-    while (N) {
-        const int k = __ffs(N) - 1;
-        N &= N - 1;
-        const uint8_t* p = win + base + 4 * k;
-        const uint32_t b3 = p[3];
-        if (k == kend ? (b3 != '\n') : (b3 != '\t')) irr = true;
-        if (gt_class3(p) < 4) {            // coded sample terminated by the line's newline
-            Craw |= 1u << k;
-        } else {
-            if (p[0] == '\t' || p[1] == '\t' || p[2] == '\t') irr = true;
-            L |= 1u << k;
-        }
-    }
-    if (kend >= 0 && ((V >> kend) & 1u) && win[base + 4 * kend + 3] != '\n') irr = true;
-    if (irr) sm.irregular = 6;                               // a sample column that is not 3 bytes + separator
-    const uint32_t Cprev = (Craw << 1) | pc_all;
-    const uint32_t same = ~(((Ap >> 1) ^ Ap) | ((Bp >> 1) ^ Bp));              // same genotype bits as the previous word
-    const uint32_t Hd = V & (F | ~(Craw & Cprev & same));
-    const uint32_t PC = (Cprev & 0xFFFFu) & ~F;              // the previous word is a coded sample of this line
-    it.V = V; it.C = Craw & V; it.L = L; it.Hd = Hd; it.CL = Hd & PC;
-    it.Ap = Ap; it.Bp = Bp;
-    it.kend = (kend >= 0 && ((V >> kend) & 1u)) ? kend : -1;
-    it.pcoded = (int)((PC >> klo) & 1u);
-    if (Hd) *lasthead = base + 4 * (31 - __clz(Hd));
-}
 
 // bytes the item emits (tokens, literals, line end) -- compress.cpp:124-190 in closed form.
 // ein = address of the last run head before the item.  *h = sample index (may be negative) at which the chunk that is
 // open at the first valid sample began; *cfbit = the sample before which that chunk fills up (127 / 31 samples).
 __device__ __forceinline__ int item_count(const Item& it, int ein, uint32_t* cfbit, int* h) {
     *cfbit = 0; *h = 0;
-    if (!it.V) return it.hdr;
+    if (!it.V) return 0;
     const int k0 = __ffs(it.V) - 1;
     *h = k0;
-    int n = it.hdr + __popc(it.CL) + 5 * __popc(it.L);
+    int n = __popc(it.CL) + 5 * __popc(it.L);
     if (it.pcoded) {
         const bool m127 = (((it.Ap | it.Bp) >> k0) & 1u) == 0;   // 0|0 chunks by 127, the others by 31
         const int dist = (it.base + 4 * k0 - 4 - ein) >> 2;      // samples between the run's head and the previous sample
@@ -340,354 +193,7 @@ __device__ __forceinline__ void item_emit(const uint8_t* __restrict__ win, const
     }
 }
 
-// ---- window staging: one bulk async copy (TMA engine) per tile, completion on an mbarrier -------------------
-__device__ __forceinline__ void issue_window_load(Smem& sm, int buf, const uint8_t* __restrict__ in, long long n, int tile) {
-    const long long t0 = (long long)tile * kTile, wbase = t0 - kHalo - kPad;
-    const long long vlo = t0 - kHalo > 0 ? t0 - kHalo : 0;
-    const long long vhi = t0 + kTile + kHalo < n ? t0 + kTile + kHalo : n;
-    const unsigned bulk = (unsigned)((vhi - vlo) & ~15ll);
-    fence_proxy_async();                       // the buffer was last touched through the generic proxy
-    mbar_expect_tx(&sm.mbar[buf], bulk);
-    if (bulk)
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(sm.win[buf] + (int)(vlo - wbase))), "l"(in + vlo), "r"(bulk), "r"(smem_u32(&sm.mbar[buf])) : "memory");
-}
-
-__global__ void __launch_bounds__(kThreads, kCtasPerSm)
-k_encode_tiles(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
-               unsigned int* __restrict__ s1, unsigned long long* __restrict__ rec_pos, unsigned long long* __restrict__ rec_size,
-               unsigned long long* __restrict__ rec_lines, int n_tiles, unsigned long long log_cap) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    // ---- persistent CTA: CTA c processes tiles c, c + G, c + 2G, ... (G = gridDim.x <= resident CTAs, so the tile a
-    //      look-back waits for is always being processed); the next window loads while this one is processed --------
-    const int G = (int)gridDim.x;
-    if (tid == 0) {
-        mbar_init(&sm.mbar[0], 1);
-        mbar_init(&sm.mbar[1], 1);
-        fence_mbar_init();
-        sm.issued[0] = sm.issued[1] = 0;
-        if ((int)blockIdx.x < n_tiles) { issue_window_load(sm, 0, in, n, (int)blockIdx.x); sm.issued[0] = 1; }
-    }
-    __syncthreads();
-    int buf = 0;
-    unsigned par[2] = {0u, 0u};
-    int irr_seen = 0;                       // thread 0: ctrl->irregular as of one tile ago (the load stays off the critical path)
-
-    for (int tile = (int)blockIdx.x; tile < n_tiles; tile += G) {
-        const int tile_next = tile + G;
-        if (tid == 0) {
-            sm.irregular = irr_seen;
-            irr_seen = *((volatile int*)&ctrl->irregular);
-            sm.tile = tile;
-            sm.n_nl = 0;
-            sm.skip_write = 0;
-            sm.n_items = 0; sm.n_seg = 0; sm.n_lines = 0;
-            sm.issued[buf ^ 1] = 0;
-            if (tile_next < n_tiles && !sm.irregular) { issue_window_load(sm, buf ^ 1, in, n, tile_next); sm.issued[buf ^ 1] = 1; }
-        }
-        const uint8_t* const win = sm.win[buf];
-        uint8_t* const winw = sm.win[buf];
-        const long long t0 = (long long)tile * kTile;
-        const long long wbase = t0 - kHalo - kPad;                 // global offset of win[0] (multiple of 32)
-        const long long vlo = t0 - kHalo > 0 ? t0 - kHalo : 0;      // valid global range held in the window
-        const long long vhi = t0 + kTile + kHalo < n ? t0 + kTile + kHalo : n;
-        const int vlo_w = (int)(vlo - wbase), vhi_w = (int)(vhi - wbase);
-        const bool was_issued = sm.issued[buf] != 0;               // (written in the previous iteration / prologue)
-
-        // ---- 1. window: wait for the bulk copy, add the <16 tail bytes and the zero pads ----------------------
-        if (was_issued) { mbar_wait(&sm.mbar[buf], par[buf]); par[buf] ^= 1u; }
-        {
-            const unsigned bulk = (unsigned)((vhi - vlo) & ~15ll);
-            for (int g = vlo_w + (int)bulk + tid; g < vhi_w; g += kThreads) winw[g] = in[wbase + g];
-            if (tid < kPad) winw[vlo_w - kPad + tid] = 0;
-            if (tid >= 32 && tid < 32 + kPad + 16) { int g = vhi_w + tid - 32; if (g < kWin) winw[g] = 0; }
-        }
-        __syncthreads();
-        if (sm.irregular || !was_issued) {     // some tile already gave up: keep the look-back chains alive and move on
-            if (tid == 0) {
-                s1[tile] = (2u << 30) | ((unsigned)kNone << 8);
-                atomicCAS(&ctrl->irregular, 0, 9);
-            }
-            buf ^= 1;
-            __syncthreads();
-            continue;
-        }
-        if (tid == 0 && vhi == n && win[vhi_w - 1] != '\n') sm.irregular = 1;   // no final newline: generic path
-
-        // ---- 2. cut points (warps 0, 1) and the newline list of the nominal range + forward halo (all warps) -----
-        if (warp < 2) {
-            int kind;
-            long long c = cut_find(win, wbase, vlo, vhi, n, warp == 0 ? t0 : t0 + kTile, lane, &kind);
-            int s0c = -1;
-            if (warp == 0 && kind == kCutLine) s0c = line_scan(win, (int)(c - wbase), vhi_w, lane);
-            if (lane == 0) {
-                if (warp == 0) { sm.cs = (int)(c - wbase); sm.cs_kind = kind; sm.cs_s0 = s0c; }
-                else           { sm.ce = (int)(c - wbase); sm.ce_kind = kind; }
-                if (kind == kCutBad) sm.irregular = 2;
-            }
-            // ---- look-back #1, published as early as possible (warp 1): what the run that leaves the tile looks like.
-            //      A sample is a run head unless it and the word before it are the same coded genotype (line_scan
-            //      guarantees that a line's first sample never passes this test), so the last head is found from the
-            //      bytes alone, scanning back from the end cut.
-            if (warp == 1) {
-                unsigned word = (2u << 30) | ((unsigned)kNone << 8);            // nothing carried out
-                int uniform = 0, lcv = kNone, nsamp = 0;
-                if (kind == kCutSample) {
-                    const int ce_w = (int)(c - wbase), lo = kHalo + kPad;        // sample starts below lo belong to the previous tile
-                    const int lc = gt_class3(win + ce_w - 4);
-                    lcv = lc;
-                    word = (2u << 30) | ((unsigned)lc << 8);
-                    if (lc < 4) {
-                        int found = -1;
-                        for (int top = ce_w - 4; top >= lo && found < 0; top -= 128) {
-                            const int p = top - 4 * lane;
-                            bool head = false;
-                            if (p >= lo) {
-                                const uint32_t* wq = reinterpret_cast<const uint32_t*>(win + (p & ~3));
-                                const int shq = 8 * (p & 3);
-                                const uint32_t w1 = __funnelshift_r(wq[0], wq[1], shq), w0 = __funnelshift_r(wq[-1], wq[0], shq);
-                                head = !((((w1 & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u) && w1 == w0);
-                            }
-                            const unsigned hm = __ballot_sync(0xffffffffu, head);
-                            if (hm) found = top - 4 * (__ffs(hm) - 1);
-                        }
-                        if (found >= 0) {
-                            word |= (unsigned)mod_chunk(((ce_w - found) >> 2) - 1, lc == 0) + 1u;
-                        } else {                                                 // the entering run covers the whole tile
-                            uniform = 1;
-                            nsamp = (ce_w - lo) >> 2;
-                            word = (1u << 30) | ((unsigned)lc << 8) | (unsigned)mod_chunk(nsamp, lc == 0);   // relative
-                        }
-                    }
-                }
-                if (lane == 0) {
-                    *((volatile unsigned*)&s1[tile]) = word;
-                    sm.lb_uniform = uniform; sm.lb_lc = lcv; sm.lb_nsamp = nsamp;
-                }
-            }
-        }
-        {
-            const int lo16 = (kHalo + kPad) >> 4, hi16 = (min(vhi_w, kHalo + kPad + kTile + kMaxReq) + 15) >> 4;
-            for (int base16 = lo16; base16 < hi16; base16 += kThreads) {          // warp-uniform trip count
-                const int c16 = base16 + tid;
-                unsigned nlmask = 0;
-                if (c16 < hi16) {
-                    uint4 v = *reinterpret_cast<const uint4*>(win + (c16 << 4));
-                    // a '\n' in any of the four words leaves a zero byte in the AND of (w ^ "\n\n\n\n")
-                    uint32_t t = (v.x ^ 0x0A0A0A0Au) & (v.y ^ 0x0A0A0A0Au) & (v.z ^ 0x0A0A0A0Au) & (v.w ^ 0x0A0A0A0Au);
-                    if (((t - 0x01010101u) & ~t & 0x80808080u) != 0u)
-                        nlmask = nibble_of(zero_bytes(v.x ^ 0x0A0A0A0Au)) | (nibble_of(zero_bytes(v.y ^ 0x0A0A0A0Au)) << 4) |
-                                 (nibble_of(zero_bytes(v.z ^ 0x0A0A0A0Au)) << 8) | (nibble_of(zero_bytes(v.w ^ 0x0A0A0A0Au)) << 12);
-                }
-                // every newline: the warp that found it also finds the first sample of the line that follows
-                unsigned any;
-                while ((any = __ballot_sync(0xffffffffu, nlmask != 0)) != 0) {
-                    const int leader = __ffs(any) - 1;
-                    const int q = __shfl_sync(0xffffffffu, (c16 << 4) + __ffs(nlmask) - 1, leader);
-                    if (lane == leader) nlmask &= nlmask - 1;
-                    int s0 = -2;                                     // -2: the line starts outside the window
-                    if (q + 1 < vhi_w && q < vhi_w) s0 = line_scan(win, q + 1, vhi_w, lane);
-                    if (lane == 0 && q < vhi_w) {
-                        const int slot = atomicAdd(&sm.n_nl, 1);
-                        if (slot < kMaxNl) { sm.nlpos[slot] = q; sm.nls0[slot] = s0; }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        const int cs = sm.cs, ce = sm.ce, cs_kind = sm.cs_kind;
-
-        // ---- 3. segments (warp 0, one lane per segment): [partial first line] + one per line start in [cs, ce) ------
-        const int first_partial = (cs_kind == kCutSample || cs_kind == kCutSampleFirst) && cs < ce ? 1 : 0;
-        if (warp == 0 && !sm.irregular) {
-            int n_nl = sm.n_nl;
-            if (n_nl > kMaxNl) { if (lane == 0) sm.irregular = 3; n_nl = 0; }
-            // sort: lane j ends up holding the j-th smallest newline position (and its first-sample offset)
-            int q = lane < n_nl ? sm.nlpos[lane] : 0x3fffffff, qs0 = lane < n_nl ? sm.nls0[lane] : -2, rank = 0;
-            for (int j = 0; j < n_nl; j++) rank += (__shfl_sync(0xffffffffu, q, j) < q);
-            __syncwarp();
-            if (lane < n_nl) { sm.nlpos[rank] = q; sm.nls0[rank] = qs0; }
-            __syncwarp();
-            q = lane < n_nl ? sm.nlpos[lane] : 0x3fffffff;
-            const int idx_lo = __popc(__ballot_sync(0xffffffffu, q < cs));                 // newlines before the tile
-            const int n_in = __popc(__ballot_sync(0xffffffffu, q >= cs && q < ce));         // newlines inside it
-            const int n_start = __popc(__ballot_sync(0xffffffffu, q >= cs && q + 1 < ce)); // ... that start a line inside it
-            const int own_first = (cs_kind == kCutLine && cs < ce) ? 1 : 0;
-            const int n_lines = own_first + n_start, n_seg = first_partial + n_lines;
-            int a = 0, e = 0, ls = -1, s0 = -1, flags = 0, nitems = 0;
-            bool irr = false;
-            if (lane < n_seg) {
-                if (first_partial && lane == 0) {
-                    a = cs;
-                    e = n_in ? sm.nlpos[idx_lo] + 1 : ce;
-                    flags = (n_in ? 1 : 0) | (cs_kind == kCutSampleFirst ? 2 : 0);
-                } else {
-                    const int l = lane - first_partial, nli = l - own_first;   // nli: newline before the line (-1: the line at cs)
-                    ls = nli < 0 ? cs : sm.nlpos[idx_lo + nli] + 1;
-                    s0 = nli < 0 ? sm.cs_s0 : sm.nls0[idx_lo + nli];
-                    const int nxt = nli + 1;                                    // the newline that ends the line, if in the tile
-                    a = s0;
-                    e = nxt < n_in ? sm.nlpos[idx_lo + nxt] + 1 : ce;
-                    flags = (nxt < n_in ? 1 : 0) | 2;
-                    if (s0 < 0 || s0 > e) irr = true;
-                }
-                if (((e - a) & 3) != 0) irr = true;
-                // blocks are indexed by where a sample word STARTS; a line start with no sample here still needs an item
-                nitems = e > a ? ((e - 4) >> 6) - (a >> 6) + 1 : 1;
-            }
-            int inc = nitems;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-            const int items = __shfl_sync(0xffffffffu, inc, 31);
-            irr = __any_sync(0xffffffffu, irr) || items > kMaxItems || n_seg > kMaxSeg;
-            if (lane < n_seg && !irr) {
-                Seg& sg = sm.seg[lane];
-                sg.a = a; sg.e = e; sg.ls = ls; sg.s0 = s0; sg.flags = flags; sg.item0 = inc - nitems; sg.out0 = 0;
-            }
-            if (lane == 0) {
-                if (irr) sm.irregular = (items > kMaxItems || n_seg > kMaxSeg) ? 5 : 4;
-#ifdef VCFC_DEBUG
-                if (irr) printf("REJECT45 tile=%d n_nl=%d n_seg=%d items=%d cs=%d(k%d) ce=%d(k%d) cs_s0=%d idx_lo=%d n_in=%d n_start=%d nl0=%d s0_0=%d nl1=%d s0_1=%d nl2=%d\n",
-                                sm.tile, sm.n_nl, n_seg, items, cs, cs_kind, ce, sm.ce_kind, sm.cs_s0, idx_lo, n_in, n_start, sm.nlpos[0], sm.nls0[0],
-                                sm.nlpos[1], sm.nls0[1], sm.nlpos[2]);
-#endif
-                else { sm.n_seg = n_seg; sm.n_lines = n_lines; sm.n_items = items; }
-            }
-        }
-        __syncthreads();
-
-        // ---- 4. classify: one item (64-byte block, 16 samples) per thread ----------------------------------------------
-        unsigned lb_pref = 0;
-        if (tid == 0 && tile > 0) lb_pref = *((volatile unsigned*)&s1[tile - 1]);   // consumed after the classification
-        Item it;
-        int lh;
-        item_classify(sm, win, tid, it, &lh);
-        // last run head before each item, inside the warp: nearest lower lane that has a head
-        int ein;
-        {
-            const unsigned hm = __ballot_sync(0xffffffffu, lh != kNoHead);
-            const unsigned below = hm & ((1u << lane) - 1u);
-            const int g = __shfl_sync(0xffffffffu, lh, below ? 31 - __clz(below) : 0);
-            ein = below ? g : kNoHead;
-            const int last = __shfl_sync(0xffffffffu, lh, hm ? 31 - __clz(hm) : 0);
-            if (lane == 0) sm.warp_h[warp] = hm ? last : kNoHead;
-        }
-        // ---- 5. look-back #1 (thread 0): chunk count of the run that enters the tile -- chunks are counted from the
-        //         run's head (compress.cpp:129-170), which can lie many tiles back ---------------------------------------
-        if (tid == 0) {
-            int einv = kNoHead;
-            if (first_partial && cs_kind == kCutSample && tile > 0) {              // the first sample continues a line
-                const int pc0 = gt_class3(win + cs - 4);
-                if (pc0 < 4) {
-                    int acc = 0;
-                    unsigned v = lb_pref;
-                    for (int j = tile - 1;;) {
-                        while ((v >> 30) == 0) v = *((volatile unsigned*)&s1[j]);
-                        acc += (int)(v & 0xFFu);
-                        if ((v >> 30) == 2u || j == 0) break;
-                        j--;
-                        v = *((volatile unsigned*)&s1[j]);
-                    }
-                    const int cnt_in = mod_chunk(acc - 1 + 127 * 31, pc0 == 0) + 1;  // open chunk count before the tile, 1..M
-                    einv = cs - 4 * cnt_in;
-                    if (sm.lb_uniform) {                                          // now absolute: shortens the successors' chains
-                        const int lc = sm.lb_lc;
-                        *((volatile unsigned*)&s1[tile]) =
-                            (2u << 30) | ((unsigned)lc << 8) | ((unsigned)mod_chunk(cnt_in + sm.lb_nsamp - 1, lc == 0) + 1u);
-                    }
-                }
-            }
-            sm.ein_virtual = einv;
-        }
-        __syncthreads();
-        bool bad = sm.irregular != 0;
-
-        // ---- 6. byte counts and their exclusive scan ----------------------------------------------------------------------
-        {
-            int pre = sm.ein_virtual;                                  // heads of earlier warps (addresses grow with the item index)
-            for (int w = 0; w < warp; w++) pre = max(pre, sm.warp_h[w]);
-            ein = max(ein, pre);
-        }
-        uint32_t cf = 0;
-        int h0 = 0;
-        const int n0 = bad ? 0 : item_count(it, ein, &cf, &h0);
-        int off0, total;
-        {
-            int inc = n0;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-            if (lane == 31) sm.warp_s[warp] = inc;
-            __syncthreads();
-            int pre = 0, all = 0;
-            for (int w = 0; w < kWarps; w++) { int v = sm.warp_s[w]; all += v; if (w < warp) pre += v; }
-            off0 = pre + inc - n0;
-            total = all;
-        }
-        if (bad) total = 0;
-        const bool staged = total <= kStage;                           // else: store straight to HBM once the offset is known
-        if (bad && tid == 0 && atomicCAS(&ctrl->irregular, 0, sm.irregular ? sm.irregular : 9) == 0) ctrl->total_lines = (unsigned long long)tile;   // (diagnostics: first rejecting tile)
-
-        // ---- 7. emit into staging; reserve the tile's place in the log with one atomic (no scan chain: the final
-        //         positions come from a device scan over the tile records, k_gather_tiles moves the bytes) -----------
-        const int nl = bad ? 0 : sm.n_lines;
-        const unsigned long long need = (unsigned long long)total + 2ull * (unsigned long long)nl;       // bytes + u16 line offsets
-        unsigned long long pos = 0ull;
-        if (tid == 0 && need) pos = atomicAdd(&ctrl->log_cursor, need);   // issued before the emission, consumed after it
-        if (!bad) {
-            if (it.hdr) sm.seg[it.seg].out0 = off0;
-            if (staged) item_emit(win, it, cf, h0, sm.stage + off0 + it.hdr);
-        }
-        if (tid == 0) {
-            rec_pos[tile] = pos; rec_size[tile] = (unsigned long long)total; rec_lines[tile] = (unsigned long long)nl;
-            if (pos + need > log_cap) { sm.skip_write = 1; atomicExch(&ctrl->cap_exceeded, 1); }
-            sm.excl_bytes = pos;
-        }
-        __syncthreads();
-        if (!bad && !sm.skip_write && total > 0) {
-            uint8_t* const dst = log + sm.excl_bytes;
-            uint8_t* const image = staged ? sm.stage : dst;            // where the tile's output bytes are assembled
-            if (!staged) item_emit(win, it, cf, h0, image + off0 + it.hdr);
-            // ---- 8. line starts: two length headers + required section; the line's offset goes to the trailer -------
-            for (int l = warp; l < nl; l += kWarps) {
-                const int si = first_partial + l;
-                const int ls = sm.seg[si].ls, rq = sm.seg[si].s0 - ls, o0 = sm.seg[si].out0;
-                uint8_t* d = image + o0;
-                if (lane < 4) d[lane] = lane == 0 ? 0xC0 : 0;                       // line length: patched by k_patch_headers
-                if (lane >= 4 && lane < 8) {
-                    unsigned v = (unsigned)rq;
-                    d[lane] = lane == 4 ? (uint8_t)((v >> 24) | 0xC0) : (uint8_t)(v >> (8 * (7 - lane)));
-                }
-                for (int k = lane; k < rq; k += 32) d[8 + k] = win[ls + k];
-                if (lane < 2) dst[total + 2 * l + lane] = (uint8_t)((unsigned)o0 >> (8 * lane));
-            }
-            // ---- 9. staging -> log: aligned 4-byte stores, source words funnel-shifted ----------------------------
-            if (staged) {
-                __syncthreads();
-                const int mis = (int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);      // bytes until dst is 4-byte aligned
-                const int head = min(mis, total);
-                if (tid < head) dst[tid] = sm.stage[tid];
-                const int nwords = (total - head) >> 2;
-                const uint32_t* sw = reinterpret_cast<const uint32_t*>(sm.stage);
-                uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
-                for (int k = tid; k < nwords; k += kThreads) dw[k] = __funnelshift_r(sw[k], sw[k + 1], 8 * head);
-                const int tail0 = head + 4 * nwords;
-                if (tid < total - tail0) dst[tail0 + tid] = sm.stage[tail0 + tid];
-            }
-        }
-        buf ^= 1;
-        __syncthreads();                                               // the window and the staging area are free again
-    }
-}
-
-// =====================================================================================================================
-// Streaming encoder: ONE WARP per tile, no CTA barriers.  The warp walks its tile line by line in steps of up to 2 KB
-// (one 64-byte block = 16 samples per lane, loaded straight from global memory into registers), carrying the line /
-// run state in registers; tokens go to a per-warp staging area in shared memory and from there to the tile log.
-// Same ownership rule (cut points), look-back #1 records, tile log, records and gather pass as above.
-// =====================================================================================================================
+// ---- the streaming kernel: one warp per tile -------------------------------------------------------------------------
 #ifndef VCFC_ENC_STILE
 #define VCFC_ENC_STILE 16384
 #define VCFC_ENC_SWARPS 4
@@ -809,7 +315,9 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
             ce = (int)(cut_find(in, 0, vlo_e, vhi_e, n, t1, lane, &ke) - gb);
             if (ke == kCutBad) irregular = 2;
         }
-        // ---- look-back #1, published first: what the run that leaves the tile looks like (see prep above) ----------------
+        // ---- look-back #1, published first: what the run that leaves the tile looks like.  A sample is a run head unless
+        //      it and the word before it are the same coded genotype (line_scan16 guarantees that a line's first sample
+        //      never passes this test), so the last head is found from the bytes alone, scanning back from the end cut ----
         int lb_uniform = 0, lb_lc = kNone, lb_nsamp = 0;
         {
             unsigned word = (2u << 30) | ((unsigned)kNone << 8);
@@ -920,7 +428,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                     accB = __funnelshift_r(accB, sw >> 16, 1);
                 }
                 Item it;
-                it.base = base; it.Ap = accA >> 15; it.Bp = accB >> 15; it.hdr = 0; it.seg = 0;
+                it.base = base; it.Ap = accA >> 15; it.Bp = accB >> 15;
                 // samples that start in [a, bound)
                 const int rel_a = a - base, rel_b = bound - base;
                 const int klo = rel_a > 0 ? rel_a >> 2 : 0, khi = rel_b >= 64 ? 16 : (rel_b > 0 ? (rel_b + 3) >> 2 : 0);
@@ -1129,19 +637,12 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         ctx->launches++;
         return VCFC_OK;
     }
-#ifndef VCFC_ENC_CTA_TILES
-    constexpr bool kStream = true;
-#else
-    constexpr bool kStream = false;
-#endif
     static bool attr_set = false;
     if (!attr_set) {
-        VCFC_CUDA(ctx, cudaFuncSetAttribute(k_encode_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         VCFC_CUDA(ctx, cudaFuncSetAttribute(k_encode_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
         attr_set = true;
     }
-    const size_t tile_bytes = kStream ? kSTile : kTile;
-    const size_t n_tiles = (in_len + tile_bytes - 1) / tile_bytes;
+    const size_t n_tiles = (in_len + kSTile - 1) / kSTile;
     const size_t lines_cap = in_len / 64 + 1024;
     DevBuf &ws = ctx->ws[10], &b_log = ctx->ws[11], &b_scr = ctx->ws[1];
     const size_t off_s1 = 256, off_rec = off_s1 + ((n_tiles * 4 + 255) & ~size_t(255));
@@ -1163,11 +664,10 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
     static int resident = 0;        // CTAs that are guaranteed to be co-resident (look-back #1 spins on its neighbour)
     if (!resident) {
         int per_sm = 0;
-        if (kStream) VCFC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_stream, 32 * kSWarps, sizeof(SmemS)));
-        else VCFC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_tiles, kThreads, sizeof(Smem)));
+        VCFC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_stream, 32 * kSWarps, sizeof(SmemS)));
         resident = std::max(1, per_sm) * ctx->sm_count;
     }
-    const unsigned grid = (unsigned)std::min<size_t>(kStream ? (n_tiles + kSWarps - 1) / kSWarps : n_tiles, (size_t)resident);
+    const unsigned grid = (unsigned)std::min<size_t>((n_tiles + kSWarps - 1) / kSWarps, (size_t)resident);
     if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeEncode], stream);
     {   // cooperative launch: every CTA is resident, which look-back #1 (a CTA spins on its neighbour's tile) relies on
         const uint8_t* a_in = d_in;
@@ -1177,10 +677,7 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         int a_tiles = (int)n_tiles;
         unsigned long long a_cap = (unsigned long long)log_cap;
         void* args[] = {&a_in, &a_n, &a_log, &ctrl, &a_s1, &rec_pos, &rec_size, &rec_lines, &a_tiles, &a_cap};
-        if (kStream)
-            VCFC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_encode_stream, dim3(grid), dim3(32 * kSWarps), args, sizeof(SmemS), stream));
-        else
-            VCFC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_encode_tiles, dim3(grid), dim3(kThreads), args, sizeof(Smem), stream));
+        VCFC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_encode_stream, dim3(grid), dim3(32 * kSWarps), args, sizeof(SmemS), stream));
     }
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeEncode + 1], stream); ctx->ev_pending[kTimeEncode] = 1; }
     ctx->launches += 1;
