@@ -5,7 +5,7 @@
 
 * launches: `ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ ...` over bench.py
   -> per-kernel launch count, total time and SHARE of the step (cold-cache, serialised: shares, not absolutes)
-* full: `ncu --set full ... -k regex:"k_encode_tiles|k_dec_expand"` -> DRAM bytes, throughput %, stall picture
+* full: `ncu --set full ... -k regex:"k_encode_stream|k_dec_expand_grid"` -> DRAM bytes, throughput %, stall picture
 """
 import collections
 import csv
