@@ -28,7 +28,6 @@ namespace dec {
 constexpr int kSeg = 2048;              // D1 segment (compressed bytes): one thread each, so keep the serial walk short
 constexpr int kTile = 16384;            // D4 output tile
 constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 constexpr int kCmax = 24576;            // longest compressed line the tile kernel parses from smem
 constexpr long long kNoCand = -1, kBroken = -2;
 
@@ -195,19 +194,6 @@ __global__ void k_dec_fill(const uint8_t* __restrict__ in, long long n, long lon
 // ---- token stream parsing -----------------------------------------------------------------------------
 // kinds of setter: 1 = a byte >= 0xE0 (enters a literal payload when read as a token, stays in it when read as payload),
 // 2 = tab / newline (ends a payload; as a token it is a 0|0 run of 9 / 10 and the state stays "token")
-__device__ __forceinline__ int last_setter_kind(const uint8_t* b, int nb) {
-    int kind = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        uint32_t c = b[i];
-        if (i < nb) {
-            if (c >= 0xE0u) kind = 1;
-            else if (c == 9u || c == 10u) kind = 2;
-        }
-    }
-    return kind;
-}
-
 // Walks nb token-region bytes starting in `payload` state; accumulates text bytes and samples.
 // is_last: the chunk ends with the line's final '\n'.  err bits: 1 = malformed for this path.
 // *tres: bit r set = a literal ended (its terminator included) at chunk-relative text offset == r (mod 4).
@@ -280,7 +266,7 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
             int nb = (int)(tn - off);
             nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
             uint8_t b[16];
-            uint32_t lit_any = 0, set_any = 0, run_sum = 0, run_zero = 0;
+            uint32_t lit_any = 0, set_any = 0, set_lit = 0, run_sum = 0, run_zero = 0;
             if (nb > 0) {       // five aligned 32-bit loads instead of sixteen byte loads; bytes past the line are never used
                 const uintptr_t ga = reinterpret_cast<uintptr_t>(p + tb + off);
                 const uint32_t* wp = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
@@ -302,15 +288,17 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
                     const uint32_t bm = nj >= 4 ? 0xFFFFFFFFu : (nj <= 0 ? 0u : ((1u << (8 * nj)) - 1u));
                     const uint32_t bmv = njv >= 4 ? 0xFFFFFFFFu : (njv <= 0 ? 0u : ((1u << (8 * njv)) - 1u));
                     const uint32_t w = v[j];
-                    lit_any |= w & (w << 1) & (w << 2) & 0x80808080u & bm;
-                    set_any |= (zero_bytes(w ^ 0x09090909u) | zero_bytes(w ^ 0x0A0A0A0Au)) & bm;
+                    const uint32_t lm = w & (w << 1) & (w << 2) & 0x80808080u & bm;                       // bytes >= 0xE0
+                    const uint32_t am = lm | ((zero_bytes(w ^ 0x09090909u) | zero_bytes(w ^ 0x0A0A0A0Au)) & bm);   // ... or tab / newline
+                    lit_any |= lm;
+                    if (am) { set_any = am; set_lit = lm; }                                             // the highest word that has a setter
                     const uint32_t cv = w & (0x7F7F7F7Fu ^ (((w >> 7) & 0x01010101u) * 0x60u)) & bmv;     // run lengths
                     run_sum = __dp4a(cv, 0x01010101u, run_sum);
                     run_zero |= zero_bytes(cv | ~bmv);
                 }
             }
-            set_any |= lit_any;
-            const int kind = (nb > 0 && set_any) ? last_setter_kind(b, nb) : 0;
+            // kind of the chunk's last setter: 1 = a byte >= 0xE0, 2 = tab / newline (kinds of setter above)
+            const int kind = set_any ? (((set_lit >> (31 - __clz(set_any))) & 1u) ? 1 : 2) : 0;
             // state at chunk start: last setter of the nearest lower lane that has one, else the carry
             const unsigned has = __ballot_sync(0xffffffffu, kind != 0);
             const unsigned below = has & ((1u << lane) - 1u);
@@ -357,7 +345,7 @@ constexpr unsigned kWholeLine = 0xFFFFFFFFu;
 __global__ void k_dec_tilemap(const unsigned long long* __restrict__ off, unsigned long long n_lines, unsigned long long total,
                               const unsigned long long* __restrict__ line_start, const unsigned* __restrict__ rq_arr,
                               const unsigned* __restrict__ gtab, unsigned int* __restrict__ first_line,
-                              unsigned int* __restrict__ first_chunk) {
+                              unsigned int* __restrict__ first_chunk, const unsigned long long tile) {
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_lines) return;
     const unsigned long long a = off[k], b = k + 1 < n_lines ? off[k + 1] : total;
@@ -366,9 +354,9 @@ __global__ void k_dec_tilemap(const unsigned long long* __restrict__ off, unsign
     const long long rq = rq_arr[k];
     const int nch = (int)(((long long)(line_start[k + 1] - ls) - 8 - rq + 15) >> 4);
     const unsigned* tab = gtab + (ls >> 4) + k;
-    for (unsigned long long t = (a + kTile - 1) / kTile; t * kTile < b; t++) {
+    for (unsigned long long t = (a + tile - 1) / tile; t * tile < b; t++) {
         first_line[t] = (unsigned int)k;
-        const long long xs = (long long)(t * kTile - a) - rq;          // text offset of the tile start inside the sample text
+        const long long xs = (long long)(t * tile - a) - rq;          // text offset of the tile start inside the sample text
         unsigned fc = kWholeLine;
         if (xs >= 0) {
             int lo = 0, hi = nch;
@@ -636,17 +624,19 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
 // text offset and writes only what differs -- a '1' for the allele bytes of 0|1 / 1|0 / 1|1 runs, literal payloads --
 // plus the required sections and the line ends.  Work is proportional to the COMPRESSED size of the tile.
 #ifndef VCFC_DEC_GTHREADS
-#define VCFC_DEC_GTHREADS 128
-#define VCFC_DEC_GCTAS 8
-#define VCFC_DEC_GCMAX 6144
+#define VCFC_DEC_GTHREADS 256
+#define VCFC_DEC_GCTAS 5
+#define VCFC_DEC_GCMAX 8192
+#define VCFC_DEC_GTILE 32768
 #endif
+constexpr int kTileG = VCFC_DEC_GTILE;         // output tile of the fill-and-patch kernel
 constexpr int kGThreads = VCFC_DEC_GTHREADS, kGWarps = kGThreads / 32;
 constexpr int kCmaxG = VCFC_DEC_GCMAX;      // compressed bytes staged per batch; a line that does not fit is continued in the next batch
 constexpr int kChunksG = kCmaxG / 16 + 2 * 32;
 static_assert(kCmaxG >= 2048 && kCmaxG % 16 == 0, "a batch must at least hold a line start (8 + 960 bytes) and some chunks");
 
 struct SmemG {
-    alignas(16) uint8_t stage[kTile];
+    alignas(16) uint8_t stage[kTileG];
     alignas(16) uint8_t cbuf[kCmaxG + 32];
     unsigned ctab[kChunksG];
     int l_pos[kMaxL + 1], l_end[kMaxL + 1], l_last[kMaxL + 1], l_coff[kMaxL + 2];
@@ -668,8 +658,8 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
     SmemG& sm = *reinterpret_cast<SmemG*>(smem_raw);
     if (ctrl->irregular) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned long long T0 = (unsigned long long)blockIdx.x * kTile;
-    const int tile_len = (int)(total - T0 < (unsigned long long)kTile ? total - T0 : (unsigned long long)kTile);
+    const unsigned long long T0 = (unsigned long long)blockIdx.x * kTileG;
+    const int tile_len = (int)(total - T0 < (unsigned long long)kTileG ? total - T0 : (unsigned long long)kTileG);
     const unsigned long long T1 = T0 + (unsigned long long)tile_len;
     unsigned long long k0 = first_line[blockIdx.x];
     unsigned fc_tile = first_chunk[blockIdx.x];         // chunk the batch's first line is staged from (kWholeLine: from its header)
@@ -948,14 +938,16 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
         ctx->launches++;
         return VCFC_OK;
     }
-    const unsigned long long n_tiles = (total + kTile - 1) / kTile;
+    const bool walk = h.not_grid || ctx->force_generic == 2;       // the span-walking kernel takes what is off the 4-byte grid
+    const unsigned long long tile = walk ? kTile : kTileG;
+    const unsigned long long n_tiles = (total + tile - 1) / tile;
     if ((rc = dev_reserve(ctx, &b_tiles, n_tiles * 8 + 64))) return rc;
     unsigned int* first_chunk = (unsigned int*)b_tiles.p + n_tiles;
     k_dec_tilemap<<<(unsigned)((n_lines + 255) / 256), 256, 0, stream>>>((unsigned long long*)b_offs.p, n_lines, total, line_start,
                                                                           (const unsigned*)b_rq.p, (const unsigned*)b_tab.p,
-                                                                          (unsigned int*)b_tiles.p, first_chunk);
+                                                                          (unsigned int*)b_tiles.p, first_chunk, tile);
     if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeDecodeExpand], stream);
-    if (h.not_grid || ctx->force_generic == 2)
+    if (walk)
         k_dec_expand<<<(unsigned)n_tiles, kXThreads, sizeof(Smem), stream>>>(d_in, line_start, (unsigned long long*)b_offs.p, n_lines,
                                                                             total, (unsigned int*)b_tiles.p, first_chunk, (const unsigned*)b_rq.p, (const unsigned*)b_tab.p, d_out, ctrl);
     else
