@@ -27,7 +27,6 @@ namespace dec {
 
 constexpr int kSeg = 2048;              // D1 segment (compressed bytes): one thread each, so keep the serial walk short
 constexpr int kTile = 16384;            // D4 output tile
-constexpr int kThreads = 256;
 constexpr int kCmax = 24576;            // longest compressed line the tile kernel parses from smem
 constexpr long long kNoCand = -1, kBroken = -2;
 
@@ -194,6 +193,7 @@ __global__ void k_dec_fill(const uint8_t* __restrict__ in, long long n, long lon
 // ---- token stream parsing -----------------------------------------------------------------------------
 // kinds of setter: 1 = a byte >= 0xE0 (enters a literal payload when read as a token, stays in it when read as payload),
 // 2 = tab / newline (ends a payload; as a token it is a 0|0 run of 9 / 10 and the state stays "token")
+
 // Walks nb token-region bytes starting in `payload` state; accumulates text bytes and samples.
 // is_last: the chunk ends with the line's final '\n'.  err bits: 1 = malformed for this path.
 // *tres: bit r set = a literal ended (its terminator included) at chunk-relative text offset == r (mod 4).
