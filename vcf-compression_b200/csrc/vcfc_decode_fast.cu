@@ -6,17 +6,18 @@
 //
 // Output bytes are those of decompress2_data_line (/root/reference/src/compress.cpp:741-986).
 // Pipeline (all on the launch stream; two small host reads size the workspace):
-//   D1 k_dec_walk     line table without a serial pointer chase: every 16 KB segment finds its first
-//                     plausible line start and follows the 4-byte length headers (utils.hpp:134-247)
-//                     to the segment end; k_dec_verify accepts the table only if every segment's
-//                     chain ends exactly where the next one began (induction from offset 0).
-//   D2 k_dec_sizes    one warp per line: validates the line and sizes its text.  The token/payload
-//                     state of a byte is the kind of the last "setter" before it (a byte >= 0xE0
+//   D1 k_dec_walk     line table without a serial pointer chase: one warp per 2 KB segment finds the
+//                     segment's first plausible line start and follows the 4-byte length headers
+//                     (utils.hpp:134-247) to the segment end; k_dec_verify accepts the table only if every
+//                     segment's chain ends exactly where the next one began (induction from offset 0).
+//   D2 k_dec_sizes    one warp per line: validates the line, sizes its text and writes the chunk table.  The
+//                     token/payload state of a byte is the kind of the last "setter" before it (a byte >= 0xE0
 //                     enters a payload, a tab/newline leaves it), so 16-byte chunks parse in parallel.
-//   D3 scan           line text offsets; k_dec_tilemap: first line of every 16 KB output tile
-//   D4 k_dec_expand   one CTA per OUTPUT tile: parses the lines that overlap it from smem, expands
-//                     runs into an smem image of the tile (long runs warp-cooperatively) and stores
-//                     the tile with aligned 16-byte stores.  HBM traffic = 2 C + N.
+//   D3 scan           line text offsets; k_dec_tilemap: first line (and chunk) of every output tile
+//   D4 k_dec_expand_grid  one CTA per 32 KB OUTPUT tile, sample text on the 4-byte grid (the normal case): the
+//                     tile image is filled with the default genotype in each line's phase, then one thread per
+//                     16 token bytes patches in what differs; aligned 16-byte stores.  HBM traffic = 2 C + N.
+//      k_dec_expand   the same for text off the grid: every thread walks the tokens of one 64-byte span.
 #include <algorithm>
 
 #include "vcfc_common.cuh"
