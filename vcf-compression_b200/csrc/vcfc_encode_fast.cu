@@ -291,14 +291,68 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
     uint8_t* const stage = sm.stage[warp];
     const int gw = (int)blockIdx.x * kSWarps + warp, nw = (int)gridDim.x * kSWarps;
     int irr_seen = 0;                       // ctrl->irregular as of one tile ago (the load stays off the critical path)
+    // The warp runs one tile AHEAD with the end cut and the look-back #1 record: iteration k publishes the record of
+    // this warp's tile k+1 and then encodes tile k, so a record is there a whole tile time before its reader needs it.
+    constexpr int kFlSkip = 1 << 9;
+    int cur_ce = 0, cur_fl = 0;             // the tile to encode: end cut (relative to its own base), cut kind | class << 4 | uniform << 8
 
-    for (int tile = gw; tile < n_tiles; tile += nw) {
-        const int irr_now = irr_seen;
-        irr_seen = *((volatile int*)&ctrl->irregular);
-        if (irr_now) {                      // some tile already gave up: keep the look-back chains alive and move on
-            if (lane == 0) s1[tile] = (2u << 30) | ((unsigned)kNone << 8);
-            continue;
+    for (int tile = gw - nw; tile < n_tiles; tile += nw) {
+        // ---- ahead: end cut of the next tile and its look-back #1 record -- what the run that leaves the tile looks
+        //      like.  A sample is a run head unless it and the word before it are the same coded genotype (line_scan16
+        //      guarantees that a line's first sample never passes this test), so the last head is found from the bytes
+        //      alone, scanning back from the end cut --------------------------------------------------------------------
+        int n_ce = 0, n_fl = 0;
+        if (tile + nw < n_tiles) {
+            const int nt = tile + nw;
+            const int irr_now = irr_seen;
+            irr_seen = *((volatile int*)&ctrl->irregular);
+            unsigned word = (2u << 30) | ((unsigned)kNone << 8);            // nothing carried out
+            if (irr_now) {                  // some tile already gave up: keep the look-back chains alive and move on
+                n_fl = kFlSkip;
+            } else {
+                const long long t0 = (long long)nt * kSTile, gb = t0 - 64, t1 = t0 + kSTile;
+                const uint8_t* const win = in + gb;
+                const int r_lo = gb < 0 ? 64 : 0;
+                const int r_hi = (int)(n - gb < (long long)(1 << 24) ? n - gb : (long long)(1 << 24));
+                const long long vlo_e = t1 - kHalo > 0 ? t1 - kHalo : 0, vhi_e = t1 + kHalo < n ? t1 + kHalo : n;
+                int ke;
+                const int ce = (int)(cut_find(in, 0, vlo_e, vhi_e, n, t1, lane, &ke) - gb);
+                int lc = kNone, uniform = 0;
+                if (ke == kCutSample) {
+                    const int lo = 64 > r_lo + 4 ? 64 : r_lo + 4;             // sample starts below t0 belong to the previous tile
+                    lc = gt_class3(win + ce - 4);
+                    word = (2u << 30) | ((unsigned)lc << 8);
+                    if (lc < 4) {
+                        int found = -1;
+                        for (int top = ce - 4; top >= lo && found < 0; top -= 128) {
+                            const int p = top - 4 * lane;
+                            bool head = false;
+                            if (p >= lo) {
+                                const int pa = p & ~3, shq = 8 * (p & 3);
+                                const uint32_t wa = ldw(win, pa - 4, r_lo, r_hi), wb = ldw(win, pa, r_lo, r_hi), wc = ldw(win, pa + 4, r_lo, r_hi);
+                                const uint32_t w1 = __funnelshift_r(wb, wc, shq), w0 = __funnelshift_r(wa, wb, shq);
+                                head = !((((w1 & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u) && w1 == w0);
+                            }
+                            const unsigned hm = __ballot_sync(0xffffffffu, head);
+                            if (hm) found = top - 4 * (__ffs(hm) - 1);
+                        }
+                        if (found >= 0) {
+                            word |= (unsigned)mod_chunk(((ce - found) >> 2) - 1, lc == 0) + 1u;
+                        } else {                                                 // the entering run covers the whole tile
+                            uniform = 1;
+                            word = (1u << 30) | ((unsigned)lc << 8) | (unsigned)mod_chunk((ce - 64) >> 2, lc == 0);   // relative
+                        }
+                    }
+                }
+                n_ce = ce;
+                n_fl = ke | (lc << 4) | (uniform << 8);
+            }
+            if (lane == 0) *((volatile unsigned*)&s1[nt]) = word;
         }
+        const int ce = cur_ce, fl = cur_fl;
+        cur_ce = n_ce; cur_fl = n_fl;
+        if (tile < 0 || (fl & kFlSkip)) continue;
+        // ---- the tile itself ---------------------------------------------------------------------------------------------
         const long long t0 = (long long)tile * kSTile;
         const long long gb = t0 - 64;                                   // tile-relative offsets: r = g - gb (a multiple of 64 apart)
         const uint8_t* const win = in + gb;
@@ -306,51 +360,9 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
         const int r_hi = (int)(n - gb < (long long)(1 << 24) ? n - gb : (long long)(1 << 24));
         int irregular = 0;
         if (t0 + kSTile >= n && in[n - 1] != '\n') irregular = 1;        // no final newline: generic path
-        // ---- cut points ------------------------------------------------------------------------------------------------
-        int ks, ke;
-        int cs, ce;
-        {   // the end cut first: the look-back record the next tile waits for depends on it alone
-            const long long t1 = t0 + kSTile;
-            const long long vlo_e = t1 - kHalo > 0 ? t1 - kHalo : 0, vhi_e = t1 + kHalo < n ? t1 + kHalo : n;
-            ce = (int)(cut_find(in, 0, vlo_e, vhi_e, n, t1, lane, &ke) - gb);
-            if (ke == kCutBad) irregular = 2;
-        }
-        // ---- look-back #1, published first: what the run that leaves the tile looks like.  A sample is a run head unless
-        //      it and the word before it are the same coded genotype (line_scan16 guarantees that a line's first sample
-        //      never passes this test), so the last head is found from the bytes alone, scanning back from the end cut ----
-        int lb_uniform = 0, lb_lc = kNone, lb_nsamp = 0;
-        {
-            unsigned word = (2u << 30) | ((unsigned)kNone << 8);
-            if (ke == kCutSample && !irregular) {
-                const int lo = 64 > r_lo + 4 ? 64 : r_lo + 4;             // sample starts below t0 belong to the previous tile
-                const int lc = gt_class3(win + ce - 4);
-                lb_lc = lc;
-                word = (2u << 30) | ((unsigned)lc << 8);
-                if (lc < 4) {
-                    int found = -1;
-                    for (int top = ce - 4; top >= lo && found < 0; top -= 128) {
-                        const int p = top - 4 * lane;
-                        bool head = false;
-                        if (p >= lo) {
-                            const int pa = p & ~3, shq = 8 * (p & 3);
-                            const uint32_t wa = ldw(win, pa - 4, r_lo, r_hi), wb = ldw(win, pa, r_lo, r_hi), wc = ldw(win, pa + 4, r_lo, r_hi);
-                            const uint32_t w1 = __funnelshift_r(wb, wc, shq), w0 = __funnelshift_r(wa, wb, shq);
-                            head = !((((w1 & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u) && w1 == w0);
-                        }
-                        const unsigned hm = __ballot_sync(0xffffffffu, head);
-                        if (hm) found = top - 4 * (__ffs(hm) - 1);
-                    }
-                    if (found >= 0) {
-                        word |= (unsigned)mod_chunk(((ce - found) >> 2) - 1, lc == 0) + 1u;
-                    } else {
-                        lb_uniform = 1;
-                        lb_nsamp = (ce - 64) >> 2;
-                        word = (1u << 30) | ((unsigned)lc << 8) | (unsigned)mod_chunk(lb_nsamp, lc == 0);   // relative
-                    }
-                }
-            }
-            if (lane == 0) *((volatile unsigned*)&s1[tile]) = word;
-        }
+        const int ke = fl & 15, lb_lc = (fl >> 4) & 15, lb_uniform = (fl >> 8) & 1, lb_nsamp = (ce - 64) >> 2;
+        if (ke == kCutBad) irregular = 2;
+        int ks, cs;
         {
             const long long vlo_s = t0 - kHalo > 0 ? t0 - kHalo : 0, vhi_s = t0 + kHalo < n ? t0 + kHalo : n;
             cs = (int)(cut_find(in, 0, vlo_s, vhi_s, n, t0, lane, &ks) - gb);
