@@ -160,11 +160,21 @@ __device__ __forceinline__ int item_count(const Item& it, int ein, uint32_t* cfb
 
 __device__ __forceinline__ void item_emit(const uint8_t* __restrict__ win, const Item& it, uint32_t cfbit, int h,
                                           uint8_t* __restrict__ dst) {
-    if (!it.V) return;
-    const uint32_t tok = it.CL | cfbit;
+    const uint32_t tok = it.V ? (it.CL | cfbit) : 0u;
     const uint32_t kendbit = it.kend >= 0 ? (1u << it.kend) : 0u;
-    uint32_t ev = tok | it.L | kendbit;
     int o = 0;
+    // run tokens only (the common case): a tight loop -- unless many lanes of the warp have literals, then one loop for all
+    const bool many = __popc(__ballot_sync(0xffffffffu, (it.L | kendbit) != 0u)) > 4;
+    if (!(it.L | kendbit) && !many) {
+        for (uint32_t t = tok; t; t &= t - 1) {
+            const int k = __ffs(t) - 1;
+            const uint32_t c = (((it.Ap >> k) & 1u) << 1) | ((it.Bp >> k) & 1u);
+            dst[o++] = (uint8_t)(cls_flag((int)c) | (uint32_t)(k - h));
+            h = k;
+        }
+        return;
+    }
+    uint32_t ev = tok | it.L | kendbit;
     while (ev) {
         const int k = __ffs(ev) - 1;
         ev &= ev - 1;
