@@ -455,34 +455,38 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 const int rel_a = a - base, rel_b = bound - base;
                 const int klo = rel_a > 0 ? rel_a >> 2 : 0, khi = rel_b >= 64 ? 16 : (rel_b > 0 ? (rel_b + 3) >> 2 : 0);
                 uint32_t V = khi > klo ? (((1u << khi) - 1u) & ~((1u << klo) - 1u)) : 0u;
-                // the line's last sample carries the '\n': the first such sample ends the step
-                int kend = -1;
-                for (uint32_t t = V & ~Craw; t; t &= t - 1) {
-                    const int k = __ffs(t) - 1;
-                    if (ldb(win, base + 4 * k + 3, r_lo, r_hi) == '\n') { kend = k; break; }
-                }
-                const unsigned endm = __ballot_sync(0xffffffffu, kend >= 0);
-                const int le = endm ? __ffs(endm) - 1 : 32;
-                if (lane > le) V = 0;
-                if (lane == le) V &= (2u << kend) - 1u;
-                const int q_end = __shfl_sync(0xffffffffu, base + 4 * kend + 3, le & 31);   // the '\n' (valid when endm)
-                // everything valid that is not "x|y\t": literals, and the sample that ends the line
+                // everything valid that is not "x|y\t": literals, and the line's last sample, which carries the '\n' (the first
+                // such sample ends the step).  Most steps of a sparse file have neither: one ballot skips all of it.
+                int kend = -1, q_end = 0;
+                unsigned endm = 0;
+                int le = 32;
                 uint32_t L = 0;
-                bool irr = false;
-                for (uint32_t t = V & ~Craw; t; t &= t - 1) {
-                    const int k = __ffs(t) - 1;
-                    const uint8_t* p = win + base + 4 * k;
-                    const bool inside = base + 4 * k >= r_lo && base + 4 * k + 4 <= r_hi;
-                    const uint32_t b0 = inside ? p[0] : 0u, b1 = inside ? p[1] : 0u, b2 = inside ? p[2] : 0u, b3 = inside ? p[3] : 0u;
-                    if (k == kend ? (b3 != '\n') : (b3 != '\t')) irr = true;
-                    if (b1 == '|' && (b0 & 0xFEu) == 0x30u && (b2 & 0xFEu) == 0x30u) {
-                        Craw |= 1u << k;           // coded sample terminated by the line's newline
-                    } else {
-                        if (is_sep(b0) || is_sep(b1) || is_sep(b2)) irr = true;
-                        L |= 1u << k;
+                if (__any_sync(0xffffffffu, (V & ~Craw) != 0u)) {
+                    for (uint32_t t = V & ~Craw; t; t &= t - 1) {
+                        const int k = __ffs(t) - 1;
+                        if (ldb(win, base + 4 * k + 3, r_lo, r_hi) == '\n') { kend = k; break; }
                     }
+                    endm = __ballot_sync(0xffffffffu, kend >= 0);
+                    le = endm ? __ffs(endm) - 1 : 32;
+                    if (lane > le) V = 0;
+                    if (lane == le) V &= (2u << kend) - 1u;
+                    q_end = __shfl_sync(0xffffffffu, base + 4 * kend + 3, le & 31);   // the '\n' (valid when endm)
+                    bool irr = false;
+                    for (uint32_t t = V & ~Craw; t; t &= t - 1) {
+                        const int k = __ffs(t) - 1;
+                        const uint8_t* p = win + base + 4 * k;
+                        const bool inside = base + 4 * k >= r_lo && base + 4 * k + 4 <= r_hi;
+                        const uint32_t b0 = inside ? p[0] : 0u, b1 = inside ? p[1] : 0u, b2 = inside ? p[2] : 0u, b3 = inside ? p[3] : 0u;
+                        if (k == kend ? (b3 != '\n') : (b3 != '\t')) irr = true;
+                        if (b1 == '|' && (b0 & 0xFEu) == 0x30u && (b2 & 0xFEu) == 0x30u) {
+                            Craw |= 1u << k;           // coded sample terminated by the line's newline
+                        } else {
+                            if (is_sep(b0) || is_sep(b1) || is_sep(b2)) irr = true;
+                            L |= 1u << k;
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, irr)) { irregular = 6; break; }    // a sample column that is not 3 bytes + separator
                 }
-                if (__any_sync(0xffffffffu, irr)) { irregular = 6; break; }    // a sample column that is not 3 bytes + separator
                 const uint32_t F = (first && lane == 0) ? (1u << klo) : 0u;
                 const uint32_t Cprev = (Craw << 1) | pc_all;
                 const uint32_t same = ~(((it.Ap >> 1) ^ it.Ap) | ((it.Bp >> 1) ^ it.Bp));   // same genotype bits as the previous word
