@@ -754,10 +754,10 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
         {
             const int f_first = contd ? (nb > 1 ? sm.l_pos[1] : sm.l_end[0]) : sm.l_pos[0];   // a continued line is already filled
             const int f_lo = f_first <= 0 ? 0 : (f_first + 15) >> 4, f_hi = (sm.l_end[nb - 1] + 15) >> 4;
+            int li = 0;
             for (int u = f_lo + tid; u < f_hi; u += kGThreads) {
                 const int pos = u << 4;
-                int li = 0;
-                for (int j = 1; j < nb; j++) li += (sm.l_pos[j] <= pos);
+                while (li + 1 < nb && sm.l_pos[li + 1] <= pos) li++;          // (a thread's units ascend)
                 const int ph = (pos - sm.l_pos[li] - sm.l_rq[li]) & 3;
                 const uint32_t P = __funnelshift_r(0x09307C30u, 0x09307C30u, 8 * ph);
                 *reinterpret_cast<uint4*>(sm.stage + pos) = make_uint4(P, P, P, P);
@@ -777,11 +777,14 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
         }
         // ... and the token chunks: only what is not the default genotype is written
         {
-            const int n_chunks = sm.l_c0[nb];
-            for (int idx = tid; idx < n_chunks; idx += kGThreads) {
-                int li = 0;
-                for (int j = 1; j < nb; j++) li += (sm.l_c0[j] <= idx);
-                const int c = idx - sm.l_c0[li];
+            // two threads per chunk: the second one starts at byte 8, with the text offset (and literal state) the first 8
+            // bytes lead to -- word-parallel when they are run tokens only (nearly always)
+            const int n_items = 2 * sm.l_c0[nb];
+            int li = 0;
+            for (int idx = tid; idx < n_items; idx += kGThreads) {
+                const int ch = idx >> 1, half = idx & 1;
+                while (li + 1 < nb && sm.l_c0[li + 1] <= ch) li++;
+                const int c = ch - sm.l_c0[li];
                 const int coff = sm.l_coff[li];
                 const bool cont = li == 0 && c_first >= 0;
                 const int rq = sm.l_rq[li];
@@ -799,28 +802,55 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
                 const uint32_t* wp = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
                 const int sh = 8 * (int)(ga & 3);
                 const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-                const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
-                                       __funnelshift_r(w3, w4, sh)};
+                const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh),
+                               v3 = __funnelshift_r(w3, w4, sh);
                 bool payload = (t0 & 1u) != 0;
+                const uint32_t lit_lo = ((v0 & (v0 << 1) & (v0 << 2)) | (v1 & (v1 << 1) & (v1 << 2))) & 0x80808080u;   // a byte >= 0xE0
+                int b_lo = 0, b_hi = nby;
+                if (nby <= 8) {
+                    if (half) continue;                                // a short last chunk: one thread
+                } else if (half) {
+                    if (!payload && !lit_lo) {                         // run tokens only: their lengths add up word-parallel
+                        const uint32_t c0 = v0 & (0x7F7F7F7Fu ^ (((v0 >> 7) & 0x01010101u) * 0x60u));
+                        const uint32_t c1 = v1 & (0x7F7F7F7Fu ^ (((v1 >> 7) & 0x01010101u) * 0x60u));
+                        pos += 4 * (int)__dp4a(c1, 0x01010101u, __dp4a(c0, 0x01010101u, 0u));
+                    } else {                                           // literals: follow the state through the first 8 bytes
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const uint32_t b = (v[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-                    if (i < nby) {
-                        if (payload) {
-                            if ((unsigned)pos < (unsigned)tile_len) sm.stage[pos] = (uint8_t)b;
-                            pos++;
-                            if (b == 9u || b == 10u) payload = false;
-                        } else if (b >= 0xE0u) {
-                            payload = true;
-                        } else if (b < 0x80u) {
-                            pos += 4 * (int)b;                        // 0|0: already there
-                        } else {
-                            const uint32_t f = b & 0xE0u;
-                            const bool a1 = f != kTok01, b1 = f != kTok10;
-                            const int cnt = (int)(b & 0x1Fu);
-                            for (int q = 0; q < cnt; q++, pos += 4) {
-                                if (a1 && (unsigned)pos < (unsigned)tile_len) sm.stage[pos] = '1';
-                                if (b1 && (unsigned)(pos + 2) < (unsigned)tile_len) sm.stage[pos + 2] = '1';
+                        for (int i = 0; i < 8; i++) {
+                            const uint32_t b = ((i < 4 ? v0 : v1) >> (8 * (i & 3))) & 0xFFu;
+                            if (payload) { pos++; if (b == 9u || b == 10u) payload = false; }
+                            else if (b >= 0xE0u) payload = true;
+                            else pos += 4 * (int)(b < 0x80u ? b : (b & 0x1Fu));
+                        }
+                    }
+                    if (pos >= tile_len) continue;
+                    b_lo = 8;
+                } else {
+                    b_hi = 8;
+                }
+                for (int b0 = b_lo; b0 < b_hi; b0 += 8) {
+                    const uint32_t wa = b0 ? v2 : v0, wbb = b0 ? v3 : v1;
+                    const int nb8 = b_hi - b0;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t b = ((i < 4 ? wa : wbb) >> (8 * (i & 3))) & 0xFFu;
+                        if (i < nb8) {
+                            if (payload) {
+                                if ((unsigned)pos < (unsigned)tile_len) sm.stage[pos] = (uint8_t)b;
+                                pos++;
+                                if (b == 9u || b == 10u) payload = false;
+                            } else if (b >= 0xE0u) {
+                                payload = true;
+                            } else if (b < 0x80u) {
+                                pos += 4 * (int)b;                        // 0|0: already there
+                            } else {
+                                const uint32_t f = b & 0xE0u;
+                                const bool a1 = f != kTok01, b1 = f != kTok10;
+                                const int cnt = (int)(b & 0x1Fu);
+                                for (int q = 0; q < cnt; q++, pos += 4) {
+                                    if (a1 && (unsigned)pos < (unsigned)tile_len) sm.stage[pos] = '1';
+                                    if (b1 && (unsigned)(pos + 2) < (unsigned)tile_len) sm.stage[pos + 2] = '1';
+                                }
                             }
                         }
                     }
