@@ -2,7 +2,7 @@
 //
 // "Regular" = what a GT-only VCF looks like: '\n'-terminated lines, single tabs, >= 10 columns,
 // every sample column exactly 3 bytes (a|b, a/b, ./. ...), required section (CHROM..FORMAT) of
-// at most kMaxReq bytes, at most kMaxNl line starts per 16 KB tile.  Anything else sets
+// at most kMaxReq bytes, at most kMaxNl (62) line starts per 16 KB tile.  Anything else sets
 // ctrl->irregular and the caller reruns the block on the generic kernels (vcfc_generic.cu).
 // Output bytes are those of compress_data_line (/root/reference/src/compress.cpp:5-203) for every line.
 //
@@ -33,7 +33,7 @@ namespace enc {
 
 constexpr int kHalo = 1024;             // how far around a nominal tile boundary a cut point is searched
 constexpr int kMaxReq = kHalo - 64;     // longest required section taken by this path
-constexpr int kMaxNl = 30;              // line starts per tile taken by this path (one lane each keeps the line's offset)
+constexpr int kMaxNl = 62;              // line starts per tile taken by this path (every lane keeps the offsets of two lines)
 
 enum { kCutLine = 0, kCutSample = 1, kCutSampleFirst = 2, kCutEnd = 3, kCutBad = 4 };
 constexpr int kNone = 7;                // "no open run" class
@@ -386,7 +386,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
         bool need_lb = pc0 < 4;
         // ---- the tile, line by line; pass 0 emits into the staging area while the output fits, pass 1 (rare) straight
         //      into the log once the size is known -------------------------------------------------------------------------
-        int total = 0, nl = 0, my_off = 0;
+        int total = 0, nl = 0, my_off = 0, my_off2 = 0;
         unsigned long long pos = 0ull;
         bool overflow = false, skip_write = false;
         for (int pass = 0; pass < 2; pass++) {
@@ -413,7 +413,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                         }
                         for (int k = lane; k < rq; k += 32) d[8 + k] = win[ls + k];
                     }
-                    if (lane == nl) my_off = o;
+                    if (lane == (nl & 31)) { if (nl < 32) my_off = o; else my_off2 = o; }
                     nl++;
                     o += 8 + rq;
                     cur = s0;
@@ -560,6 +560,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
         if (irregular || skip_write || total == 0) continue;
         uint8_t* const dst = log + pos;
         if (lane < nl) { dst[total + 2 * lane] = (uint8_t)my_off; dst[total + 2 * lane + 1] = (uint8_t)((unsigned)my_off >> 8); }
+        if (lane + 32 < nl) { dst[total + 2 * lane + 64] = (uint8_t)my_off2; dst[total + 2 * lane + 65] = (uint8_t)((unsigned)my_off2 >> 8); }
         if (!overflow) {
             // staging -> log: aligned 4-byte stores, source words funnel-shifted
             __syncwarp();
