@@ -133,7 +133,7 @@ uint64_t vcfc_launch_count(const vcfc_ctx *ctx);
  * lines), 2 = generic line-serial kernels (any input the reference accepts).  Both run on the GPU. */
 int vcfc_last_path(const vcfc_ctx *ctx);
 /* Why the tile kernels last declined a block (0 = never): 1 no final newline, 2 cut point not found inside the
- * halo (required section > 960 B), 3 more than 62 lines per 16 KB tile, 4 line grammar (empty field, < 10 columns,
+ * halo (required section > 960 B), 3 more than 62 lines per 32 KB tile, 4 line grammar (empty field, < 10 columns,
  * sample region not a multiple of 4 bytes), 5 too many segments, 6 a sample column that is not 3 bytes wide,
  * 8 line table overflow, 9 follow-up of another tile's reject. */
 int vcfc_last_reject_reason(const vcfc_ctx *ctx);

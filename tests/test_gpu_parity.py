@@ -130,18 +130,18 @@ def test_regular_blocks_take_the_tile_kernels(codec):
 
 
 def test_short_lines_up_to_62_per_tile(codec):
-    """~0.3 KB lines (62 line starts per 16 KB tile) are still served by the tile kernels; shorter ones by the generic ones."""
-    _, data = vcfgen.random_vcf_like(600, 70, seed=11)           # ~310-byte lines
-    check_block(codec, data, sample_count=70, expect_path=pkg.PATH_FAST)
+    """~0.6 KB lines (up to 62 line starts per 32 KB tile) are still served by the tile kernels; shorter ones by the generic ones."""
+    _, data = vcfgen.random_vcf_like(600, 140, seed=11)          # ~590-byte lines
+    check_block(codec, data, sample_count=140, expect_path=pkg.PATH_FAST)
     _, data = vcfgen.random_vcf_like(600, 30, seed=12)           # ~150-byte lines: more than 62 per tile
     check_block(codec, data, sample_count=30)
     codec.compress_block(data)
     assert codec.last_path == pkg.PATH_GENERIC and codec.last_reject_reason == 3
 
 
-@pytest.mark.parametrize("n_samples", [1, 2, 3, 5, 31, 32, 33, 127, 128, 129, 255, 1000, 3583, 3584, 3585, 7000, 20000])
+@pytest.mark.parametrize("n_samples", [1, 2, 3, 5, 31, 32, 33, 127, 128, 129, 255, 1000, 3583, 3584, 3585, 4096, 7000, 8180, 8191, 8192, 8193, 20000])
 def test_tile_boundaries_sweep(codec, n_samples):
-    """Line widths around the 16 KB tile / 64-byte block / 127- and 31-sample chunk sizes; allele mixes from almost
+    """Line widths around the 32 KB tile / 64-byte block / 127- and 31-sample chunk sizes; allele mixes from almost
     all-default to literal-heavy (allele 2: "0|2" ... stay on the 4-byte grid, so the decoder's fill-and-patch kernel
     needs several staging batches per tile)."""
     for seed, probs in ((1, (0.90, 0.08, 0.02)), (2, (0.9995, 0.0005, 0.0)), (3, (0.0, 1.0, 0.0)), (4, (0.3, 0.3, 0.4))):

@@ -2,11 +2,11 @@
 //
 // "Regular" = what a GT-only VCF looks like: '\n'-terminated lines, single tabs, >= 10 columns,
 // every sample column exactly 3 bytes (a|b, a/b, ./. ...), required section (CHROM..FORMAT) of
-// at most kMaxReq bytes, at most kMaxNl (62) line starts per 16 KB tile.  Anything else sets
+// at most kMaxReq bytes, at most kMaxNl (62) line starts per 32 KB tile.  Anything else sets
 // ctrl->irregular and the caller reruns the block on the generic kernels (vcfc_generic.cu).
 // Output bytes are those of compress_data_line (/root/reference/src/compress.cpp:5-203) for every line.
 //
-// k_encode_stream: ONE WARP per tile of 16 KB, no CTA barriers; HBM traffic = input read once + output
+// k_encode_stream: ONE WARP per tile of 32 KB, no CTA barriers; HBM traffic = input read once + output
 // written once (+ the tile log, see 6):
 //   1. cut points: a tile owns the units (one sample column, or one whole required section) that
 //      START in [cut(i*T), cut((i+1)*T)); both neighbours derive the shared cut from the same bytes
@@ -205,10 +205,10 @@ __device__ __forceinline__ void item_emit(const uint8_t* __restrict__ win, const
 
 // ---- the streaming kernel: one warp per tile -------------------------------------------------------------------------
 #ifndef VCFC_ENC_STILE
-#define VCFC_ENC_STILE 16384
+#define VCFC_ENC_STILE 32768
 #define VCFC_ENC_SWARPS 4
 #define VCFC_ENC_SCTAS 8
-#define VCFC_ENC_SSTAGE 3072
+#define VCFC_ENC_SSTAGE 6144
 #endif
 constexpr int kSTile = VCFC_ENC_STILE;          // nominal input bytes per tile
 constexpr int kSWarps = VCFC_ENC_SWARPS;        // warps per CTA (independent of each other)
