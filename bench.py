@@ -72,7 +72,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.002)
 
     def __enter__(self):
         if self.nv:
@@ -168,7 +168,7 @@ def host_sample(kind, n_lines, n_samples, seed):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lines", type=int, default=int(os.environ.get("VCFC_BENCH_LINES", 1_800_000)))
