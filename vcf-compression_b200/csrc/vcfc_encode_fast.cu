@@ -434,6 +434,8 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
 #pragma unroll
                     for (int q = 0; q < 16; q++) W[q + 1] = ldw(win, blk + 4 * q, r_lo, r_hi);
                 }
+                // the next step's block: a prefetch hint costs no registers and turns its loads into L1 hits
+                if (blk + kStep + 64 <= r_hi && blk + kStep < ce + 64) asm volatile("prefetch.global.L1 [%0];" ::"l"(win + blk + kStep));
                 W[0] = __shfl_up_sync(0xffffffffu, W[16], 1);
                 W[17] = __shfl_down_sync(0xffffffffu, W[1], 1);
                 if (lane == 0) W[0] = ldw(win, blk - 4, r_lo, r_hi);
