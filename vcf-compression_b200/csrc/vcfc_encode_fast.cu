@@ -464,12 +464,20 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 int le = 32;
                 uint32_t L = 0;
                 if (__any_sync(0xffffffffu, (V & ~Craw) != 0u)) {
-                    for (uint32_t t = V & ~Craw; t; t &= t - 1) {
-                        const int k = __ffs(t) - 1;
-                        if (ldb(win, base + 4 * k + 3, r_lo, r_hi) == '\n') { kend = k; break; }
+                    // in rounds, one candidate sample per lane and round: behind the line's end every sample looks odd, and those
+                    // lanes must not walk all of theirs -- only lanes in front of the best newline found so far keep looking
+                    for (uint32_t rem = V & ~Craw;;) {
+                        const bool look = rem != 0u && lane < le;
+                        if (!__any_sync(0xffffffffu, look)) break;
+                        if (look) {
+                            const int k = __ffs(rem) - 1;
+                            rem &= rem - 1;
+                            if (ldb(win, base + 4 * k + 3, r_lo, r_hi) == '\n') { kend = k; rem = 0u; }
+                        }
+                        endm = __ballot_sync(0xffffffffu, kend >= 0);
+                        if (endm) le = __ffs(endm) - 1;
                     }
-                    endm = __ballot_sync(0xffffffffu, kend >= 0);
-                    le = endm ? __ffs(endm) - 1 : 32;
+                    if (lane > le) kend = -1;
                     if (lane > le) V = 0;
                     if (lane == le) V &= (2u << kend) - 1u;
                     q_end = __shfl_sync(0xffffffffu, base + 4 * kend + 3, le & 31);   // the '\n' (valid when endm)
