@@ -129,6 +129,23 @@ def test_regular_blocks_take_the_tile_kernels(codec):
         check_block(codec, data, sample_count=args["n_samples"], expect_path=pkg.PATH_FAST)
 
 
+def test_long_required_sections(codec):
+    """INFO columns of 0.5 - 0.9 KB: the 9th tab lies in the line scan's second 512-byte round, and tile boundaries fall
+    inside required sections; beyond 960 bytes the block goes to the generic kernels.  All byte-identical to the oracle."""
+    rng = __import__("random").Random(17)
+    for info_len, n_samples, expect in ((480, 700, pkg.PATH_FAST), (700, 700, pkg.PATH_FAST), (850, 300, pkg.PATH_FAST),
+                                        (1300, 300, pkg.PATH_GENERIC)):
+        lines = []
+        for i in range(160):
+            info = "AC=1;X=" + "".join(rng.choice("ACGT0123456789;=") for _ in range(info_len + rng.randrange(40)))
+            gts = "\t".join(rng.choice(("0|0",) * 12 + ("0|1", "1|0", "1|1", "0|2", "./.")) for _ in range(n_samples))
+            lines.append(f"7\t{1000 + i}\trs{i}\tA\tC,G\t50\tPASS\t{info}\tGT\t{gts}\n".encode())
+        data = b"".join(lines)
+        check_block(codec, data, sample_count=n_samples)
+        codec.compress_block(data)
+        assert codec.last_path == expect, (info_len, codec.last_reject_reason)
+
+
 def test_short_lines_up_to_62_per_tile(codec):
     """~0.6 KB lines (up to 62 line starts per 32 KB tile) are still served by the tile kernels; shorter ones by the generic ones."""
     _, data = vcfgen.random_vcf_like(600, 140, seed=11)          # ~590-byte lines
