@@ -278,6 +278,14 @@ def test_device_pointer_api(codec):
     r2 = codec.fetch_result(d_res.data_ptr(), st)
     assert r2.status == 0 and r2.out_len == len(data)
     assert torch.equal(d_txt[:len(data)], d_in)
+    # device buffers at odd addresses: compressed input and text output one / three bytes off any alignment
+    d_c2 = torch.empty(r.out_len + 64, dtype=torch.uint8, device=dev)
+    d_c2[1:1 + r.out_len] = d_out[:r.out_len]
+    d_t2 = torch.zeros(len(data) + 64, dtype=torch.uint8, device=dev)
+    codec.decode_dev(d_c2.data_ptr() + 1, r.out_len, 2504, d_t2.data_ptr() + 3, len(data) + 32, d_res.data_ptr(), st)
+    r3 = codec.fetch_result(d_res.data_ptr(), st)
+    assert r3.status == 0 and r3.out_len == len(data)
+    assert torch.equal(d_t2[3:3 + len(data)], d_in)
 
 
 # ---- file drivers and the CLI (reference verbs) ----------------------------------------------------

@@ -66,30 +66,62 @@ __global__ void k_dec_walk(const uint8_t* __restrict__ in, long long n, long lon
     if (s >= n_seg) return;
     const long long lo = s * kSeg, hi = lo + kSeg < n ? lo + kSeg : n;
     long long c = kNoCand, ll = 0;
-    for (long long base = lo; base < hi && c == kNoCand; base += 128) {
-        unsigned hit[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const long long p = base + 32 * u + lane;
-            bool h = false;
-            if (p < hi && n - p >= 8) {
-                const bool after_nl = p == 0 || in[p - 1] == '\n';
-                h = after_nl && (in[p] >> 6) == 3 && (in[p + 4] >> 6) == 3;      // both length tags present
+    if ((reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+        // 512 bytes per round trip: newline bytes by word-parallel tests, then the candidates behind them in order
+        if (lo == 0) {
+            if (plausible_line(in, n, 0, &ll)) c = 0;            // offset 0 must be a line start
+        } else {
+            for (long long wb = lo - 16; wb < hi && c == kNoCand; wb += 512) {
+                const long long g = wb + 16 * lane;
+                unsigned nlm = 0;                                // bit j: byte g + j is a newline
+                if (g + 16 <= n) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(in + g);
+                    nlm = nibble_of(zero_bytes(v.x ^ 0x0A0A0A0Au)) | (nibble_of(zero_bytes(v.y ^ 0x0A0A0A0Au)) << 4) |
+                          (nibble_of(zero_bytes(v.z ^ 0x0A0A0A0Au)) << 8) | (nibble_of(zero_bytes(v.w ^ 0x0A0A0A0Au)) << 12);
+                } else {
+                    for (int j = 0; j < 16; j++) if (g + j < n && in[g + j] == '\n') nlm |= 1u << j;
+                }
+                unsigned cand = 0;                               // bit j: a line may start at g + j + 1
+                for (unsigned t = nlm; t; t &= t - 1) {
+                    const int j = __ffs(t) - 1;
+                    const long long p = g + j + 1;
+                    if (p >= lo && p < hi && n - p >= 8 && (in[p] >> 6) == 3 && (in[p + 4] >> 6) == 3) cand |= 1u << j;   // both length tags
+                }
+                unsigned any;
+                while (c == kNoCand && (any = __ballot_sync(0xffffffffu, cand != 0u)) != 0u) {
+                    const int leader = __ffs(any) - 1;
+                    const long long p = __shfl_sync(0xffffffffu, g + __ffs(cand), leader);
+                    if (lane == leader) cand &= cand - 1;
+                    if (plausible_line(in, n, p, &ll)) c = p;
+                }
             }
-            hit[u] = __ballot_sync(0xffffffffu, h);
         }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            unsigned m = hit[u];
-            while (m && c == kNoCand) {
-                const long long p = base + 32 * u + (__ffs(m) - 1);
-                m &= m - 1;
-                if (plausible_line(in, n, p, &ll)) c = p;
+    } else {
+        for (long long base = lo; base < hi && c == kNoCand; base += 128) {
+            unsigned hit[4];
+    #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const long long p = base + 32 * u + lane;
+                bool h = false;
+                if (p < hi && n - p >= 8) {
+                    const bool after_nl = p == 0 || in[p - 1] == '\n';
+                    h = after_nl && (in[p] >> 6) == 3 && (in[p + 4] >> 6) == 3;      // both length tags present
+                }
+                hit[u] = __ballot_sync(0xffffffffu, h);
             }
+    #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                unsigned m = hit[u];
+                while (m && c == kNoCand) {
+                    const long long p = base + 32 * u + (__ffs(m) - 1);
+                    m &= m - 1;
+                    if (plausible_line(in, n, p, &ll)) c = p;
+                }
+            }
+            if (lo == 0 && c != 0) break;                        // offset 0 must be a line start
         }
-        if (lo == 0 && c != 0) break;                        // offset 0 must be a line start
+        if (lo == 0 && c != 0) c = kNoCand;
     }
-    if (lo == 0 && c != 0) c = kNoCand;
     unsigned long long k = 0;
     long long p = c;
     if (c >= 0) {
