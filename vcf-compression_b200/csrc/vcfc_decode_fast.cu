@@ -207,7 +207,7 @@ __global__ void k_dec_repair(const uint8_t* __restrict__ in, long long n, long l
 
 __global__ void k_dec_fill(const uint8_t* __restrict__ in, long long n, long long n_seg, const long long* __restrict__ cand,
                            const unsigned long long* __restrict__ base, unsigned long long* __restrict__ line_start,
-                           unsigned long long n_lines, const Ctrl* __restrict__ ctrl) {
+                           unsigned* __restrict__ rq_arr, unsigned long long n_lines, const Ctrl* __restrict__ ctrl) {
     long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg || ctrl->irregular) return;
     long long p = cand[s];
@@ -216,6 +216,7 @@ __global__ void k_dec_fill(const uint8_t* __restrict__ in, long long n, long lon
     unsigned long long k = base[s];
     while (true) {
         long long ll = hdr_len(in + p);
+        rq_arr[k] = (unsigned)hdr_len(in + p + 4);          // (same sector as the line length: saves k_dec_sizes a dependent load)
         line_start[k++] = (unsigned long long)p;
         p += 4 + ll;
         if (p >= hi || n - p < 8) break;
@@ -270,7 +271,7 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
     const unsigned long long ls = line_start[k], le = line_start[k + 1];
     const uint8_t* p = in + ls;
     const long long clen = (long long)(le - ls);
-    const long long rq = hdr_len(p + 4);
+    const long long rq = (long long)(int)rq_arr[k];          // second length header, read by k_dec_fill (-1: bad tag)
     bool bad = rq < 1 || rq + 9 > clen || clen > 0x7fffffffll;
     if (lane == 0) rq_arr[k] = (unsigned)(bad ? 0 : rq);
     // required section: exactly 9 tabs (compress.cpp:820-828; the 8-tab form means no samples -> generic path)
@@ -981,7 +982,7 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
     if ((rc = dev_reserve(ctx, &b_tab, ((size_t)in_len / 16 + n_lines + 8) * 4))) return rc;
     if ((rc = dev_reserve(ctx, &b_rq, (n_lines + 2) * 4))) return rc;
     unsigned long long* line_start = (unsigned long long*)b_ls.p;
-    k_dec_fill<<<gs, 128, 0, stream>>>(d_in, n, n_seg, cand, base, line_start, n_lines, ctrl);
+    k_dec_fill<<<gs, 128, 0, stream>>>(d_in, n, n_seg, cand, base, line_start, (unsigned*)b_rq.p, n_lines, ctrl);
     k_dec_sizes<<<(unsigned)((n_lines * 32 + 127) / 128), 128, 0, stream>>>(d_in, line_start, n_lines, sample_count,
                                                                              (unsigned long long*)b_sizes.p, (unsigned*)b_tab.p, (unsigned*)b_rq.p, ctrl);
     ctx->launches += 2;
