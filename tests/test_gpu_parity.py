@@ -191,6 +191,29 @@ def test_run_length_lines(any_path):
     check_block(any_path, b"".join(vcfgen.run_length_lines(lengths=(126, 127, 128, 381), n_samples=2504)), sample_count=2504)
 
 
+def test_fuzz_blocks(any_path):
+    """Seeded random blocks over regular and odd genotype columns (the alphabet of tests/test_oracle.py's fuzz against the
+    reference binary), run lengths around the 31 / 127 chunk sizes, long and short lines mixed in one block."""
+    import random
+    rng = random.Random(77)
+    alphabet = ["0|0"] * 6 + ["0|1", "1|0", "1|1", "0|2", "2|1", "./.", ".", "0/0", "0/1", "1", "10|0", "0|0|0", "0|0:3", "1|1:12"]
+    regular = ["0|0"] * 8 + ["0|1", "1|0", "1|1", "0|2", "./.", "0/1"]
+    runs = [1, 2, 3, 30, 31, 32, 33, 62, 63, 126, 127, 128, 129, 254, 255, 300, 1000]
+    for case in range(24):
+        n_samples = rng.choice([7, 200, 700, 2504, 9000])
+        alpha = regular if case % 2 else alphabet            # odd cases stay inside the tile kernels' grammar
+        lines = []
+        for i in range(rng.randrange(1, 40)):
+            gts = []
+            while len(gts) < n_samples:
+                gts += [rng.choice(alpha)] * rng.choice(runs if rng.random() < 0.5 else [1, 1, 1, 2, 5])
+            gts = gts[:n_samples]
+            info = "AC=%d;" % rng.randrange(100) + "X" * rng.randrange(0, 300)
+            lines.append("%s\t%d\trs%d\tA\tC,G\t%d\tPASS\t%s\tGT\t%s\n" % (
+                rng.choice(["1", "20", "X"]), 100 + 7 * i, i, rng.randrange(1000), info, "\t".join(gts)))
+        check_block(any_path, "".join(lines).encode(), sample_count=n_samples)
+
+
 def test_ragged_and_empty_inputs(any_path):
     rc, out, nl, _ = any_path.compress_block(b"")
     assert rc == 0 and out == b"" and nl == 0

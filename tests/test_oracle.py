@@ -126,6 +126,39 @@ def test_live_reference_binary(maker, args):
         assert rc == 0 and txt == open(rp, "rb").read() == vcf
 
 
+@pytest.mark.skipif(not O.have_ref_binary(), reason="oracle/_ref/main_release not built")
+def test_fuzz_vs_reference_binary(tmp_path):
+    """Seeded random files over an alphabet of regular and odd genotype columns, run lengths around the 31 / 127 chunk
+    sizes, CR-LF and GT:DP lines: the oracle and the unmodified reference must write the same bytes both ways."""
+    import random
+    rng = random.Random(2024)
+    alphabet = ["0|0"] * 6 + ["0|1", "1|0", "1|1", "0|2", "2|1", "./.", ".", "0/0", "0/1", "1", "10|0", "0|0|0", "0|0:3", "1|1:12"]
+    runs = [1, 2, 3, 30, 31, 32, 33, 62, 63, 126, 127, 128, 129, 254, 255, 300]
+    for case in range(40):
+        n_samples = rng.choice([1, 2, 7, 31, 32, 200, 700])
+        crlf = rng.random() < 0.15
+        lines = []
+        for i in range(rng.randrange(1, 12)):
+            gts = []
+            while len(gts) < n_samples:
+                gts += [rng.choice(alphabet)] * rng.choice(runs if rng.random() < 0.5 else [1, 1, 1, 2, 5])
+            gts = gts[:n_samples]
+            info = "AC=%d;AF=0.%d" % (rng.randrange(100), rng.randrange(1000))
+            fmt = "GT:DP" if any(":" in g for g in gts) else "GT"
+            lines.append("%s\t%d\trs%d\tA\tC,G\t%d\tPASS\t%s\t%s\t%s%s\n" % (
+                rng.choice(["1", "20", "X"]), 100 + 7 * i, i, rng.randrange(1000), info, fmt, "\t".join(gts), "\r" if crlf else ""))
+        vcf = vcfgen.header(n_samples) + "".join(lines).encode()
+        ip, op, rp = (str(tmp_path / x) for x in ("a.vcf", "a.vcfc", "a.rt"))
+        open(ip, "wb").write(vcf)
+        assert subprocess.run([O.REF_BIN, "compress", ip, op], capture_output=True).returncode == 0, case
+        ref = open(op, "rb").read()
+        rc, mine = O.compress_vcf(vcf)
+        assert rc == 0 and mine == ref, case
+        assert subprocess.run([O.REF_BIN, "decompress", op, rp], capture_output=True).returncode == 0, case
+        rc, txt = O.decompress_vcfc(ref)
+        assert rc == 0 and txt == open(rp, "rb").read(), case
+
+
 def test_file_drivers(tmp_path):
     h, d = vcfgen.random_vcf_like(20, 50, seed=2)
     ip, op, rp = (str(tmp_path / x) for x in ("a.vcf", "a.vcfc", "a.rt"))
