@@ -242,6 +242,18 @@ def test_error_lines(any_path):
     assert rc == pkg.E_CAP
 
 
+def test_exact_capacity(any_path):
+    """A multi-tile block into a buffer of exactly the output size succeeds; one byte less is VCFC_E_CAP (both ways)."""
+    _, data = vcfgen.kg_like(60, 2504, seed=3)
+    ref = O.compress_block(data)[1]
+    rc, out, nl, _ = any_path.compress_block(data, out_cap=len(ref))
+    assert rc == 0 and out == ref and nl == 60
+    assert any_path.compress_block(data, out_cap=len(ref) - 1)[0] == pkg.E_CAP
+    rc, txt, nl, _ = any_path.decompress_block(ref, 2504, out_cap=len(data))
+    assert rc == 0 and txt == data and nl == 60
+    assert any_path.decompress_block(ref, 2504, out_cap=len(data) - 1)[0] == pkg.E_CAP
+
+
 def test_decode_rejects_bad_input(any_path):
     _, data = vcfgen.random_vcf_like(3, 8, seed=1)
     rc, out, _, _ = any_path.compress_block(data)
