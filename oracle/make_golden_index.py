@@ -1,0 +1,74 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/index/ from the UNMODIFIED reference (run in the build container only):
+.vcfci files written by `main_release create-binned-index <bin> <file.vcfc>` (main.cpp:1284-1637) for some of
+the committed .vcfc fixtures and for a structural-variant / multi-chromosome file made here.  They pin
+oracle/vcfc_oracle.c:vcfc_oracle_build_binned_index, the oracle of the next scope row.
+"""
+import json
+import os
+import random
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oracle", "_ref", "main_release")
+OUT = os.path.join(ROOT, "tests", "golden", "index")
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import goldenlib  # noqa: E402
+import vcfgen  # noqa: E402
+
+
+def sv_mix(n_lines=240, seed=5) -> bytes:
+    rng = random.Random(seed)
+    lines, pos = [], 1000
+    for i in range(n_lines):
+        chrom = rng.choice(["1", "1", "2", "X", "22", "GL000207.1", "M"])
+        pos += rng.randrange(1, 500)
+        kind = rng.randrange(7)
+        if kind == 0:
+            ref, alt, info = "A", "<DEL>", "SVTYPE=DEL;END=%d" % (pos + rng.randrange(5000))
+        elif kind == 1:
+            ref, alt, info = "A", "<DUP>", "SVTYPE=DUP;SVLEN=%d" % rng.randrange(-3000, 3000)
+        elif kind == 2:
+            ref, alt, info = "A", "<INS:ME:ALU>", "SVTYPE=ALU;TSD=null"
+        elif kind == 3:
+            ref, alt, info = "ACGTACGT", "A,AC", "AC=1;AF=0.5"
+        elif kind == 4:
+            ref, alt, info = "A", "ACGTTTT,G", "AC=1;;DB"
+        elif kind == 5:
+            ref, alt, info = "A", "<CN0>,<CN2>", "END=%d,%d;CS=x" % (pos + 10, pos + 999)
+        else:
+            ref, alt, info = "A", "<DEL>", "SVLEN=-%d,%d;END" % (rng.randrange(100), rng.randrange(100))
+        gts = "\t".join(rng.choice(["0|0", "0|1", "1|1"]) for _ in range(6))
+        lines.append("%s\t%d\trs%d\t%s\t%s\t100\tPASS\t%s\tGT\t%s\n" % (chrom, pos, i, ref, alt, info, gts))
+    return vcfgen.header(6) + "".join(lines).encode()
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    manifest = {}
+    with tempfile.TemporaryDirectory() as wd:
+        ip, op = os.path.join(wd, "a.vcf"), os.path.join(wd, "a.vcfc")
+        open(ip, "wb").write(sv_mix())
+        assert subprocess.run([BIN, "compress", ip, op], capture_output=True).returncode == 0
+        open(os.path.join(OUT, "sv_mix.vcfc"), "wb").write(open(op, "rb").read())
+        sources = {"sv_mix": open(op, "rb").read()}
+        for name in ("refgen_300x40", "kg_2504x60", "edge_8samples"):
+            sources[name] = goldenlib.read(name + ".vcfc")
+        for name, vcfc in sources.items():
+            open(op, "wb").write(vcfc)
+            for b in (1, 4, 25):
+                r = subprocess.run([BIN, "create-binned-index", str(b), op], capture_output=True)
+                assert r.returncode == 0, (name, b, r.stderr[-300:])
+                idx = open(op + ".vcfci", "rb").read()
+                fn = "%s.bin%d.vcfci" % (name, b)
+                open(os.path.join(OUT, fn), "wb").write(idx)
+                manifest[fn] = {"source": name + ".vcfc" + ("" if name == "sv_mix" else " (tests/golden/)"),
+                                "entries_per_bin": b, "entries": len(idx) // 13}
+    json.dump(manifest, open(os.path.join(OUT, "MANIFEST.json"), "w"), indent=1, sort_keys=True)
+    print("wrote", len(manifest), "index fixtures to", OUT)
+
+
+if __name__ == "__main__":
+    main()

@@ -284,6 +284,199 @@ long vcfc_oracle_parse_headers(const uint8_t *in, size_t in_len, uint64_t *sampl
     return (long)p;
 }
 
+/* ---- binned index (.vcfci), the next row of the scope table --------------------------
+ * Restates create_binned_index4 (main.cpp:1284-1637) on a whole .vcfc file held in memory.
+ * Entry = {u8 reference index, u32 position, u64 byte offset of the line in the file}, 13 bytes,
+ * native little-endian (write_index_entry, main.cpp:600-626).  Not used by the product yet. */
+
+/* strtoul-based integer parse of utils.cpp:152-175: whole field must be consumed; leading blanks,
+ * '+', '-' accepted (a '-' negates modulo 2^64).  Returns 0 on success. */
+static int parse_ul_field(const uint8_t *p, size_t n, long *out) {
+    char buf[64];
+    char *end = NULL;
+    if (n >= sizeof buf) return -1;
+    memcpy(buf, p, n);
+    buf[n] = 0;
+    if (strlen(buf) != n) return -1;                       /* an embedded NUL ends the C string early */
+    *out = (long)strtoul(buf, &end, 10);
+    return end == buf + n ? 0 : -1;
+}
+
+/* reference_name_map (utils.hpp:90-103, utils.cpp:16-25): "1".."22","X","Y","M" -> 1..25, else 0 */
+static uint8_t ref_name_index(const uint8_t *p, size_t n) {
+    if (n == 1 && p[0] == 'X') return 23;
+    if (n == 1 && p[0] == 'Y') return 24;
+    if (n == 1 && p[0] == 'M') return 25;
+    if (n == 1 && p[0] >= '1' && p[0] <= '9') return (uint8_t)(p[0] - '0');
+    if (n == 2 && p[0] >= '1' && p[0] <= '2' && p[1] >= '0' && p[1] <= '9') {
+        int v = 10 * (p[0] - '0') + (p[1] - '0');
+        return v <= 22 ? (uint8_t)v : 0;
+    }
+    return 0;
+}
+
+/* value of key (exact match) in a ';'-separated key=value list, parse_kvp semantics (main.cpp:737-757):
+ * empty pairs are skipped (split_string drops empty terms, utils.cpp:95), "k" alone has the value "",
+ * "k=a=b" is an error (-1), a later duplicate wins.  Returns 1 found, 0 absent, -1 malformed list. */
+static int kvp_lookup(const uint8_t *info, size_t n, const char *key, const uint8_t **val, size_t *val_len) {
+    size_t klen = strlen(key), i = 0;
+    int found = 0;
+    while (i < n) {
+        size_t j = i;
+        while (j < n && info[j] != ';') j++;
+        if (j > i) {
+            /* split the pair on '=' dropping empty parts */
+            const uint8_t *part[3];
+            size_t plen[3];
+            int np = 0;
+            size_t a = i;
+            while (a < j) {
+                size_t b = a;
+                while (b < j && info[b] != '=') b++;
+                if (b > a) {
+                    if (np == 2) return -1;
+                    part[np] = info + a; plen[np] = b - a; np++;
+                }
+                a = b + 1;
+            }
+            if (np == 0) return -1;                          /* "=" alone: parts.size() == 0 -> throws */
+            if (plen[0] == klen && memcmp(part[0], key, klen) == 0) {
+                found = 1;
+                if (np == 2) { *val = part[1]; *val_len = plen[1]; }
+                else { *val = part[0]; *val_len = 0; }
+            }
+        }
+        i = j + 1;
+    }
+    return found;
+}
+
+/* compute_end_position (main.cpp:763-852).  Returns 0, or -1 where the reference throws. */
+static int end_position(long pos, size_t ref_len, const uint8_t *alt, size_t alt_len,
+                        const uint8_t *info, size_t info_len, long *end_out) {
+    if (memchr(alt, '<', alt_len) != NULL) {                /* alt_is_structural, main.cpp:759-761 */
+        const uint8_t *v = NULL;
+        size_t vl = 0;
+        int r = kvp_lookup(info, info_len, "END", &v, &vl);
+        if (r < 0) return -1;
+        if (r == 1) {
+            long max_end = 0;
+            size_t i = 0;
+            while (i < vl) {                                /* split on ',' dropping empty terms */
+                size_t j = i;
+                long e;
+                while (j < vl && v[j] != ',') j++;
+                if (j > i) {
+                    if (parse_ul_field(v + i, j - i, &e) != 0) return -1;
+                    if (e > max_end) max_end = e;
+                }
+                i = j + 1;
+            }
+            *end_out = max_end < 0 ? -max_end : max_end;
+            return 0;
+        }
+        r = kvp_lookup(info, info_len, "SVLEN", &v, &vl);
+        if (r < 0) return -1;
+        if (r == 1) {
+            long max_len = 0;
+            size_t i = 0;
+            while (i < vl) {
+                size_t j = i;
+                long e;
+                while (j < vl && v[j] != ',') j++;
+                if (j > i) {
+                    if (parse_ul_field(v + i, j - i, &e) != 0) return -1;
+                    if (e < 0) e = -e;
+                    if (e > max_len) max_len = e;
+                }
+                i = j + 1;
+            }
+            *end_out = pos + max_len - 1;
+            return 0;
+        }
+        *end_out = pos;
+        return 0;
+    }
+    {
+        size_t max_alt = 0, i = 0;
+        while (i < alt_len) {                               /* longest ',' separated ALT allele */
+            size_t j = i;
+            while (j < alt_len && alt[j] != ',') j++;
+            if (j - i > max_alt) max_alt = j - i;
+            i = j + 1;
+        }
+        *end_out = pos + (long)(ref_len >= max_alt ? ref_len : max_alt) - 1;
+    }
+    return 0;
+}
+
+/*
+ * Whole .vcfc file -> .vcfci bytes.  Walks the compressed lines by their length headers, reads only
+ * columns 1-8 of each required section, and applies the bin rule of main.cpp:1430-1470: a line whose
+ * number is a multiple of entries_per_bin opens a new entry if its END exceeds the last entry's position,
+ * every other line can only grow the last entry's position (compared as u32, never looking at the
+ * chromosome).  Returns the number of entries or a negative code.
+ */
+long vcfc_oracle_build_binned_index(const uint8_t *in, size_t in_len, uint64_t entries_per_bin,
+                                    uint8_t *out, size_t cap, size_t *out_len) {
+    uint64_t sample_count = 0, line_number = 0;
+    long hdr = vcfc_oracle_parse_headers(in, in_len, &sample_count);
+    size_t p, n_entries = 0;
+    if (hdr < 0) return hdr;
+    if (entries_per_bin == 0) return VCFC_E_FORMAT;         /* the reference divides by it */
+    p = (size_t)hdr;
+    *out_len = 0;
+    while (in_len - p >= 8) {                               /* fewer than 8 bytes left: EOF (compress.cpp:270-330) */
+        int64_t ll = get_len_header(in + p), rq = get_len_header(in + p + 4);
+        const uint8_t *f[8];
+        size_t fl[8], q = p + 8, line_end;
+        int k;
+        long pos, endp;
+        uint8_t idx;
+        if (ll < 0 || rq < 0) return VCFC_E_FORMAT;
+        line_end = p + 4 + (size_t)ll;
+        if (line_end > in_len) return VCFC_E_TRUNC;
+        for (k = 0; k < 8; k++) {                           /* read_to(..., '\t') x 8 (main.cpp:1371-1405) */
+            size_t e = q;
+            while (e < in_len && in[e] != '\t') e++;
+            if (e >= in_len) return VCFC_E_TRUNC;
+            f[k] = in + q; fl[k] = e - q;
+            q = e + 1;
+        }
+        if (parse_ul_field(f[1], fl[1], &pos) != 0) return VCFC_E_FORMAT;
+        if (end_position(pos, fl[3], f[4], fl[4], f[7], fl[7], &endp) != 0) return VCFC_E_FORMAT;
+        idx = ref_name_index(f[0], fl[0]);
+        if (n_entries == 0) {
+            if (cap < 13) return VCFC_E_CAP;
+            out[0] = idx;
+            { uint32_t v = (uint32_t)endp; memcpy(out + 1, &v, 4); }
+            { uint64_t v = (uint64_t)p; memcpy(out + 5, &v, 8); }
+            n_entries = 1;
+        } else {
+            uint8_t *last = out + 13 * (n_entries - 1);
+            uint32_t last_end;
+            memcpy(&last_end, last + 1, 4);
+            if ((unsigned long)endp > (unsigned long)last_end) {
+                if (line_number % entries_per_bin == 0) {
+                    uint8_t *e = out + 13 * n_entries;
+                    if (cap < 13 * (n_entries + 1)) return VCFC_E_CAP;
+                    e[0] = idx;
+                    { uint32_t v = (uint32_t)endp; memcpy(e + 1, &v, 4); }
+                    { uint64_t v = (uint64_t)p; memcpy(e + 5, &v, 8); }
+                    n_entries++;
+                } else {
+                    uint32_t v = (uint32_t)endp;
+                    memcpy(last + 1, &v, 4);
+                }
+            }
+        }
+        line_number++;
+        p = line_end;
+    }
+    *out_len = 13 * n_entries;
+    return (long)n_entries;
+}
+
 /* ---- file-level drivers (compress.cpp:205-257 and 1214-1257), for the CPU baseline ---- */
 
 static uint8_t *read_file(const char *path, size_t *len) {

@@ -33,6 +33,8 @@ def lib():
         _lib.vcfc_oracle_parse_headers.argtypes = [u8p, sz, C.POINTER(C.c_uint64)]
         _lib.vcfc_oracle_parse_headers.restype = C.c_long
         _lib.vcfc_oracle_compress_file.argtypes = [C.c_char_p, C.c_char_p]
+        _lib.vcfc_oracle_build_binned_index.argtypes = [u8p, sz, C.c_uint64, C.c_void_p, sz, szp]
+        _lib.vcfc_oracle_build_binned_index.restype = C.c_long
         _lib.vcfc_oracle_decompress_file.argtypes = [C.c_char_p, C.c_char_p]
     return _lib
 
@@ -96,3 +98,12 @@ def decompress_vcfc(vcfc: bytes):
 
 def have_ref_binary():
     return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
+
+
+def build_binned_index(vcfc: bytes, entries_per_bin: int):
+    """Whole .vcfc file -> (rc_or_entry_count, .vcfci bytes); restates create_binned_index4 (main.cpp:1284-1637)."""
+    cap = 13 * (vcfc.count(b"\n") + 2)
+    out = C.create_string_buffer(cap)
+    olen = C.c_size_t(0)
+    rc = lib().vcfc_oracle_build_binned_index(vcfc, len(vcfc), entries_per_bin, out, cap, C.byref(olen))
+    return rc, out.raw[:olen.value]

@@ -5,6 +5,7 @@
 (c) the reference binary run live on fresh seeded inputs, when oracle/_ref is present.
 """
 import hashlib
+import json
 import os
 import subprocess
 import tempfile
@@ -157,6 +158,34 @@ def test_fuzz_vs_reference_binary(tmp_path):
         assert subprocess.run([O.REF_BIN, "decompress", op, rp], capture_output=True).returncode == 0, case
         rc, txt = O.decompress_vcfc(ref)
         assert rc == 0 and txt == open(rp, "rb").read(), case
+
+
+# ---- binned index (.vcfci): oracle of the next scope row, not yet served by the CUDA library ----
+def test_binned_index_golden():
+    """vcfc_oracle_build_binned_index == the .vcfci files written by `main_release create-binned-index`
+    (oracle/make_golden_index.py): plain SNP files, edge-case lines, structural variants over several chromosomes."""
+    idir = os.path.join(goldenlib.GOLDEN, "index")
+    man = json.load(open(os.path.join(idir, "MANIFEST.json")))
+    assert len(man) >= 12
+    for fn, e in man.items():
+        name = fn.split(".bin")[0]
+        vcfc = open(os.path.join(idir, name + ".vcfc"), "rb").read() if name == "sv_mix" else goldenlib.read(name + ".vcfc")
+        rc, idx = O.build_binned_index(vcfc, e["entries_per_bin"])
+        assert rc == e["entries"], fn
+        assert idx == open(os.path.join(idir, fn), "rb").read(), fn
+
+
+@pytest.mark.skipif(not O.have_ref_binary(), reason="oracle/_ref/main_release not built")
+def test_binned_index_live_reference(tmp_path):
+    h, d = vcfgen.kg_like(150, 40, seed=21)
+    ip, op = str(tmp_path / "a.vcf"), str(tmp_path / "a.vcfc")
+    open(ip, "wb").write(h + d)
+    assert subprocess.run([O.REF_BIN, "compress", ip, op], capture_output=True).returncode == 0
+    vcfc = open(op, "rb").read()
+    for b in (1, 2, 7, 1000):
+        assert subprocess.run([O.REF_BIN, "create-binned-index", str(b), op], capture_output=True).returncode == 0
+        rc, idx = O.build_binned_index(vcfc, b)
+        assert rc > 0 and idx == open(op + ".vcfci", "rb").read(), b
 
 
 def test_file_drivers(tmp_path):
