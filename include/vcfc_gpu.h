@@ -121,6 +121,12 @@ int vcfc_compress_file(vcfc_ctx *ctx, const char *in_path, const char *out_path)
 int vcfc_decompress_file(vcfc_ctx *ctx, const char *in_path, const char *out_path);
 /* query_compressed_file(in, REF:START-END) -> matching lines to out_fd, src/main.cpp:3777-3929 */
 int vcfc_query_file(vcfc_ctx *ctx, const char *in_path, const char *region, int out_fd);
+/* create_binned_index4(compressed, index, entries_per_bin), src/main.cpp:1284-1637 (CLI verb create-binned-index,
+ * main.cpp:4097-4115): writes the .vcfci index -- 13-byte entries {u8 chromosome index, u32 max END position of the
+ * bin, u64 byte offset of the bin's first line} -- of a .vcfc file.  Columns 1-8 of every line are read and turned
+ * into an END position on the GPU; the sequential bin rule runs on the host.  *n_entries (nullable) = entries written. */
+int vcfc_create_binned_index_file(vcfc_ctx *ctx, const char *vcfc_path, const char *index_path, uint64_t entries_per_bin,
+                                  uint64_t *n_entries);
 
 /* Instrumentation: device time (ms, CUDA events on the launch stream) of the kernels of the
  * most recent *_dev call when timing is enabled.  which: 0 = encode kernel, 1 = decode scan

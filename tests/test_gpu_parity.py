@@ -359,6 +359,45 @@ def test_query_matches_reference_outputs(codec, golden, tmp_path):
     assert codec.query(fp, "1:5", 1) == pkg.E_QUERY
 
 
+# ---- binned index (.vcfci): the next row of the scope table -------------------------------
+def test_binned_index_matches_oracle_and_reference(codec, tmp_path):
+    """vcfc_create_binned_index_file (per-line END / chromosome index on the GPU) writes the bytes of the reference's
+    create-binned-index: against the committed fixtures of the reference binary, the oracle on fresh files, the CLI verb."""
+    import json
+    idir = os.path.join(goldenlib.GOLDEN, "index")
+    man = json.load(open(os.path.join(idir, "MANIFEST.json")))
+    for fn, e in man.items():
+        name = fn.split(".bin")[0]
+        vcfc = open(os.path.join(idir, name + ".vcfc"), "rb").read() if name == "sv_mix" else goldenlib.read(name + ".vcfc")
+        ip, xp = str(tmp_path / "g.vcfc"), str(tmp_path / "g.vcfci")
+        open(ip, "wb").write(vcfc)
+        rc, n = codec.create_binned_index(ip, xp, e["entries_per_bin"])
+        assert rc == 0 and n == e["entries"], fn
+        assert open(xp, "rb").read() == open(os.path.join(idir, fn), "rb").read(), fn
+    # a larger file with long INFO columns, through the compressor of this library, several bin sizes
+    h, d = vcfgen.kg_like(3000, 100, seed=31)
+    vp, cp = str(tmp_path / "k.vcf"), str(tmp_path / "k.vcfc")
+    open(vp, "wb").write(h + d)
+    assert codec.compress(vp, cp) == 0
+    vcfc = open(cp, "rb").read()
+    for b in (1, 10, 1000, 100000):
+        rc, n = codec.create_binned_index(cp, cp + ".x", b)
+        orc, oidx = O.build_binned_index(vcfc, b)
+        assert rc == 0 and n == orc and open(cp + ".x", "rb").read() == oidx, b
+    # the CLI verb writes <file>.vcfci (main.cpp:4097-4115)
+    assert subprocess.run([pkg.CLI_PATH, "create-binned-index", "10", cp], capture_output=True).returncode == 0
+    assert open(cp + ".vcfci", "rb").read() == O.build_binned_index(vcfc, 10)[1]
+    # malformed input: the reference throws, the library returns a code
+    bad = bytearray(vcfc)
+    data0 = vcfc.index(b"\n", vcfc.index(b"\n#CHROM") + 1) + 1
+    tab = vcfc.index(b"\t", data0 + 8)
+    bad[tab + 1] = ord("x")                                  # POS of the first line is no longer a number
+    open(cp, "wb").write(bytes(bad))
+    assert codec.create_binned_index(cp, cp + ".x", 10)[0] == pkg.E_FORMAT
+    assert O.build_binned_index(bytes(bad), 10)[0] < 0
+    assert codec.create_binned_index(str(tmp_path / "missing.vcfc"), cp + ".x", 10)[0] == pkg.E_IO
+
+
 def test_live_reference_binary_if_shipped(codec, tmp_path):
     """oracle/_ref/main_release (the unmodified reference, prebuilt) travels to the GPU box."""
     if not O.have_ref_binary():

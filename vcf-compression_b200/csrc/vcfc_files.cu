@@ -6,6 +6,7 @@
 //   decompress2_metadata_headers_fd()   src/compress.cpp:1108-1211
 //   query_compressed_file()             src/main.cpp:3777-3929
 //   parse_coordinate_string()           src/main.cpp:3993-4026
+//   create_binned_index4()              src/main.cpp:1284-1637 (per-line fields on the GPU: vcfc_index.cu)
 #include <errno.h>
 #include <fcntl.h>
 #include <stdlib.h>
@@ -266,3 +267,90 @@ int vcfc_query_file(vcfc_ctx* ctx, const char* in_path, const char* region, int 
 }
 
 }  // extern "C"
+
+// create-binned-index (main.cpp:4097-4115 -> create_binned_index4, main.cpp:1284-1637).  The host walks the line-length
+// headers (one header per line, as every reference consumer does), the GPU reads columns 1-8 of every line and
+// computes its END position and chromosome index (vcfc_index.cu), the host applies the bin rule (main.cpp:1430-1470:
+// a line whose number is a multiple of entries_per_bin opens an entry if its END exceeds the last entry's position,
+// any other line can only grow that position) and writes 13 bytes per entry (main.cpp:600-626).
+int vcfc_create_binned_index_file(vcfc_ctx* ctx, const char* vcfc_path, const char* index_path, uint64_t entries_per_bin,
+                                  uint64_t* n_entries) {
+    if (!ctx || !vcfc_path || !index_path || entries_per_bin == 0) return VCFC_E_ARG;
+    if (n_entries) *n_entries = 0;
+    HostFile f;
+    int rc = f.load(vcfc_path);
+    if (rc) return rc;
+    size_t hlen = 0;
+    uint64_t sc = 0;
+    if ((rc = vcfc_parse_headers(f.p, f.n, &hlen, &sc))) return rc;
+    // line starts (absolute file offsets = the index's byte offsets)
+    std::vector<unsigned long long> starts;
+    size_t pos = hlen;
+    while (f.n - pos >= 8) {                                            // fewer than 8 bytes left: EOF (compress.cpp:270-330)
+        if ((f.p[pos] >> 6) != 3 || (f.p[pos + 4] >> 6) != 3) return VCFC_E_FORMAT;
+        size_t ll = ((size_t)(f.p[pos] & 0x3F) << 24) | ((size_t)f.p[pos + 1] << 16) | ((size_t)f.p[pos + 2] << 8) | f.p[pos + 3];
+        if (ll + 4 > f.n - pos) return VCFC_E_TRUNC;
+        starts.push_back((unsigned long long)pos);
+        pos += 4 + ll;
+    }
+    const size_t n_lines = starts.size();
+    std::vector<long long> ends(n_lines);
+    std::vector<uint8_t> refs(n_lines), errs(n_lines);
+    // per-line fields on the device, in pieces of whole lines
+    const size_t piece = (size_t)512 << 20;
+    cudaStream_t st = ctx->stream;
+    for (size_t l0 = 0; l0 < n_lines;) {
+        size_t l1 = l0 + 1;
+        while (l1 < n_lines && starts[l1] - starts[l0] < piece) l1++;
+        const size_t b0 = (size_t)starts[l0], b1 = l1 < n_lines ? (size_t)starts[l1] : f.n, nl = l1 - l0;
+        vcfc::DevBuf &d_data = ctx->d_in[0], &d_ls = ctx->ws[3], &d_end = ctx->ws[4], &d_ref = ctx->ws[5], &d_err = ctx->ws[6];
+        if ((rc = vcfc::dev_reserve(ctx, &d_data, b1 - b0 + 16))) return rc;
+        if ((rc = vcfc::dev_reserve(ctx, &d_ls, nl * 8 + 8))) return rc;
+        if ((rc = vcfc::dev_reserve(ctx, &d_end, nl * 8 + 8))) return rc;
+        if ((rc = vcfc::dev_reserve(ctx, &d_ref, nl + 8))) return rc;
+        if ((rc = vcfc::dev_reserve(ctx, &d_err, nl + 8))) return rc;
+        std::vector<unsigned long long> rel(nl);
+        for (size_t k = 0; k < nl; k++) rel[k] = starts[l0 + k] - b0;
+        VCFC_CUDA(ctx, cudaMemcpyAsync(d_data.p, f.p + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+        VCFC_CUDA(ctx, cudaMemcpyAsync(d_ls.p, rel.data(), nl * 8, cudaMemcpyHostToDevice, st));
+        if ((rc = vcfc::index_line_ends(ctx, (const uint8_t*)d_data.p, b1 - b0, (const unsigned long long*)d_ls.p, nl, (long long*)d_end.p,
+                                        (uint8_t*)d_ref.p, (uint8_t*)d_err.p, st)))
+            return rc;
+        VCFC_CUDA(ctx, cudaMemcpyAsync(ends.data() + l0, d_end.p, nl * 8, cudaMemcpyDeviceToHost, st));
+        VCFC_CUDA(ctx, cudaMemcpyAsync(refs.data() + l0, d_ref.p, nl, cudaMemcpyDeviceToHost, st));
+        VCFC_CUDA(ctx, cudaMemcpyAsync(errs.data() + l0, d_err.p, nl, cudaMemcpyDeviceToHost, st));
+        VCFC_CUDA(ctx, cudaStreamSynchronize(st));
+        l0 = l1;
+    }
+    // the bin rule, and the entries
+    std::vector<uint8_t> out;
+    out.reserve(13 * (n_lines / entries_per_bin + 2));
+    size_t n_ent = 0;
+    uint32_t last_end = 0;
+    auto put = [&](uint8_t ref, uint32_t position, uint64_t offset) {
+        out.push_back(ref);
+        const uint8_t* a = reinterpret_cast<const uint8_t*>(&position);
+        out.insert(out.end(), a, a + 4);
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(&offset);
+        out.insert(out.end(), b, b + 8);
+    };
+    for (size_t k = 0; k < n_lines; k++) {
+        if (errs[k]) return errs[k] == 2 ? VCFC_E_TRUNC : VCFC_E_FORMAT;    // the reference throws at this line
+        const unsigned long e = (unsigned long)ends[k];
+        if (n_ent == 0) {
+            last_end = (uint32_t)e;
+            put(refs[k], last_end, starts[k]);
+            n_ent = 1;
+        } else if (e > (unsigned long)last_end) {
+            last_end = (uint32_t)e;
+            if (k % entries_per_bin == 0) { put(refs[k], last_end, starts[k]); n_ent++; }
+            else memcpy(out.data() + 13 * (n_ent - 1) + 1, &last_end, 4);
+        }
+    }
+    int fd = open(index_path, O_CREAT | O_TRUNC | O_WRONLY, 0644);
+    if (fd < 0) return VCFC_E_IO;
+    rc = write_all(fd, out.data(), out.size());
+    close(fd);
+    if (n_entries) *n_entries = n_ent;
+    return rc;
+}

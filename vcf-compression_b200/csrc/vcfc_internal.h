@@ -88,4 +88,9 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
                 uint8_t* d_out, size_t out_cap, vcfc_result* d_result, bool size_only,
                 cudaStream_t stream);
 
+// ---- per-line fields of the binned index (vcfc_index.cu): END position, chromosome index, error flag for every
+//      compressed line whose start offset is listed in d_line_start (offsets into d_in) ----
+int index_line_ends(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, const unsigned long long* d_line_start,
+                    unsigned long long n_lines, long long* d_end, uint8_t* d_ref, uint8_t* d_err, cudaStream_t stream);
+
 }  // namespace vcfc

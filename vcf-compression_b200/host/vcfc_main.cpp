@@ -3,6 +3,7 @@
 //     vcfc compress   IN.vcf  OUT.vcfc
 //     vcfc decompress IN.vcfc OUT.vcf
 //     vcfc query      IN.vcfc REF[:START-END]
+//     vcfc create-binned-index BIN_SIZE IN.vcfc          (writes IN.vcfc.vcfci, main.cpp:4097-4115)
 // Host C++ only; all coding work is done by libvcfc_gpu.so through its C ABI.  Where the
 // reference lets an exception escape (abort, exit 134) this prints the reason and exits 1.
 #include <stdio.h>
@@ -17,6 +18,7 @@
 static int usage() {
     fprintf(stderr,
             "usage: vcfc compress IN.vcf OUT.vcfc | decompress IN.vcfc OUT.vcf | query IN.vcfc REF[:START-END]\n"
+            "       vcfc create-binned-index BIN_SIZE IN.vcfc\n"
             "       env: VCFC_DEVICE (default 0), VCFC_CHUNK_MB (default 256)\n");
     return 1;
 }
@@ -24,13 +26,37 @@ static int usage() {
 int main(int argc, char** argv) {
     if (argc < 2) return usage();
     std::string action(argv[1]);
-    const char* verbs_elsewhere[] = {"gap-analysis", "sparsify", "sparse-query", "create-binned-index",
+    const char* verbs_elsewhere[] = {"gap-analysis", "sparsify", "sparse-query",
                                      "query-binned-index", "create-sparse-index", "query-sparse-index"};
     for (const char* v : verbs_elsewhere)
         if (action == v) {
             fprintf(stderr, "vcfc: verb '%s' is outside the GPU hot path; use the reference binary for it\n", v);
             return 2;
         }
+    if (action == "create-binned-index") {
+        if (argc != 4) {
+            printf("Usage: ./main create-binned-index <bin-size> <compressed-filename>\n");   // main.cpp:4098-4101
+            return 1;
+        }
+        char* endp = nullptr;
+        const unsigned long bin = strtoul(argv[2], &endp, 10);                               // str_to_uint64, utils.cpp:152-165
+        if (*endp != 0 || bin == 0) {
+            printf("bin size must be a positive integer\n");
+            return 1;
+        }
+        int dev = getenv("VCFC_DEVICE") ? atoi(getenv("VCFC_DEVICE")) : 0;
+        vcfc_ctx* ictx = nullptr;
+        int irc = vcfc_gpu_init(dev, &ictx);
+        if (irc != VCFC_OK) {
+            fprintf(stderr, "vcfc: cannot use CUDA device %d: %s (there is no CPU path)\n", dev, vcfc_strerror(irc));
+            return 1;
+        }
+        const std::string index_path = std::string(argv[3]) + ".vcfci";                       // VCFC_BINNING_INDEX_EXTENSION, utils.hpp:29
+        irc = vcfc_create_binned_index_file(ictx, argv[3], index_path.c_str(), bin, nullptr);
+        if (irc != VCFC_OK) fprintf(stderr, "vcfc create-binned-index: %s\n", vcfc_strerror(irc));
+        vcfc_gpu_destroy(ictx);
+        return irc == VCFC_OK ? 0 : 1;
+    }
     if (action != "compress" && action != "decompress" && action != "query") {
         printf("Unknown action name: %s\n", action.c_str());   // main.cpp:4181-4183
         return 0;
