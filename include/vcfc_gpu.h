@@ -127,6 +127,10 @@ int vcfc_query_file(vcfc_ctx *ctx, const char *in_path, const char *region, int 
  * into an END position on the GPU; the sequential bin rule runs on the host.  *n_entries (nullable) = entries written. */
 int vcfc_create_binned_index_file(vcfc_ctx *ctx, const char *vcfc_path, const char *index_path, uint64_t entries_per_bin,
                                   uint64_t *n_entries);
+/* query_binned_index_binarysearch(compressed, REF:START-END), src/main.cpp:2974-3350 (CLI verb query-binned-index,
+ * main.cpp:4117-4143): the index is <vcfc_path>.vcfci.  Lines whose [POS, END] overlaps the query, found from the index
+ * entry the reference's binary search ends on, are decoded on the GPU and written to out_fd. */
+int vcfc_query_binned_index_file(vcfc_ctx *ctx, const char *vcfc_path, const char *region, int out_fd);
 
 /* Instrumentation: device time (ms, CUDA events on the launch stream) of the kernels of the
  * most recent *_dev call when timing is enabled.  which: 0 = encode kernel, 1 = decode scan

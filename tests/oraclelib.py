@@ -107,3 +107,122 @@ def build_binned_index(vcfc: bytes, entries_per_bin: int):
     olen = C.c_size_t(0)
     rc = lib().vcfc_oracle_build_binned_index(vcfc, len(vcfc), entries_per_bin, out, cap, C.byref(olen))
     return rc, out.raw[:olen.value]
+
+
+# ---- indexed range query: pure-Python restatement (small cases only) of query_binned_index_binarysearch,
+#      /root/reference/src/main.cpp:2974-3350, with compare_to_range (main.cpp:108-140) and compute_end_position
+#      (main.cpp:763-852).  Pinned by tests/golden/index/QUERIES.json (outputs of the reference binary). ----
+_REFS = {**{str(i): i for i in range(1, 23)}, "X": 23, "Y": 24, "M": 25}
+
+
+def _strtoul_field(b: bytes):
+    """str_to_uint64 / str_to_long (utils.cpp:152-175): strtoul must consume the whole field; None on failure."""
+    import re
+    if b == b"":
+        return 0
+    m = re.fullmatch(rb"[ \t\n\v\f\r]*([+-]?)([0-9]+)", b)
+    if not m:
+        return None
+    v = min(int(m.group(2)), 2**64 - 1)
+    if m.group(1) == b"-" and v != 2**64 - 1:
+        v = (-v) % 2**64
+    return v - 2**64 if v >= 2**63 else v          # stored in a long
+
+
+def _kvp(info: bytes):
+    d = {}
+    for pair in info.split(b";"):
+        if not pair:
+            continue
+        parts = [x for x in pair.split(b"=") if x]
+        if len(parts) == 2:
+            d[parts[0]] = parts[1]
+        elif len(parts) == 1:
+            d[parts[0]] = b""
+        else:
+            raise ValueError("Invalid kvp format")
+    return d
+
+
+def end_position(pos: int, ref: bytes, alt: bytes, info: bytes) -> int:
+    if b"<" in alt:
+        kv = _kvp(info)
+        if b"END" in kv:
+            m = 0
+            for t in kv[b"END"].split(b","):
+                if t:
+                    v = _strtoul_field(t)
+                    if v is None:
+                        raise ValueError("END")
+                    m = max(m, v)
+            return abs(m)
+        if b"SVLEN" in kv:
+            m = 0
+            for t in kv[b"SVLEN"].split(b","):
+                if t:
+                    v = _strtoul_field(t)
+                    if v is None:
+                        raise ValueError("SVLEN")
+                    m = max(m, abs(v))
+            return pos + m - 1
+        return pos
+    longest = max((len(a) for a in alt.split(b",")), default=0)
+    return pos + max(len(ref), longest) - 1
+
+
+def query_binned_index(vcfc: bytes, index: bytes, region: str) -> bytes:
+    """Text the reference prints for `query-binned-index file REGION` (index entries of 13 bytes)."""
+    import struct
+    if ":" in region:
+        name, rng = region.split(":", 1)
+        a, b = rng.split("-", 1)
+        q_start, q_end = int(a), int(b)
+    else:
+        name, q_start, q_end = region, 0, 0
+    qidx = _REFS.get(name, 0)
+    sc = C.c_uint64(0)
+    hlen = lib().vcfc_oracle_parse_headers(vcfc, len(vcfc), C.byref(sc))
+    assert hlen >= 0 and len(index) % 13 == 0
+    count = len(index) // 13
+    if count == 0:
+        return b""
+    rd = lambda i: struct.unpack_from("<BIQ", index, 13 * i)
+    greater = lambda e: e[0] > qidx or (e[0] == qidx and e[1] > q_start)
+    less = lambda e: e[0] < qidx or (e[0] == qidx and e[1] < q_start)
+    lo, hi = 0, count - 1
+    mid = (lo + hi) // 2
+    entry = rd(0)                                   # (the reference's struct is uninitialised when count == 1)
+    while lo < hi:
+        mid = (lo + hi) // 2
+        entry = rd(mid)
+        if entry[0] == qidx and entry[1] == q_start:
+            break
+        if greater(entry):
+            if mid == 0:
+                break
+            hi = mid - 1
+        elif less(entry):
+            lo = mid + 1
+    if mid > 0 and greater(entry):
+        mid -= 1
+        entry = rd(mid)
+    pos, hits = entry[2], []
+    while len(vcfc) - pos >= 8:
+        ll = ((vcfc[pos] & 0x3F) << 24) | (vcfc[pos + 1] << 16) | (vcfc[pos + 2] << 8) | vcfc[pos + 3]
+        cols = vcfc[pos + 8: pos + 4 + ll].split(b"\t", 8)
+        lpos = _strtoul_field(cols[1])
+        info = cols[7] if b"<" in cols[4] else b""
+        lend = end_position(lpos, cols[3], cols[4], info)
+        lidx = _REFS.get(cols[0].decode("latin1"), 0)
+        if lidx < qidx or (lidx == qidx and (lend % 2**64) < q_start):
+            pass                                    # before the query
+        elif lidx > qidx or (lidx == qidx and lpos > q_end):
+            break                                   # behind it
+        else:
+            hits.append(vcfc[pos: pos + 4 + ll])
+        pos += 4 + ll
+    if not hits:
+        return b""
+    rc, txt, _, _ = decompress_block(b"".join(hits), sc.value)
+    assert rc == 0
+    return txt

@@ -368,7 +368,7 @@ def test_binned_index_matches_oracle_and_reference(codec, tmp_path):
     man = json.load(open(os.path.join(idir, "MANIFEST.json")))
     for fn, e in man.items():
         name = fn.split(".bin")[0]
-        vcfc = open(os.path.join(idir, name + ".vcfc"), "rb").read() if name == "sv_mix" else goldenlib.read(name + ".vcfc")
+        vcfc = open(os.path.join(idir, name + ".vcfc"), "rb").read() if name.startswith("sv_") else goldenlib.read(name + ".vcfc")
         ip, xp = str(tmp_path / "g.vcfc"), str(tmp_path / "g.vcfci")
         open(ip, "wb").write(vcfc)
         rc, n = codec.create_binned_index(ip, xp, e["entries_per_bin"])
@@ -396,6 +396,35 @@ def test_binned_index_matches_oracle_and_reference(codec, tmp_path):
     assert codec.create_binned_index(cp, cp + ".x", 10)[0] == pkg.E_FORMAT
     assert O.build_binned_index(bytes(bad), 10)[0] < 0
     assert codec.create_binned_index(str(tmp_path / "missing.vcfc"), cp + ".x", 10)[0] == pkg.E_IO
+
+
+def test_indexed_query_matches_reference_outputs(codec, tmp_path):
+    """vcfc_query_binned_index_file / `vcfc query-binned-index` against the outputs of the reference binary
+    (tests/golden/index/QUERIES.json): the index is built by this library first, then queried."""
+    import json
+    idir = os.path.join(goldenlib.GOLDEN, "index")
+    cases = json.load(open(os.path.join(idir, "QUERIES.json")))
+    built = {}
+    for key, e in sorted(cases.items()):
+        name, b, region = key.split("|")
+        cp = str(tmp_path / ("%s.%s.vcfc" % (name, b)))
+        if (name, b) not in built:
+            vcfc = open(os.path.join(idir, name + ".vcfc"), "rb").read() if name.startswith("sv_") else goldenlib.read(name + ".vcfc")
+            open(cp, "wb").write(vcfc)
+            assert codec.create_binned_index(cp, cp + ".vcfci", int(b))[0] == 0
+            built[(name, b)] = True
+        outp = str(tmp_path / "q.out")
+        fd = os.open(outp, os.O_CREAT | os.O_TRUNC | os.O_WRONLY, 0o644)
+        rc = codec.query_binned_index(cp, region, fd)
+        os.close(fd)
+        out = open(outp, "rb").read()
+        assert rc == 0 and hashlib.sha256(out).hexdigest() == e["sha256"], key
+    # the CLI verb, and the error paths
+    cp = str(tmp_path / "sv_sorted.4.vcfc")
+    r = subprocess.run([pkg.CLI_PATH, "query-binned-index", cp, "X:5000-9000"], capture_output=True)
+    assert r.returncode == 0 and hashlib.sha256(r.stdout).hexdigest() == cases["sv_sorted|4|X:5000-9000"]["sha256"]
+    assert codec.query_binned_index(cp, "X:5000", 1) == pkg.E_QUERY
+    assert codec.query_binned_index(str(tmp_path / "nope.vcfc"), "X:1-2", 1) == pkg.E_IO
 
 
 def test_live_reference_binary_if_shipped(codec, tmp_path):

@@ -169,7 +169,7 @@ def test_binned_index_golden():
     assert len(man) >= 12
     for fn, e in man.items():
         name = fn.split(".bin")[0]
-        vcfc = open(os.path.join(idir, name + ".vcfc"), "rb").read() if name == "sv_mix" else goldenlib.read(name + ".vcfc")
+        vcfc = open(os.path.join(idir, name + ".vcfc"), "rb").read() if name.startswith("sv_") else goldenlib.read(name + ".vcfc")
         rc, idx = O.build_binned_index(vcfc, e["entries_per_bin"])
         assert rc == e["entries"], fn
         assert idx == open(os.path.join(idir, fn), "rb").read(), fn
@@ -186,6 +186,22 @@ def test_binned_index_live_reference(tmp_path):
         assert subprocess.run([O.REF_BIN, "create-binned-index", str(b), op], capture_output=True).returncode == 0
         rc, idx = O.build_binned_index(vcfc, b)
         assert rc > 0 and idx == open(op + ".vcfci", "rb").read(), b
+
+
+def test_indexed_query_golden():
+    """The restatement of query_binned_index_binarysearch (tests/oraclelib.py) prints what the reference binary printed
+    for every committed (file, bin size, region) case: sorted and unsorted files, symbolic alleles, unknown chromosomes."""
+    idir = os.path.join(goldenlib.GOLDEN, "index")
+    cases = json.load(open(os.path.join(idir, "QUERIES.json")))
+    assert len(cases) >= 60
+    for key, e in cases.items():
+        name, b, region = key.split("|")
+        vcfc = open(os.path.join(idir, name + ".vcfc"), "rb").read() if name.startswith("sv_") else goldenlib.read(name + ".vcfc")
+        index = open(os.path.join(idir, "%s.bin%s.vcfci" % (name, b)), "rb").read()
+        out = O.query_binned_index(vcfc, index, region)
+        assert hashlib.sha256(out).hexdigest() == e["sha256"] and out.count(b"\n") == e["lines"], key
+        if e["file"]:
+            assert out == open(os.path.join(idir, e["file"]), "rb").read(), key
 
 
 def test_file_drivers(tmp_path):

@@ -69,6 +69,7 @@ def lib() -> C.CDLL:
         "vcfc_decompress_file": (i, [vp, C.c_char_p, C.c_char_p]),
         "vcfc_query_file": (i, [vp, C.c_char_p, C.c_char_p, i]),
         "vcfc_create_binned_index_file": (i, [vp, C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+        "vcfc_query_binned_index_file": (i, [vp, C.c_char_p, C.c_char_p, i]),
         "vcfc_set_timing": (i, [vp, i]),
         "vcfc_last_kernel_ms": (C.c_float, [vp, i]),
         "vcfc_launch_count": (u64, [vp]),
@@ -252,6 +253,10 @@ class Codec:
 
     def query(self, in_path: str, region: str, out_fd: int) -> int:
         return lib().vcfc_query_file(self._ctx, in_path.encode(), region.encode(), out_fd)
+
+    def query_binned_index(self, vcfc_path: str, region: str, out_fd: int) -> int:
+        """Indexed range query (query_binned_index_binarysearch, main.cpp:2974-3350); the index is vcfc_path + '.vcfci'."""
+        return lib().vcfc_query_binned_index_file(self._ctx, vcfc_path.encode(), region.encode(), out_fd)
 
     def create_binned_index(self, vcfc_path: str, index_path: str, entries_per_bin: int):
         """-> (rc, number of entries); writes the .vcfci file (create_binned_index4, main.cpp:1284-1637)."""

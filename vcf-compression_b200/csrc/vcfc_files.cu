@@ -7,6 +7,7 @@
 //   query_compressed_file()             src/main.cpp:3777-3929
 //   parse_coordinate_string()           src/main.cpp:3993-4026
 //   create_binned_index4()              src/main.cpp:1284-1637 (per-line fields on the GPU: vcfc_index.cu)
+//   query_binned_index_binarysearch()   src/main.cpp:2974-3350
 #include <errno.h>
 #include <fcntl.h>
 #include <stdlib.h>
@@ -16,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "vcfc_index.cuh"
 #include "vcfc_internal.h"
 
 namespace {
@@ -353,4 +355,100 @@ int vcfc_create_binned_index_file(vcfc_ctx* ctx, const char* vcfc_path, const ch
     close(fd);
     if (n_entries) *n_entries = n_ent;
     return rc;
+}
+
+// query-binned-index (main.cpp:4117-4143 -> query_binned_index_binarysearch, main.cpp:2974-3350): binary search of the
+// .vcfci entries for the query's chromosome index and start position, then a walk over the compressed lines from the
+// chosen entry's byte offset -- a line is printed when [POS, END] overlaps the query, the walk stops at the first line
+// behind it -- and ONE GPU decode of the lines that matched.  The search keeps the reference's exact steps (the entry
+// it ends on is the last one READ, not necessarily the one at the final bounds).  Differences: an index with a single
+// entry starts at that entry (the reference reads an uninitialised struct there), and the text is written as is
+// (the reference passes it to printf as the format string, so a '%' in a line would be mangled).
+int vcfc_query_binned_index_file(vcfc_ctx* ctx, const char* vcfc_path, const char* region, int out_fd) {
+    if (!ctx || !vcfc_path) return VCFC_E_ARG;
+    Query q;
+    int rc = parse_query(region, &q);
+    if (rc) return rc;
+    HostFile f, x;
+    if ((rc = f.load(vcfc_path))) return rc;
+    if ((rc = x.load((std::string(vcfc_path) + ".vcfci").c_str()))) return rc;
+    size_t hlen = 0;
+    uint64_t sc = 0;
+    if ((rc = vcfc_parse_headers(f.p, f.n, &hlen, &sc))) return rc;
+    const uint8_t qidx = vcfc::idx::ref_name_index((const uint8_t*)q.ref.data(), (int)q.ref.size());
+    if (x.n % 13 != 0) return VCFC_E_FORMAT;                             // "Index size was not a multiple of entry size"
+    const long count = (long)(x.n / 13);
+    if (count == 0) return VCFC_OK;
+    struct Entry { uint8_t ref; uint32_t position; uint64_t offset; };
+    auto read_entry = [&](long i) {
+        Entry e;
+        e.ref = x.p[13 * i];
+        memcpy(&e.position, x.p + 13 * i + 1, 4);
+        memcpy(&e.offset, x.p + 13 * i + 5, 8);
+        return e;
+    };
+    auto greater = [&](const Entry& e) { return e.ref > qidx || (e.ref == qidx && (uint64_t)e.position > q.start); };
+    auto less = [&](const Entry& e) { return e.ref < qidx || (e.ref == qidx && (uint64_t)e.position < q.start); };
+    long s_lo = 0, s_hi = count - 1, mid = (s_lo + s_hi) / 2;
+    Entry entry = read_entry(0);
+    while (s_lo < s_hi) {                                                // main.cpp:3040-3128
+        mid = (s_lo + s_hi) / 2;
+        entry = read_entry(mid);
+        if (entry.ref == qidx && (uint64_t)entry.position == q.start) break;
+        if (greater(entry)) {
+            if (mid == 0) break;
+            s_hi = mid - 1;
+        } else if (less(entry)) {
+            s_lo = mid + 1;
+        }
+    }
+    if (mid > 0 && greater(entry)) {                                     // main.cpp:3130-3152: one entry back
+        mid--;
+        entry = read_entry(mid);
+    }
+    const uint8_t* in = f.p;
+    std::vector<uint8_t> hits, out;
+    size_t pos = (size_t)entry.offset;
+    while (pos <= f.n && f.n - pos >= 8) {                               // main.cpp:3170-3330
+        if ((in[pos] >> 6) != 3 || (in[pos + 4] >> 6) != 3) return VCFC_E_FORMAT;
+        const size_t ll = ((size_t)(in[pos] & 0x3F) << 24) | ((size_t)in[pos + 1] << 16) | ((size_t)in[pos + 2] << 8) | in[pos + 3];
+        const uint8_t* fld[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        int fl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        size_t p = pos + 8;
+        int n_fields = 5;
+        for (int c = 0; c < n_fields; c++) {                             // read_to(..., '\t'): CHROM POS ID REF ALT [QUAL FILTER INFO]
+            size_t e = p;
+            while (e < f.n && in[e] != '\t') e++;
+            if (e >= f.n) return VCFC_E_TRUNC;
+            fld[c] = in + p; fl[c] = (int)(e - p);
+            p = e + 1;
+            if (c == 4) for (int i = 0; i < fl[4]; i++) if (fld[4][i] == '<') { n_fields = 8; break; }   // alt_is_structural
+        }
+        long long lpos = 0, lend = 0;
+        if (!vcfc::idx::parse_ul(fld[1], fl[1], &lpos)) return VCFC_E_FORMAT;
+        if (!vcfc::idx::line_end_position(lpos, fl[3], fld[4], fl[4], fld[7], fl[7], &lend)) return VCFC_E_FORMAT;
+        const uint8_t lidx = vcfc::idx::ref_name_index(fld[0], fl[0]);
+        // VcfCoordinateQuery::compare_to_range (main.cpp:108-140)
+        int cmp;
+        if (lidx < qidx || (lidx == qidx && (uint64_t)lend < q.start)) cmp = 1;            // the line lies before the query
+        else if (lidx > qidx || (lidx == qidx && (uint64_t)lpos > q.end)) cmp = -1;        // ... behind it
+        else cmp = 0;
+        if (cmp < 0) break;
+        if (cmp == 0) {
+            if (ll + 4 > f.n - pos) return VCFC_E_TRUNC;
+            hits.insert(hits.end(), in + pos, in + pos + 4 + ll);
+        }
+        pos += 4 + ll;
+    }
+    if (hits.empty()) return VCFC_OK;
+    size_t olen = 0, nl = 0, cap = std::max<size_t>(hits.size() * 12, (size_t)1 << 20);
+    uint64_t el = 0;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        out.resize(cap);
+        rc = vcfc_decode_block(ctx, hits.data(), hits.size(), sc, out.data(), cap, &olen, &nl, &el);
+        if (rc != VCFC_E_CAP) break;
+        cap *= 4;
+    }
+    const int w = write_all(out_fd, out.data(), olen);
+    return rc != VCFC_OK ? rc : w;
 }

@@ -4,6 +4,7 @@
 //     vcfc decompress IN.vcfc OUT.vcf
 //     vcfc query      IN.vcfc REF[:START-END]
 //     vcfc create-binned-index BIN_SIZE IN.vcfc          (writes IN.vcfc.vcfci, main.cpp:4097-4115)
+//     vcfc query-binned-index  IN.vcfc REF:START-END     (reads IN.vcfc.vcfci, main.cpp:4117-4143)
 // Host C++ only; all coding work is done by libvcfc_gpu.so through its C ABI.  Where the
 // reference lets an exception escape (abort, exit 134) this prints the reason and exits 1.
 #include <stdio.h>
@@ -18,7 +19,7 @@
 static int usage() {
     fprintf(stderr,
             "usage: vcfc compress IN.vcf OUT.vcfc | decompress IN.vcfc OUT.vcf | query IN.vcfc REF[:START-END]\n"
-            "       vcfc create-binned-index BIN_SIZE IN.vcfc\n"
+            "       vcfc create-binned-index BIN_SIZE IN.vcfc | query-binned-index IN.vcfc REF:START-END\n"
             "       env: VCFC_DEVICE (default 0), VCFC_CHUNK_MB (default 256)\n");
     return 1;
 }
@@ -26,8 +27,7 @@ static int usage() {
 int main(int argc, char** argv) {
     if (argc < 2) return usage();
     std::string action(argv[1]);
-    const char* verbs_elsewhere[] = {"gap-analysis", "sparsify", "sparse-query",
-                                     "query-binned-index", "create-sparse-index", "query-sparse-index"};
+    const char* verbs_elsewhere[] = {"gap-analysis", "sparsify", "sparse-query", "create-sparse-index", "query-sparse-index"};
     for (const char* v : verbs_elsewhere)
         if (action == v) {
             fprintf(stderr, "vcfc: verb '%s' is outside the GPU hot path; use the reference binary for it\n", v);
@@ -57,7 +57,7 @@ int main(int argc, char** argv) {
         vcfc_gpu_destroy(ictx);
         return irc == VCFC_OK ? 0 : 1;
     }
-    if (action != "compress" && action != "decompress" && action != "query") {
+    if (action != "compress" && action != "decompress" && action != "query" && action != "query-binned-index") {
         printf("Unknown action name: %s\n", action.c_str());   // main.cpp:4181-4183
         return 0;
     }
@@ -71,8 +71,9 @@ int main(int argc, char** argv) {
         fprintf(stderr, "vcfc: cannot use CUDA device %d: %s (there is no CPU path)\n", dev, vcfc_strerror(rc));
         return 1;
     }
-    if (action == "query") {
-        rc = vcfc_query_file(ctx, in, argv[3], STDOUT_FILENO);
+    if (action == "query" || action == "query-binned-index") {
+        rc = action == "query" ? vcfc_query_file(ctx, in, argv[3], STDOUT_FILENO)
+                               : vcfc_query_binned_index_file(ctx, in, argv[3], STDOUT_FILENO);
         if (rc == VCFC_E_QUERY) printf("Failed to parse query string: %s\n", argv[3]);   // main.cpp:4064-4067
     } else {
         if (strcmp(in, argv[3]) == 0) {
