@@ -410,6 +410,27 @@ static int end_position(long pos, size_t ref_len, const uint8_t *alt, size_t alt
     return 0;
 }
 
+/* Columns 1-8 of one line (in points at CHROM, i.e. just behind the two length headers; reading may run up to in + n):
+ * END position and chromosome index as create_binned_index4 computes them (main.cpp:1371-1423).  0, or a negative code
+ * where the reference throws. */
+int vcfc_oracle_line_index_fields(const uint8_t *in, size_t n, long *end_out, uint8_t *ref_out) {
+    const uint8_t *f[8];
+    size_t fl[8], q = 0;
+    int k;
+    long pos;
+    for (k = 0; k < 8; k++) {
+        size_t e = q;
+        while (e < n && in[e] != '\t') e++;
+        if (e >= n) return VCFC_E_TRUNC;
+        f[k] = in + q; fl[k] = e - q;
+        q = e + 1;
+    }
+    if (parse_ul_field(f[1], fl[1], &pos) != 0) return VCFC_E_FORMAT;
+    if (end_position(pos, fl[3], f[4], fl[4], f[7], fl[7], end_out) != 0) return VCFC_E_FORMAT;
+    *ref_out = ref_name_index(f[0], fl[0]);
+    return 0;
+}
+
 /*
  * Whole .vcfc file -> .vcfci bytes.  Walks the compressed lines by their length headers, reads only
  * columns 1-8 of each required section, and applies the bin rule of main.cpp:1430-1470: a line whose
@@ -428,24 +449,15 @@ long vcfc_oracle_build_binned_index(const uint8_t *in, size_t in_len, uint64_t e
     *out_len = 0;
     while (in_len - p >= 8) {                               /* fewer than 8 bytes left: EOF (compress.cpp:270-330) */
         int64_t ll = get_len_header(in + p), rq = get_len_header(in + p + 4);
-        const uint8_t *f[8];
-        size_t fl[8], q = p + 8, line_end;
-        int k;
-        long pos, endp;
+        size_t line_end;
+        long endp;
         uint8_t idx;
+        int frc;
         if (ll < 0 || rq < 0) return VCFC_E_FORMAT;
         line_end = p + 4 + (size_t)ll;
         if (line_end > in_len) return VCFC_E_TRUNC;
-        for (k = 0; k < 8; k++) {                           /* read_to(..., '\t') x 8 (main.cpp:1371-1405) */
-            size_t e = q;
-            while (e < in_len && in[e] != '\t') e++;
-            if (e >= in_len) return VCFC_E_TRUNC;
-            f[k] = in + q; fl[k] = e - q;
-            q = e + 1;
-        }
-        if (parse_ul_field(f[1], fl[1], &pos) != 0) return VCFC_E_FORMAT;
-        if (end_position(pos, fl[3], f[4], fl[4], f[7], fl[7], &endp) != 0) return VCFC_E_FORMAT;
-        idx = ref_name_index(f[0], fl[0]);
+        frc = vcfc_oracle_line_index_fields(in + p + 8, in_len - (p + 8), &endp, &idx);   /* read_to x 8 etc. (main.cpp:1371-1423) */
+        if (frc != 0) return frc;
         if (n_entries == 0) {
             if (cap < 13) return VCFC_E_CAP;
             out[0] = idx;

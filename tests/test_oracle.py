@@ -188,6 +188,45 @@ def test_binned_index_live_reference(tmp_path):
         assert rc > 0 and idx == open(op + ".vcfci", "rb").read(), b
 
 
+@pytest.mark.skipif(not O.have_ref_binary(), reason="oracle/_ref/main_release not built")
+def test_binned_index_fuzz_vs_reference_binary(tmp_path):
+    """Seeded random ALT / INFO / POS columns, including ones the reference throws on (bad integers, "a=b=c" pairs): the
+    oracle fails exactly when the reference aborts, and writes the same index bytes otherwise."""
+    import random
+    rng = random.Random(99)
+    alts = ["C", "G,T", "ACGTT,A", "<DEL>", "<DUP>", "<INS:ME:ALU>", "<CN0>,<CN2>", "A,<DEL>", ""]
+    infos = ["AC=1", "SVTYPE=DEL;END=%d", "END=%d,%d", "SVLEN=-%d", "SVLEN=%d,-%d;END", "END=", "END", "SVLEN=;X=1", ";;AC=2;",
+             "END=12x", "SVLEN=abc", "A=B=C", "=", "END= 77", "END=+%d", "END=-5", "DB;H2;END=%d", "END=%d;END=%d"]
+    n_fail = n_ok = 0
+    for case in range(60):
+        risky = case % 3 == 0
+        lines, pos = [], 1000
+        for i in range(rng.randrange(1, 30)):
+            pos += rng.randrange(1, 900)
+            info = rng.choice(infos if risky else infos[:9] + infos[13:])
+            info = info.replace("%d", "{}").format(*[pos + rng.randrange(5000) for _ in range(info.count("%d"))])
+            pos_s = str(pos) if not (risky and rng.random() < 0.05) else rng.choice(["12a", "", " 7", "-3"])
+            lines.append("%s\t%s\trs%d\t%s\t%s\t9\tPASS\t%s\tGT\t0|0\t0|1\n" % (
+                rng.choice(["1", "2", "X", "chrUn"]), pos_s, i, rng.choice(["A", "ACGT", "ACGTACGTAC"]), rng.choice(alts), info))
+        vcf = vcfgen.header(2) + "".join(lines).encode()
+        ip, op = str(tmp_path / "a.vcf"), str(tmp_path / "a.vcfc")
+        open(ip, "wb").write(vcf)
+        assert subprocess.run([O.REF_BIN, "compress", ip, op], capture_output=True).returncode == 0
+        vcfc = open(op, "rb").read()
+        b = rng.choice([1, 2, 5, 100])
+        if os.path.exists(op + ".vcfci"):
+            os.remove(op + ".vcfci")
+        r = subprocess.run([O.REF_BIN, "create-binned-index", str(b), op], capture_output=True)
+        rc, idx = O.build_binned_index(vcfc, b)
+        if r.returncode != 0:
+            assert rc < 0, (case, rc)
+            n_fail += 1
+        else:
+            assert rc >= 0 and idx == open(op + ".vcfci", "rb").read(), case
+            n_ok += 1
+    assert n_ok >= 30 and n_fail >= 3
+
+
 def test_indexed_query_golden():
     """The restatement of query_binned_index_binarysearch (tests/oraclelib.py) prints what the reference binary printed
     for every committed (file, bin size, region) case: sorted and unsorted files, symbolic alleles, unknown chromosomes."""
