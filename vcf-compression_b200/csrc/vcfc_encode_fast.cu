@@ -674,7 +674,8 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         ctx->launches++;
         return VCFC_OK;
     }
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};                    // per device: function attributes belong to the device's context
+    bool& attr_set = attr_set_dev[ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0];
     if (!attr_set) {
         VCFC_CUDA(ctx, cudaFuncSetAttribute(k_encode_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
         attr_set = true;
