@@ -51,7 +51,9 @@ typedef struct vcfc_result {
     uint64_t err_line;
 } vcfc_result;
 
-/* Context: one per (process, GPU).  Owns workspace, pinned staging and two streams. */
+/* Context: one per (process, GPU).  Owns workspace, pinned staging and two streams.
+ * Threading: a context is used by ONE thread at a time (the library keeps no process-global mutable state, so
+ * different contexts -- also several on the same device -- may be driven from different threads concurrently). */
 int  vcfc_gpu_init(int device, vcfc_ctx **ctx);
 void vcfc_gpu_destroy(vcfc_ctx *ctx);
 const char *vcfc_strerror(int code);
@@ -119,6 +121,12 @@ int vcfc_parse_headers(const uint8_t *buf, size_t len, size_t *header_len, uint6
 int vcfc_compress_file(vcfc_ctx *ctx, const char *in_path, const char *out_path);
 /* decompress2_fd(in, out), src/compress.cpp:1214-1257 */
 int vcfc_decompress_file(vcfc_ctx *ctx, const char *in_path, const char *out_path);
+/* The same two verbs over SEVERAL contexts (normally one per GPU of the box; SURVEY.md 8(e), no reference counterpart):
+ * the file is cut into newline-aligned (compress) / line-header-aligned (decompress) chunks, every context takes chunks
+ * in file order on its own thread, and the host concatenates the chunk outputs by their out_len running sum -- no
+ * collective.  The output file is byte-identical to the single-context call.  ctxs[0] also owns the pinned buffers. */
+int vcfc_compress_file_multi(vcfc_ctx **ctxs, int n_ctx, const char *in_path, const char *out_path);
+int vcfc_decompress_file_multi(vcfc_ctx **ctxs, int n_ctx, const char *in_path, const char *out_path);
 /* query_compressed_file(in, REF:START-END) -> matching lines to out_fd, src/main.cpp:3777-3929 */
 int vcfc_query_file(vcfc_ctx *ctx, const char *in_path, const char *region, int out_fd);
 /* create_binned_index4(compressed, index, entries_per_bin), src/main.cpp:1284-1637 (CLI verb create-binned-index,

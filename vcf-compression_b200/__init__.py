@@ -67,6 +67,8 @@ def lib() -> C.CDLL:
         "vcfc_parse_headers": (i, [vp, sz, szp, u64p]),
         "vcfc_compress_file": (i, [vp, C.c_char_p, C.c_char_p]),
         "vcfc_decompress_file": (i, [vp, C.c_char_p, C.c_char_p]),
+        "vcfc_compress_file_multi": (i, [C.POINTER(vp), i, C.c_char_p, C.c_char_p]),
+        "vcfc_decompress_file_multi": (i, [C.POINTER(vp), i, C.c_char_p, C.c_char_p]),
         "vcfc_query_file": (i, [vp, C.c_char_p, C.c_char_p, i]),
         "vcfc_create_binned_index_file": (i, [vp, C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]),
         "vcfc_query_binned_index_file": (i, [vp, C.c_char_p, C.c_char_p, i]),
@@ -250,6 +252,17 @@ class Codec:
 
     def decompress2_fd(self, in_path: str, out_path: str) -> int:
         return lib().vcfc_decompress_file(self._ctx, in_path.encode(), out_path.encode())
+
+    @staticmethod
+    def compress_multi(codecs, in_path: str, out_path: str) -> int:
+        """compress() over several contexts (one worker thread per context, host concatenation by chunk offsets)."""
+        arr = (C.c_void_p * len(codecs))(*[c._ctx for c in codecs])
+        return lib().vcfc_compress_file_multi(arr, len(codecs), in_path.encode(), out_path.encode())
+
+    @staticmethod
+    def decompress_multi(codecs, in_path: str, out_path: str) -> int:
+        arr = (C.c_void_p * len(codecs))(*[c._ctx for c in codecs])
+        return lib().vcfc_decompress_file_multi(arr, len(codecs), in_path.encode(), out_path.encode())
 
     def query(self, in_path: str, region: str, out_fd: int) -> int:
         return lib().vcfc_query_file(self._ctx, in_path.encode(), region.encode(), out_fd)

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libvcfc_gpu.so")
 CLI = os.path.join(HERE, "vcfc")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-CU = ["vcfc_api.cu", "vcfc_files.cu", "vcfc_generic.cu", "vcfc_encode_fast.cu", "vcfc_decode_fast.cu", "vcfc_index.cu"]
+CU = ["vcfc_api.cu", "vcfc_files.cu", "vcfc_generic.cu", "vcfc_encode_fast.cu", "vcfc_decode_fast.cu", "vcfc_index.cu", "vcfc_pipeline.cu"]
 FLAGS = (["-DVCFC_DEBUG"] if os.environ.get("VCFC_DEBUG") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
 
@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
         for cmd, p in procs:
             if p.wait() != 0:
                 raise RuntimeError("nvcc failed: " + " ".join(cmd))
-        subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-cudart", "static"])
+        subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-cudart", "static", "-Xcompiler", "-pthread", "-lpthread"])
     main = os.path.join(HERE, "host", "vcfc_main.cpp")
     if os.path.exists(main) and (force or _stale(CLI, [main, LIB])):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), main,

@@ -82,9 +82,10 @@ void vcfc_gpu_destroy(vcfc_ctx* ctx) {
     for (int i = 0; i < 2; i++) {
         if (ctx->d_in[i].p) cudaFree(ctx->d_in[i].p);
         if (ctx->d_out[i].p) cudaFree(ctx->d_out[i].p);
-        if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
         if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
     }
+    for (auto& b : ctx->pin_free) if (b.p) cudaFreeHost(b.p);
+    ctx->pin_free.clear();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
     if (ctx->d_result) cudaFree(ctx->d_result);

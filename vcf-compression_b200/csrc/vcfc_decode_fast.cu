@@ -941,12 +941,10 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
         ctx->launches++;
         return VCFC_OK;
     }
-    static bool attr_set_dev[64] = {false};                    // per device: function attributes belong to the device's context
-    bool& attr_set = attr_set_dev[ctx->device >= 0 && ctx->device < 64 ? ctx->device : 0];
-    if (!attr_set) {
+    if (!ctx->dec_attr_set) {                                  // per context (= per device)
         VCFC_CUDA(ctx, cudaFuncSetAttribute(k_dec_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
         VCFC_CUDA(ctx, cudaFuncSetAttribute(k_dec_expand_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemG)));
-        attr_set = true;
+        ctx->dec_attr_set = 1;
     }
     int rc;
     const long long n = (long long)in_len, n_seg = (n + kSeg - 1) / kSeg;

@@ -130,91 +130,7 @@ int vcfc_parse_headers(const uint8_t* in, size_t in_len, size_t* header_len, uin
     return VCFC_OK;
 }
 
-int vcfc_compress_file(vcfc_ctx* ctx, const char* in_path, const char* out_path) {
-    if (!ctx || !in_path || !out_path) return VCFC_E_ARG;
-    HostFile f;
-    int rc = f.load(in_path);
-    if (rc) return rc;
-    int ofd = open(out_path, O_CREAT | O_TRUNC | O_WRONLY, 0644);
-    if (ofd < 0) return VCFC_E_IO;
-    std::vector<uint8_t> out;
-    size_t pos = 0;
-    const uint8_t* in = f.p;
-    while (pos < f.n && rc == VCFC_OK) {
-        if (in[pos] == '\n') { pos++; continue; }                       // compress.cpp:219-221
-        if (in[pos] == '#') {                                           // compress.cpp:222-238
-            const uint8_t* e = (const uint8_t*)memchr(in + pos, '\n', f.n - pos);
-            size_t len = e ? (size_t)(e - (in + pos)) : f.n - pos;
-            rc = write_all(ofd, in + pos, len);
-            if (rc == VCFC_OK) rc = write_all(ofd, (const uint8_t*)"\n", 1);
-            pos += len + 1;
-            continue;
-        }
-        // data region: up to the next line that starts with '#'
-        size_t end = f.n;
-        for (size_t s = pos;;) {
-            const uint8_t* h = (const uint8_t*)memmem(in + s, f.n - s, "\n#", 2);
-            if (!h) break;
-            end = (size_t)(h - in) + 1;
-            break;
-        }
-        size_t len = end - pos, olen = 0, nl = 0;
-        uint64_t el = 0;
-        size_t cap = vcfc_encode_bound(len);
-        out.resize(cap);
-        rc = vcfc_encode_block(ctx, in + pos, len, out.data(), cap, &olen, nullptr, 0, &nl, &el);
-        int wrc = write_all(ofd, out.data(), olen);                     // lines before a bad one stand
-        if (rc == VCFC_OK) rc = wrc;
-        pos = end;
-    }
-    close(ofd);
-    return rc;
-}
-
-int vcfc_decompress_file(vcfc_ctx* ctx, const char* in_path, const char* out_path) {
-    if (!ctx || !in_path || !out_path) return VCFC_E_ARG;
-    HostFile f;
-    int rc = f.load(in_path);
-    if (rc) return rc;
-    int ofd = open(out_path, O_CREAT | O_TRUNC | O_WRONLY, 0644);       // the reference truncates first (compress.cpp:1217)
-    if (ofd < 0) return VCFC_E_IO;
-    size_t hlen = 0;
-    uint64_t sc = 0;
-    rc = vcfc_parse_headers(f.p, f.n, &hlen, &sc);
-    if (rc) { close(ofd); return rc; }
-    rc = write_all(ofd, f.p, hlen);
-    // decoded size: required bytes pass through, a token byte expands to at most 127 * 4 bytes
-    const uint8_t* in = f.p + hlen;
-    size_t len = f.n - hlen, pos = 0;
-    std::vector<uint8_t> out;
-    const size_t piece = (size_t)64 << 20;
-    while (rc == VCFC_OK && len - pos >= 8) {
-        // take whole lines up to `piece` compressed bytes per call
-        size_t end = pos;
-        while (len - end >= 8 && (in[end] >> 6) == 3) {
-            size_t ll = ((size_t)(in[end] & 0x3F) << 24) | ((size_t)in[end + 1] << 16) | ((size_t)in[end + 2] << 8) | in[end + 3];
-            if (ll + 4 > len - end) { end = len; break; }
-            if (end + 4 + ll - pos > piece && end > pos) break;
-            end += 4 + ll;
-        }
-        if (end == pos || len - end < 8) end = len;
-        // exact output size from the per-line sample count: every sample is >= 2 bytes; use the device's count
-        size_t olen = 0, nl = 0;
-        uint64_t el = 0;
-        size_t cap = std::max<size_t>((end - pos) * 12, (size_t)1 << 20);
-        for (int attempt = 0; attempt < 8; attempt++) {
-            out.resize(cap);
-            rc = vcfc_decode_block(ctx, in + pos, end - pos, sc, out.data(), cap, &olen, &nl, &el);
-            if (rc != VCFC_E_CAP) break;
-            cap *= 4;
-        }
-        int wrc = write_all(ofd, out.data(), olen);
-        if (rc == VCFC_OK) rc = wrc;
-        pos = end;
-    }
-    close(ofd);
-    return rc;
-}
+// vcfc_compress_file / vcfc_decompress_file: the pinned, threaded file pipeline in vcfc_pipeline.cu.
 
 int vcfc_query_file(vcfc_ctx* ctx, const char* in_path, const char* region, int out_fd) {
     if (!ctx || !in_path) return VCFC_E_ARG;
@@ -245,8 +161,7 @@ int vcfc_query_file(vcfc_ctx* ctx, const char* in_path, const char* region, int 
         return r != VCFC_OK ? r : w;
     };
     while (pos < f.n) {                                                 // main.cpp:3799-3924
-        if (f.n - pos < 4) return VCFC_E_TRUNC;                          // "Only read %d bytes, expected 4"
-        if (f.n - pos < 8) return VCFC_E_TRUNC;
+        if (f.n - pos < 8) { rc = flush(); return rc ? rc : VCFC_E_TRUNC; }   // "Only read %d bytes, expected 4": hits so far were printed
         if ((in[pos] >> 6) != 3) { flush(); return VCFC_E_FORMAT; }
         size_t ll = ((size_t)(in[pos] & 0x3F) << 24) | ((size_t)in[pos + 1] << 16) | ((size_t)in[pos + 2] << 8) | in[pos + 3];
         size_t p = pos + 8;

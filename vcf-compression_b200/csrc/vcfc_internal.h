@@ -7,6 +7,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "../../include/vcfc_gpu.h"
 
 namespace vcfc {
@@ -33,9 +36,14 @@ struct vcfc_ctx {
     vcfc::DevBuf ws[12];
     // device staging for the host-pointer API
     vcfc::DevBuf d_in[2], d_out[2];
-    // pinned host staging (file drivers / pageable callers)
-    void*  h_pin[2]   = {nullptr, nullptr};
-    size_t h_pin_cap[2] = {0, 0};
+    // pinned host buffers of the file pipeline (vcfc_pipeline.cu): a pool that survives across calls
+    struct PinBuf { uint8_t* p; size_t cap; };
+    std::mutex          pin_mu;
+    std::vector<PinBuf> pin_free;
+    // launch configuration of the cooperative encoder, per context (= per device)
+    int          enc_attr_set = 0;
+    int          enc_resident = 0;
+    int          dec_attr_set = 0;
     vcfc_result* h_result = nullptr;      // pinned
     vcfc_result* d_result = nullptr;
     // instrumentation

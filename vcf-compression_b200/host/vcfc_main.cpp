@@ -13,6 +13,7 @@
 #include <unistd.h>
 
 #include <string>
+#include <vector>
 
 #include "vcfc_gpu.h"
 
@@ -20,7 +21,8 @@ static int usage() {
     fprintf(stderr,
             "usage: vcfc compress IN.vcf OUT.vcfc | decompress IN.vcfc OUT.vcf | query IN.vcfc REF[:START-END]\n"
             "       vcfc create-binned-index BIN_SIZE IN.vcfc | query-binned-index IN.vcfc REF:START-END\n"
-            "       env: VCFC_DEVICE (default 0), VCFC_CHUNK_MB (default 256)\n");
+            "       env: VCFC_DEVICE (default 0), VCFC_GPUS (compress / decompress over that many GPUs starting at VCFC_DEVICE,\n"
+            "            default 1, \"all\" = every GPU of the box), VCFC_FILE_CHUNK_MB (default 64)\n");
     return 1;
 }
 
@@ -81,7 +83,19 @@ int main(int argc, char** argv) {
             vcfc_gpu_destroy(ctx);
             return 1;
         }
-        rc = action == "compress" ? vcfc_compress_file(ctx, in, argv[3]) : vcfc_decompress_file(ctx, in, argv[3]);
+        // one context per GPU: line-block chunks are handed out in file order, outputs concatenated by offsets
+        std::vector<vcfc_ctx*> ctxs{ctx};
+        const char* g = getenv("VCFC_GPUS");
+        int want = 1;
+        if (g && *g) want = strcmp(g, "all") == 0 ? 1 << 20 : atoi(g);
+        for (int d = dev + 1; (int)ctxs.size() < want; d++) {
+            vcfc_ctx* c = nullptr;
+            if (vcfc_gpu_init(d, &c) != VCFC_OK) break;              // fewer GPUs than asked for: use what is there
+            ctxs.push_back(c);
+        }
+        rc = action == "compress" ? vcfc_compress_file_multi(ctxs.data(), (int)ctxs.size(), in, argv[3])
+                                  : vcfc_decompress_file_multi(ctxs.data(), (int)ctxs.size(), in, argv[3]);
+        for (size_t k = 1; k < ctxs.size(); k++) vcfc_gpu_destroy(ctxs[k]);
     }
     if (rc != VCFC_OK) {
         fprintf(stderr, "vcfc %s: %s", action.c_str(), vcfc_strerror(rc));
