@@ -20,7 +20,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libvcfc_gpu.so")
+LIB_PATH = os.environ.get("VCFC_LIB_PATH") or os.path.join(HERE, "libvcfc_gpu.so")   # (override: tuning builds)
 CLI_PATH = os.path.join(HERE, "vcfc")
 HEADER = os.path.join(ROOT, "include", "vcfc_gpu.h")
 
