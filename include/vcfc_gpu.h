@@ -127,6 +127,13 @@ int vcfc_decompress_file(vcfc_ctx *ctx, const char *in_path, const char *out_pat
  * collective.  The output file is byte-identical to the single-context call.  ctxs[0] also owns the pinned buffers. */
 int vcfc_compress_file_multi(vcfc_ctx **ctxs, int n_ctx, const char *in_path, const char *out_path);
 int vcfc_decompress_file_multi(vcfc_ctx **ctxs, int n_ctx, const char *in_path, const char *out_path);
+/* compress() and create_binned_index4() (main.cpp:1284-1637) in ONE pass: the index's per-line fields (END position,
+ * chromosome index) are computed from the encoder's own line offsets while each compressed chunk is still on the device;
+ * nothing is re-read.  Writes out_path exactly as vcfc_compress_file does and index_path exactly as
+ * vcfc_create_binned_index_file(out_path, ...) would.  If the index cannot be built (the reference's builder throws: bad
+ * header region, malformed POS / INFO, '#' line behind a data line) the compressed file stands and the code says why. */
+int vcfc_compress_index_file_multi(vcfc_ctx **ctxs, int n_ctx, const char *in_path, const char *out_path,
+                                   const char *index_path, uint64_t entries_per_bin, uint64_t *n_entries);
 /* query_compressed_file(in, REF:START-END) -> matching lines to out_fd, src/main.cpp:3777-3929 */
 int vcfc_query_file(vcfc_ctx *ctx, const char *in_path, const char *region, int out_fd);
 /* create_binned_index4(compressed, index, entries_per_bin), src/main.cpp:1284-1637 (CLI verb create-binned-index,

@@ -128,3 +128,44 @@ def test_cli_over_two_contexts_env(tmp_path, golden):
     assert open(op, "rb").read() == g["vcfc"]
     assert subprocess.run([pkg.CLI_PATH, "decompress", op, rp], env=env).returncode == 0
     assert open(rp, "rb").read() == g["rt"]
+
+
+def test_fused_index_equals_the_separate_pass_and_the_oracle(codecs, tmp_path, monkeypatch):
+    """compress + create-binned-index in one pass (index fields from the encoder's own line offsets, chunk by chunk, any
+    number of contexts) writes the bytes of create_binned_index4 (main.cpp:1284-1637) on the finished file."""
+    monkeypatch.setenv("VCFC_FILE_CHUNK_MB", "1")
+    h, d = vcfgen.kg_like(3000, 500, seed=41)                       # ~6 MB: several chunks
+    vp, cp = str(tmp_path / "k.vcf"), str(tmp_path / "k.vcfc")
+    open(vp, "wb").write(h + d)
+    orc, want = O.compress_vcf(h + d)
+    assert orc == 0
+    for n_ctx in (1, 3):
+        for b in (1, 7, 1000):
+            rc, n = pkg.Codec.compress_index_multi(codecs[:n_ctx], vp, cp, cp + ".vcfci", b)
+            assert rc == 0 and open(cp, "rb").read() == want
+            on, oidx = O.build_binned_index(want, b)
+            assert n == on and open(cp + ".vcfci", "rb").read() == oidx, (n_ctx, b)
+            rc2, n2 = codecs[0].create_binned_index(cp, cp + ".sep", b)
+            assert rc2 == 0 and n2 == n and open(cp + ".sep", "rb").read() == oidx
+    # structural variants (INFO END / SVLEN decide the END position): the committed fixture of the reference binary
+    import json
+    import goldenlib
+    idir = os.path.join(goldenlib.GOLDEN, "index")
+    man = json.load(open(os.path.join(idir, "MANIFEST.json")))
+    for fn, e in man.items():
+        name = fn.split(".bin")[0]
+        if name.startswith("sv_") or not goldenlib.exists(name + ".vcf"):
+            continue
+        open(vp, "wb").write(goldenlib.read(name + ".vcf"))
+        rc, n = pkg.Codec.compress_index_multi(codecs[:2], vp, cp, cp + ".vcfci", e["entries_per_bin"])
+        assert rc == 0 and n == e["entries"], fn
+        assert open(cp + ".vcfci", "rb").read() == open(os.path.join(idir, fn), "rb").read(), fn
+    # a '#' line behind a data line: the compressed file stands, the index is refused (the reference's walk fails there)
+    open(vp, "wb").write(h + d[:200000].rsplit(b"\n", 1)[0] + b"\n##late\n" + d[:5000].rsplit(b"\n", 1)[0] + b"\n")
+    rc, _ = pkg.Codec.compress_index_multi(codecs[:1], vp, cp, cp + ".bad", 10)
+    assert rc == pkg.E_FORMAT and open(cp, "rb").read() == O.compress_vcf(open(vp, "rb").read())[1]
+    # the CLI: VCFC_INDEX_BIN
+    open(vp, "wb").write(h + d)
+    env = dict(os.environ, VCFC_INDEX_BIN="7")
+    assert subprocess.run([pkg.CLI_PATH, "compress", vp, cp], env=env).returncode == 0
+    assert open(cp + ".vcfci", "rb").read() == O.build_binned_index(want, 7)[1]

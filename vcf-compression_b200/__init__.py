@@ -69,6 +69,7 @@ def lib() -> C.CDLL:
         "vcfc_decompress_file": (i, [vp, C.c_char_p, C.c_char_p]),
         "vcfc_compress_file_multi": (i, [C.POINTER(vp), i, C.c_char_p, C.c_char_p]),
         "vcfc_decompress_file_multi": (i, [C.POINTER(vp), i, C.c_char_p, C.c_char_p]),
+        "vcfc_compress_index_file_multi": (i, [C.POINTER(vp), i, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]),
         "vcfc_query_file": (i, [vp, C.c_char_p, C.c_char_p, i]),
         "vcfc_create_binned_index_file": (i, [vp, C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]),
         "vcfc_query_binned_index_file": (i, [vp, C.c_char_p, C.c_char_p, i]),
@@ -258,6 +259,15 @@ class Codec:
         """compress() over several contexts (one worker thread per context, host concatenation by chunk offsets)."""
         arr = (C.c_void_p * len(codecs))(*[c._ctx for c in codecs])
         return lib().vcfc_compress_file_multi(arr, len(codecs), in_path.encode(), out_path.encode())
+
+    @staticmethod
+    def compress_index_multi(codecs, in_path: str, out_path: str, index_path: str, entries_per_bin: int):
+        """compress() + create_binned_index4() in one pass -> (rc, number of index entries)."""
+        arr = (C.c_void_p * len(codecs))(*[c._ctx for c in codecs])
+        n = C.c_uint64(0)
+        rc = lib().vcfc_compress_index_file_multi(arr, len(codecs), in_path.encode(), out_path.encode(), index_path.encode(),
+                                                  entries_per_bin, C.byref(n))
+        return rc, n.value
 
     @staticmethod
     def decompress_multi(codecs, in_path: str, out_path: str) -> int:

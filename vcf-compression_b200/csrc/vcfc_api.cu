@@ -79,6 +79,7 @@ void vcfc_gpu_destroy(vcfc_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto& b : ctx->ws) if (b.p) cudaFree(b.p);
+    for (auto& b : ctx->ix) if (b.p) cudaFree(b.p);
     for (int i = 0; i < 2; i++) {
         if (ctx->d_in[i].p) cudaFree(ctx->d_in[i].p);
         if (ctx->d_out[i].p) cudaFree(ctx->d_out[i].p);
@@ -224,6 +225,13 @@ static size_t text_chunk_end(const uint8_t* in, size_t pos, size_t in_len, size_
 
 int vcfc_encode_block(vcfc_ctx* ctx, const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len,
                       uint64_t* line_out_offsets, size_t line_cap, size_t* n_lines, uint64_t* err_line) {
+    return vcfc::encode_block_host(ctx, in, in_len, out, out_cap, out_len, line_out_offsets, line_cap, n_lines, err_line, nullptr);
+}
+
+}  // extern "C"
+
+int vcfc::encode_block_host(vcfc_ctx* ctx, const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len,
+                            uint64_t* line_out_offsets, size_t line_cap, size_t* n_lines, uint64_t* err_line, LineIndexOut* idx) {
     if (!ctx || (in_len && (!in || !out)) || !out_len) return VCFC_E_ARG;
     VCFC_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t chunk = env_size("VCFC_CHUNK_MB", 256) << 20;
@@ -250,6 +258,23 @@ int vcfc_encode_block(vcfc_ctx* ctx, const uint8_t* in, size_t in_len, uint8_t* 
             VCFC_CUDA(ctx, cudaStreamSynchronize(st));
             for (size_t k = 0; k < nl; k++) dst[k] += o;
         }
+        if (idx && r.n_lines) {
+            // the binned index's per-line fields, from the encoder's own line offsets, while the chunk is on the device
+            const size_t nl = (size_t)r.n_lines, per = d_lo->cap / 16, b0 = idx->ends.size();
+            const unsigned long long* d_offs = (const unsigned long long*)d_lo->p + (size_t)s * per;
+            long long* d_end = (long long*)ctx->ix[0].p + (size_t)s * per;
+            uint8_t* d_ref = (uint8_t*)ctx->ix[1].p + (size_t)s * per;
+            uint8_t* d_err = (uint8_t*)ctx->ix[2].p + (size_t)s * per;
+            int irc = index_line_ends(ctx, (const uint8_t*)ctx->d_out[s].p, (size_t)r.out_len, d_offs, nl, d_end, d_ref, d_err, st);
+            if (irc) return irc;
+            idx->offs.resize(b0 + nl); idx->ends.resize(b0 + nl); idx->refs.resize(b0 + nl); idx->errs.resize(b0 + nl);
+            VCFC_CUDA(ctx, cudaMemcpyAsync(idx->offs.data() + b0, d_offs, nl * 8, cudaMemcpyDeviceToHost, st));
+            VCFC_CUDA(ctx, cudaMemcpyAsync(idx->ends.data() + b0, d_end, nl * 8, cudaMemcpyDeviceToHost, st));
+            VCFC_CUDA(ctx, cudaMemcpyAsync(idx->refs.data() + b0, d_ref, nl, cudaMemcpyDeviceToHost, st));
+            VCFC_CUDA(ctx, cudaMemcpyAsync(idx->errs.data() + b0, d_err, nl, cudaMemcpyDeviceToHost, st));
+            VCFC_CUDA(ctx, cudaStreamSynchronize(st));
+            for (size_t k = 0; k < nl; k++) idx->offs[b0 + k] += o;
+        }
         if (r.status != VCFC_OK) { status = r.status; eline = lines + r.err_line; }
         o += r.out_len;
         lines += r.n_lines;
@@ -257,9 +282,16 @@ int vcfc_encode_block(vcfc_ctx* ctx, const uint8_t* in, size_t in_len, uint8_t* 
     };
 
     int rc = VCFC_OK, i = 0;
-    if (line_out_offsets && line_cap) {
+    const bool want_offs = (line_out_offsets && line_cap) || idx;
+    if (want_offs) {
         size_t per = std::min(chunk, std::max<size_t>(in_len, 1)) / 18 + 2;
         if ((rc = dev_reserve(ctx, d_lo, 2 * per * 8 + 32))) return rc;
+        if (idx) {
+            const size_t per_cap = d_lo->cap / 16;
+            if ((rc = dev_reserve(ctx, &ctx->ix[0], 2 * per_cap * 8 + 32))) return rc;
+            if ((rc = dev_reserve(ctx, &ctx->ix[1], 2 * per_cap + 32))) return rc;
+            if ((rc = dev_reserve(ctx, &ctx->ix[2], 2 * per_cap + 32))) return rc;
+        }
     }
     while (pos < in_len && status == VCFC_OK) {
         int s = i & 1;
@@ -275,7 +307,7 @@ int vcfc_encode_block(vcfc_ctx* ctx, const uint8_t* in, size_t in_len, uint8_t* 
         }
         uint64_t* d_offs = nullptr;
         size_t cap_s = 0;
-        if (line_out_offsets && line_cap) {
+        if (want_offs) {
             cap_s = d_lo->cap / 16;
             d_offs = (uint64_t*)d_lo->p + (size_t)s * cap_s;
         }
@@ -297,6 +329,8 @@ int vcfc_encode_block(vcfc_ctx* ctx, const uint8_t* in, size_t in_len, uint8_t* 
     if (err_line) *err_line = eline;
     return rc != VCFC_OK ? rc : status;
 }
+
+extern "C" {
 
 int vcfc_decode_block(vcfc_ctx* ctx, const uint8_t* in, size_t in_len, uint64_t sample_count, uint8_t* out,
                       size_t out_cap, size_t* out_len, size_t* n_lines, uint64_t* err_line) {

@@ -11,6 +11,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <stdlib.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -22,27 +23,23 @@
 
 namespace {
 
-struct HostFile {
+struct HostFile {                 // the file mapped read-only: a range query touches only the pages it walks over
     uint8_t* p = nullptr;
     size_t   n = 0;
-    ~HostFile() { free(p); }
+    ~HostFile() { if (p && n) munmap(p, n); }
     int load(const char* path) {
         int fd = open(path, O_RDONLY);
         if (fd < 0) return VCFC_E_IO;
         struct stat st;
         if (fstat(fd, &st) != 0) { close(fd); return VCFC_E_IO; }
         n = (size_t)st.st_size;
-        p = (uint8_t*)malloc(n + 1);
-        if (!p) { close(fd); return VCFC_E_IO; }
-        size_t got = 0;
-        while (got < n) {
-            ssize_t r = read(fd, p + got, n - got);
-            if (r < 0 && errno == EINTR) continue;
-            if (r <= 0) break;
-            got += (size_t)r;
+        if (n) {
+            void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) { close(fd); p = nullptr; n = 0; return VCFC_E_IO; }
+            p = (uint8_t*)m;
         }
         close(fd);
-        return got == n ? VCFC_OK : VCFC_E_IO;
+        return VCFC_OK;
     }
 };
 

@@ -36,6 +36,7 @@ struct vcfc_ctx {
     vcfc::DevBuf ws[12];
     // device staging for the host-pointer API
     vcfc::DevBuf d_in[2], d_out[2];
+    vcfc::DevBuf ix[3];                   // per-line index fields of the fused compress + index pass (END, chromosome, error)
     // pinned host buffers of the file pipeline (vcfc_pipeline.cu): a pool that survives across calls
     struct PinBuf { uint8_t* p; size_t cap; };
     std::mutex          pin_mu;
@@ -95,6 +96,17 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
 int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t sample_count,
                 uint8_t* d_out, size_t out_cap, vcfc_result* d_result, bool size_only,
                 cudaStream_t stream);
+
+// ---- host-pointer block encode with the per-line fields of the binned index taken from the encoder's own line offsets
+//      while the compressed chunk is still on the device (vcfc_api.cu); vcfc_encode_block is this with idx = nullptr ----
+struct LineIndexOut {
+    std::vector<uint64_t>  offs;     // offset of every encoded line in `out`
+    std::vector<long long> ends;     // END position (compute_end_position, main.cpp:763-852)
+    std::vector<uint8_t>   refs;     // chromosome index (utils.hpp:90-103)
+    std::vector<uint8_t>   errs;     // 0 ok, 1 malformed columns (the reference's index builder throws), 2 truncated
+};
+int encode_block_host(vcfc_ctx* ctx, const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* out_len,
+                      uint64_t* line_out_offsets, size_t line_cap, size_t* n_lines, uint64_t* err_line, LineIndexOut* idx);
 
 // ---- per-line fields of the binned index (vcfc_index.cu): END position, chromosome index, error flag for every
 //      compressed line whose start offset is listed in d_line_start (offsets into d_in) ----

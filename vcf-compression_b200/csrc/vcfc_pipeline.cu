@@ -135,6 +135,10 @@ struct Chunk {
     size_t  out_len = 0, out_off = 0;
     int     rc = VCFC_OK;
     bool    last = false;         // decode: the splitter saw the end of the file
+    // fused index (encode with P.want_index): per-line fields of this chunk's data lines, offsets relative to the chunk's output
+    LineIndexOut* idx = nullptr;
+    size_t  n_hash = 0;           // '#' lines in the chunk
+    bool    hash_after_data = false;
 };
 
 struct Pipe {
@@ -144,6 +148,7 @@ struct Pipe {
     int         ifd = -1, ofd = -1;
     size_t      file_len = 0;
     bool        encode = true;
+    bool        want_index = false;       // encode: also collect the binned index's per-line fields
     uint64_t    sample_count = 0;         // decode
     size_t      data_off = 0;             // decode: first byte after the header region
     size_t      chunk_bytes = 0, slack = 0;
@@ -185,6 +190,11 @@ static void encode_chunk(Pipe& P, vcfc_ctx* ctx, Chunk& c) {
         if (!c.out.p) { c.rc = VCFC_E_CUDA; return; }
         size_t pos = c.begin, o = 0;
         int rc = VCFC_OK;
+        if (P.want_index) {
+            if (!c.idx) c.idx = new LineIndexOut();
+            c.idx->offs.clear(); c.idx->ends.clear(); c.idx->refs.clear(); c.idx->errs.clear();
+            c.n_hash = 0; c.hash_after_data = false;
+        }
         while (pos < c.end && rc == VCFC_OK) {
             size_t h = pos;                                         // next line that starts with '#'
             for (;;) {
@@ -197,8 +207,10 @@ static void encode_chunk(Pipe& P, vcfc_ctx* ctx, Chunk& c) {
             if (h > pos) {
                 size_t olen = 0, nl = 0;
                 uint64_t el = 0;
-                rc = vcfc_encode_block(ctx, p + pos, h - pos, c.out.p + o, c.out.cap - o, &olen, nullptr, 0, &nl, &el);
+                const size_t i0 = c.idx ? c.idx->offs.size() : 0;
+                rc = encode_block_host(ctx, p + pos, h - pos, c.out.p + o, c.out.cap - o, &olen, nullptr, 0, &nl, &el, c.idx);
                 if (rc == VCFC_E_CAP) break;
+                if (c.idx) for (size_t k = i0; k < c.idx->offs.size(); k++) c.idx->offs[k] += o;
                 o += olen;                                          // lines before a bad one stand
                 if (rc != VCFC_OK) break;
             }
@@ -206,6 +218,8 @@ static void encode_chunk(Pipe& P, vcfc_ctx* ctx, Chunk& c) {
                 const uint8_t* e = (const uint8_t*)memchr(p + h, '\n', c.end - h);
                 const size_t ll = e ? (size_t)(e - (p + h)) : c.end - h;
                 if ((rc = hash_line_ok(p + h, ll))) break;
+                c.n_hash++;
+                if (c.idx && !c.idx->offs.empty()) c.hash_after_data = true;
                 if (o + ll + 1 > c.out.cap) { rc = VCFC_E_CAP; break; }
                 memcpy(c.out.p + o, p + h, ll);
                 c.out.p[o + ll] = '\n';
@@ -452,6 +466,43 @@ static int run(Pipe& P, int n_readers, int n_writers) {
     return P.rc;
 }
 
+// create_binned_index4's entries (main.cpp:1430-1470, 600-626) from the per-line fields the chunks collected while they were
+// encoded: a line whose number is a multiple of entries_per_bin opens an entry if its END exceeds the last entry's position,
+// any other line can only grow that position.  Byte offsets are positions in the output file.
+static int build_index(Pipe& P, uint64_t entries_per_bin, std::vector<uint8_t>& out, uint64_t* n_entries) {
+    size_t n_ent = 0, k = 0;
+    uint32_t last_end = 0;
+    bool seen_data = false;
+    for (auto& c : P.chunks) {
+        if (c.n_hash && (seen_data || c.hash_after_data)) return VCFC_E_FORMAT;   // a '#' line behind a data line: the reference's walk fails there
+        if (!c.idx) continue;
+        const LineIndexOut& li = *c.idx;
+        for (size_t i = 0; i < li.offs.size(); i++, k++) {
+            seen_data = true;
+            if (li.errs[i]) return li.errs[i] == 2 ? VCFC_E_TRUNC : VCFC_E_FORMAT;
+            const unsigned long e = (unsigned long)li.ends[i];
+            const uint64_t off = (uint64_t)(c.out_off + li.offs[i]);
+            bool open_entry = false;
+            if (n_ent == 0) { last_end = (uint32_t)e; open_entry = true; }
+            else if (e > (unsigned long)last_end) {
+                last_end = (uint32_t)e;
+                if (k % entries_per_bin == 0) open_entry = true;
+                else memcpy(out.data() + 13 * (n_ent - 1) + 1, &last_end, 4);
+            }
+            if (open_entry) {
+                const size_t b = out.size();
+                out.resize(b + 13);
+                out[b] = li.refs[i];
+                memcpy(out.data() + b + 1, &last_end, 4);
+                memcpy(out.data() + b + 5, &off, 8);
+                n_ent++;
+            }
+        }
+    }
+    if (n_entries) *n_entries = n_ent;
+    return VCFC_OK;
+}
+
 static int n_threads_default(const char* env, int dflt) {
     return (int)std::max<size_t>(1, env_sz(env, (size_t)dflt));
 }
@@ -464,16 +515,18 @@ using namespace vcfc::pipe;
 
 extern "C" {
 
-int vcfc_compress_file_multi(vcfc_ctx** ctxs, int n_ctx, const char* in_path, const char* out_path) {
-    if (!ctxs || n_ctx <= 0 || !ctxs[0] || !in_path || !out_path) return VCFC_E_ARG;
+static int compress_file_impl(vcfc_ctx** ctxs, int n_ctx, const char* in_path, const char* out_path, const char* index_path,
+                              uint64_t entries_per_bin, uint64_t* n_entries) {
+    if (!ctxs || n_ctx <= 0 || !ctxs[0] || !in_path || !out_path || (index_path && entries_per_bin == 0)) return VCFC_E_ARG;
+    if (n_entries) *n_entries = 0;
     Pipe P;
-    P.ctxs = ctxs; P.n_ctx = n_ctx; P.lead = ctxs[0]; P.encode = true;
+    P.ctxs = ctxs; P.n_ctx = n_ctx; P.lead = ctxs[0]; P.encode = true; P.want_index = index_path != nullptr;
     P.ifd = open(in_path, O_RDONLY);
     if (P.ifd < 0) return VCFC_E_IO;
     struct stat st;
     if (fstat(P.ifd, &st) != 0) { close(P.ifd); return VCFC_E_IO; }
     P.file_len = (size_t)st.st_size;
-    P.ofd = open(out_path, O_CREAT | O_TRUNC | O_WRONLY, 0644);
+    P.ofd = open(out_path, O_CREAT | O_TRUNC | (index_path ? O_RDWR : O_WRONLY), 0644);
     if (P.ofd < 0) { close(P.ifd); return VCFC_E_IO; }
     const int hw = (int)std::max(2u, std::thread::hardware_concurrency());
     const int n_readers = n_threads_default("VCFC_READERS", std::min(8, std::max(2, hw / 2)));
@@ -491,10 +544,39 @@ int vcfc_compress_file_multi(vcfc_ctx** ctxs, int n_ctx, const char* in_path, co
     cudaSetDevice(P.lead->device);
     int rc = P.n_chunks ? run(P, n_readers, n_writers) : VCFC_OK;
     if (ftruncate(P.ofd, (off_t)(P.out_base + P.out_total)) != 0 && rc == VCFC_OK) rc = VCFC_E_IO;
+    if (index_path && rc == VCFC_OK) {
+        // what create_binned_index4 checks before its walk: the header region of the compressed file (main.cpp:1304)
+        std::vector<uint8_t> head(std::min<size_t>(P.out_total, (size_t)64 << 20));
+        size_t got = 0, hlen = 0;
+        uint64_t sc = 0;
+        rc = pread_all(P.ofd, head.data(), head.size(), 0, &got);
+        if (rc == VCFC_OK) rc = vcfc_parse_headers(head.data(), got, &hlen, &sc);
+        std::vector<uint8_t> entries;
+        if (rc == VCFC_OK) rc = build_index(P, entries_per_bin, entries, n_entries);
+        if (rc == VCFC_OK) {
+            int xfd = open(index_path, O_CREAT | O_TRUNC | O_WRONLY, 0644);
+            if (xfd < 0) rc = VCFC_E_IO;
+            else {
+                rc = pwrite_all(xfd, entries.data(), entries.size(), 0);
+                if (close(xfd) != 0 && rc == VCFC_OK) rc = VCFC_E_IO;
+            }
+        }
+    }
+    for (auto& c : P.chunks) { delete c.idx; c.idx = nullptr; }
     close(P.ifd);
     if (close(P.ofd) != 0 && rc == VCFC_OK) rc = VCFC_E_IO;
     pin_trim(P.lead, env_sz("VCFC_PIN_KEEP_MB", 4096) << 20);
     return rc;
+}
+
+int vcfc_compress_file_multi(vcfc_ctx** ctxs, int n_ctx, const char* in_path, const char* out_path) {
+    return compress_file_impl(ctxs, n_ctx, in_path, out_path, nullptr, 0, nullptr);
+}
+
+int vcfc_compress_index_file_multi(vcfc_ctx** ctxs, int n_ctx, const char* in_path, const char* out_path, const char* index_path,
+                                   uint64_t entries_per_bin, uint64_t* n_entries) {
+    if (!index_path) return VCFC_E_ARG;
+    return compress_file_impl(ctxs, n_ctx, in_path, out_path, index_path, entries_per_bin, n_entries);
 }
 
 int vcfc_decompress_file_multi(vcfc_ctx** ctxs, int n_ctx, const char* in_path, const char* out_path) {

@@ -22,7 +22,8 @@ static int usage() {
             "usage: vcfc compress IN.vcf OUT.vcfc | decompress IN.vcfc OUT.vcf | query IN.vcfc REF[:START-END]\n"
             "       vcfc create-binned-index BIN_SIZE IN.vcfc | query-binned-index IN.vcfc REF:START-END\n"
             "       env: VCFC_DEVICE (default 0), VCFC_GPUS (compress / decompress over that many GPUs starting at VCFC_DEVICE,\n"
-            "            default 1, \"all\" = every GPU of the box), VCFC_FILE_CHUNK_MB (default 64)\n");
+            "            default 1, \"all\" = every GPU of the box), VCFC_FILE_CHUNK_MB (default 64),\n"
+            "            VCFC_INDEX_BIN=N (compress also writes OUT.vcfci with N lines per bin, in the same pass)\n");
     return 1;
 }
 
@@ -93,8 +94,14 @@ int main(int argc, char** argv) {
             if (vcfc_gpu_init(d, &c) != VCFC_OK) break;              // fewer GPUs than asked for: use what is there
             ctxs.push_back(c);
         }
-        rc = action == "compress" ? vcfc_compress_file_multi(ctxs.data(), (int)ctxs.size(), in, argv[3])
-                                  : vcfc_decompress_file_multi(ctxs.data(), (int)ctxs.size(), in, argv[3]);
+        const char* xb = getenv("VCFC_INDEX_BIN");                 // compress + create-binned-index in one pass: OUT.vcfci beside OUT
+        if (action == "compress" && xb && atol(xb) > 0) {
+            const std::string index_path = std::string(argv[3]) + ".vcfci";
+            rc = vcfc_compress_index_file_multi(ctxs.data(), (int)ctxs.size(), in, argv[3], index_path.c_str(), (uint64_t)atol(xb), nullptr);
+        } else {
+            rc = action == "compress" ? vcfc_compress_file_multi(ctxs.data(), (int)ctxs.size(), in, argv[3])
+                                      : vcfc_decompress_file_multi(ctxs.data(), (int)ctxs.size(), in, argv[3]);
+        }
         for (size_t k = 1; k < ctxs.size(); k++) vcfc_gpu_destroy(ctxs[k]);
     }
     if (rc != VCFC_OK) {
