@@ -164,6 +164,138 @@ def host_sample(kind, n_lines, n_samples, seed):
     return bytes(b.cpu().numpy())
 
 
+
+# ------------------------------------------------------------------------------------------------
+# file -> file: the verbs a user of the reference runs (compress IN OUT / decompress IN OUT), on tmpfs
+# ------------------------------------------------------------------------------------------------
+def _best(fn, n=3):
+    ts = []
+    for _ in range(n):
+        t = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t)
+    return min(ts)
+
+
+def file_bench(pkg, codec, d_in, starts, n_lines, header: bytes, samples: int):
+    """e2e_file: vcfc_compress_file / vcfc_decompress_file (pinned chunk ring, reader / worker / writer threads) and the
+    `vcfc` CLI on a bounded prefix of the workload written to tmpfs, beside the reference CLI on a smaller prefix."""
+    import shutil
+    import oraclelib as O
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    wd = tempfile.mkdtemp(prefix="vcfc_file_", dir=shm)
+    res = {"tmpfs": shm}
+    try:
+        free = shutil.disk_usage(shm).free
+        target = min(float(starts[n_lines]), 4e9, free * 0.25)
+        k = int((starts[:n_lines + 1] <= target).sum().item()) - 1
+        k = max(1, k)
+        nbytes = int(starts[k])
+        ip, op, rp = (os.path.join(wd, x) for x in ("in.vcf", "out.vcfc", "rt.vcf"))
+        with open(ip, "wb") as f:
+            f.write(header)
+            step = 256 << 20
+            for a in range(0, nbytes, step):
+                f.write(d_in[a:min(nbytes, a + step)].cpu().numpy().tobytes())
+        fbytes = os.path.getsize(ip)
+        res["file_bytes"] = fbytes
+        res["lines"] = k
+        rc = codec.compress(ip, op)                      # warm-up: pinned pool, device buffers
+        if rc != 0:
+            raise RuntimeError(f"compress rc {rc}")
+        tc = _best(lambda: codec.compress(ip, op), 3)
+        codec.decompress2_fd(op, rp)
+        td = _best(lambda: codec.decompress2_fd(op, rp), 2)
+        same = subprocess.run(["cmp", "-s", ip, rp]).returncode == 0
+        res["lib"] = {"api": "vcfc_compress_file / vcfc_decompress_file (context warm)", "compress_gbs": fbytes / tc / 1e9,
+                      "decompress_gbs": fbytes / td / 1e9, "round_trip_identical": bool(same),
+                      "vcfc_bytes": os.path.getsize(op)}
+        if os.path.exists(pkg.CLI_PATH):
+            op2, rp2 = os.path.join(wd, "cli.vcfc"), os.path.join(wd, "cli.vcf")
+            t = time.perf_counter()
+            r1 = subprocess.run([pkg.CLI_PATH, "compress", ip, op2], capture_output=True)
+            tcc = time.perf_counter() - t
+            t = time.perf_counter()
+            r2 = subprocess.run([pkg.CLI_PATH, "decompress", op2, rp2], capture_output=True)
+            tdc = time.perf_counter() - t
+            ok = r1.returncode == 0 and r2.returncode == 0 and subprocess.run(["cmp", "-s", op, op2]).returncode == 0
+            res["cli"] = {"cmd": "vcfc compress / decompress (one process each: includes CUDA context creation and pinned allocation)",
+                          "compress_gbs": fbytes / tcc / 1e9, "decompress_gbs": fbytes / tdc / 1e9, "compress_s": tcc,
+                          "decompress_s": tdc, "same_bytes_as_lib": bool(ok)}
+            for x in (op2, rp2):
+                if os.path.exists(x):
+                    os.remove(x)
+        if O.have_ref_binary():
+            kr = max(1, int((starts[:n_lines + 1] <= 150e6).sum().item()) - 1)
+            nb = int(starts[kr])
+            ipr, opr, rpr = (os.path.join(wd, x) for x in ("ref.vcf", "ref.vcfc", "ref.rt"))
+            with open(ipr, "wb") as f:
+                f.write(header)
+                f.write(d_in[:nb].cpu().numpy().tobytes())
+            t = time.perf_counter()
+            a = subprocess.run([O.REF_BIN, "compress", ipr, opr], capture_output=True).returncode
+            trc = time.perf_counter() - t
+            t = time.perf_counter()
+            b = subprocess.run([O.REF_BIN, "decompress", opr, rpr], capture_output=True).returncode
+            trd = time.perf_counter() - t
+            if a == 0 and b == 0:
+                fb = os.path.getsize(ipr)
+                res["reference_cli"] = {"cmd": "oracle/_ref/main_release compress / decompress (one process, one core)",
+                                        "sample_bytes": fb, "compress_gbs": fb / trc / 1e9, "decompress_gbs": fb / trd / 1e9}
+    except Exception as e:  # noqa: BLE001
+        res["error"] = str(e)[:200]
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+    return res
+
+
+def index_query_bench(pkg, codec, dev):
+    """The next rows of the scope table on the configuration BASELINE.md quotes them on (config 1 shape: 10k x 2504,
+    random_vcf.py distribution): binned index build (separate pass and fused with compress), indexed range query, linear
+    query -- library calls with a warm context, the `vcfc` CLI, and the reference binary on the same files."""
+    import shutil
+    import oraclelib as O
+    import vcfsynth
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    wd = tempfile.mkdtemp(prefix="vcfc_idx_", dir=shm)
+    res = {"workload": "random_vcf.py distribution, 10000 lines x 2504 samples (config 1 shape), bin size 150, query 1:12000-14000"}
+    try:
+        d, _ = vcfsynth.generate("random", 10000, 2504, seed=5, device=dev)
+        vcf = vcfsynth.header(2504) + d.cpu().numpy().tobytes()
+        ip, op = os.path.join(wd, "c1.vcf"), os.path.join(wd, "c1.vcfc")
+        open(ip, "wb").write(vcf)
+        null = os.open(os.devnull, os.O_WRONLY)
+        codec.compress(ip, op)
+        t_c = _best(lambda: codec.compress(ip, op))
+        t_ci = _best(lambda: pkg.Codec.compress_index_multi([codec], ip, op, op + ".vcfci", 150))
+        fused = open(op + ".vcfci", "rb").read()
+        t_i = _best(lambda: codec.create_binned_index(op, op + ".vcfci", 150))
+        same = fused == open(op + ".vcfci", "rb").read()
+        t_qi = _best(lambda: codec.query_binned_index(op, "1:12000-14000", null))
+        t_q = _best(lambda: codec.query(op, "1:12000-14000", null))
+        res["lib"] = {"compress_s": t_c, "compress_plus_index_fused_s": t_ci, "index_fused_extra_s": max(0.0, t_ci - t_c),
+                      "create_binned_index_s": t_i, "fused_index_same_bytes": bool(same),
+                      "query_binned_index_s": t_qi, "query_s": t_q, "note": "library calls, context warm, files on tmpfs"}
+        if os.path.exists(pkg.CLI_PATH):
+            def cli(*a):
+                return _best(lambda: subprocess.run([pkg.CLI_PATH, *a], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL), 2)
+            res["cli"] = {"create_binned_index_s": cli("create-binned-index", "150", op), "query_binned_index_s": cli("query-binned-index", op, "1:12000-14000"),
+                          "query_s": cli("query", op, "1:12000-14000"), "note": "one process per verb: includes CUDA context creation (~0.3-0.5 s)"}
+        if O.have_ref_binary():
+            def ref(*a):
+                return _best(lambda: subprocess.run([O.REF_BIN, *a], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL), 2)
+            shutil.copy(op, op + ".ref")
+            res["reference_cli"] = {"create_binned_index_s": ref("create-binned-index", "150", op + ".ref"),
+                                    "query_binned_index_s": ref("query-binned-index", op + ".ref", "1:12000-14000"),
+                                    "query_s": ref("query", op + ".ref", "1:12000-14000"),
+                                    "index_same_bytes": open(op + ".ref.vcfci", "rb").read() == fused if os.path.exists(op + ".ref.vcfci") else None}
+        os.close(null)
+    except Exception as e:  # noqa: BLE001
+        res["error"] = str(e)[:200]
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+    return res
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -402,6 +534,34 @@ def main():
                           "api": "vcfc_encode_block (host pointers, pinned; chunked H2D/kernels/D2H on two streams)",
                           "bytes_match_device_run": bool(ok),
                           "workload_note": "full workload" if e2e_in == n_in else f"first {e2e_in} bytes (host RAM bound)"}
+            # what plain copies of the same bytes cost on this box with all ranks copying at once (H2D of the text and D2H
+            # of the .vcfc on two streams, pinned memory): the ceiling the end-to-end number is to be read against
+            try:
+                d_c = torch.empty(e2e_out + 64, dtype=torch.uint8, device=dev)
+                h_c = torch.empty(e2e_out + 64, dtype=torch.uint8, pin_memory=True)
+                s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+
+                def copies():
+                    with torch.cuda.stream(s_a):
+                        d_buf[:e2e_in].copy_(h_in, non_blocking=True)
+                    with torch.cuda.stream(s_b):
+                        h_c[:e2e_out].copy_(d_c[:e2e_out], non_blocking=True)
+                    s_a.synchronize()
+                    s_b.synchronize()
+
+                copies()
+                barrier()
+                t1 = time.perf_counter()
+                for _ in range(3):
+                    copies()
+                ct = max_over_ranks((time.perf_counter() - t1) / 3)
+                barrier()
+                ceil_v = sum_over_ranks(float(e2e_in)) / ct / 1e9
+                out["e2e"]["copy_ceiling"] = {"value": ceil_v, "unit": UNIT, "what": "pinned H2D of the input + D2H of the output bytes only, "
+                                              "all ranks at once, two streams", "frac": out["e2e"]["value"] / ceil_v}
+                del d_c, h_c
+            except Exception as e:  # noqa: BLE001
+                out["e2e"]["copy_ceiling"] = {"error": str(e)[:120]}
             if not args.no_decode:
                 h_txt = torch.empty(e2e_in + 64, dtype=torch.uint8, pin_memory=True)
                 dres = None
@@ -427,6 +587,13 @@ def main():
             del h_in, h_out
         except RuntimeError as e:
             out["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(e)[:200]}
+
+    # ---- file -> file and the index / query rows: N = 1 only ----
+    if world == 1 and not args.no_e2e:
+        out["e2e_file"] = file_bench(pkg, codec, d_in, starts, args.lines, vcfsynth.header(args.samples), args.samples)
+        if "lib" in out["e2e_file"] and out.get("e2e", {}).get("value"):
+            out["e2e_file"]["lib_vs_block_e2e"] = out["e2e_file"]["lib"]["compress_gbs"] / out["e2e"]["value"]
+        out["index_query"] = index_query_bench(pkg, codec, dev)
 
     # ---- CPU baseline beside it: rank 0, N = 1 only, bounded sample ----
     if world == 1 and not args.no_cpu:

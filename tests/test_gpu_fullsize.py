@@ -112,3 +112,33 @@ def test_config4_range_query(codec, tmp_path):
     rp = str(tmp_path / "a.rt")
     assert codec.decompress2_fd(op, rp) == 0
     assert open(rp, "rb").read() == vcf
+
+
+def test_config1_exact_file(codec, tmp_path):
+    """BASELINE.json configs[0] / SURVEY.md 7 step 4: the reference generator's exact 10k x 2504 file (tests/config1gen.py,
+    input sha256 c7c9e4e3...) through the file drivers: the compressed file has the sha256 the unmodified reference binary
+    produced (580246c9...), the round trip is the input, `query 1:12000-14000` prints the 1001 lines of the
+    window, and the index / indexed query agree with the oracle."""
+    import hashlib
+    import config1gen
+    vcf = config1gen.generate()
+    assert hashlib.sha256(vcf).hexdigest() == config1gen.INPUT_SHA256
+    ip, op, rp = (str(tmp_path / x) for x in ("c1.vcf", "c1.vcfc", "c1.rt"))
+    open(ip, "wb").write(vcf)
+    rc, n_ent = pkg.Codec.compress_index_multi([codec], ip, op, op + ".vcfci", 150)
+    assert rc == 0
+    vcfc = open(op, "rb").read()
+    assert len(vcfc) == config1gen.VCFC_LEN and hashlib.sha256(vcfc).hexdigest() == config1gen.VCFC_SHA256
+    assert codec.decompress2_fd(op, rp) == 0
+    assert hashlib.sha256(open(rp, "rb").read()).hexdigest() == config1gen.INPUT_SHA256
+    lines = vcf[vcf.index(b"\n1\t") + 1:].split(b"\n")[:-1]
+    want = b"".join(l + b"\n" for l in lines if 12000 <= int(l.split(b"\t", 2)[1]) <= 14000)
+    assert want.count(b"\n") == 1001
+    for verb in (codec.query, codec.query_binned_index):
+        outp = str(tmp_path / "q.out")
+        fd = os.open(outp, os.O_CREAT | os.O_TRUNC | os.O_WRONLY, 0o644)
+        assert verb(op, "1:12000-14000", fd) == 0
+        os.close(fd)
+        assert open(outp, "rb").read() == want
+    on, oidx = O.build_binned_index(vcfc, 150)
+    assert n_ent == on and open(op + ".vcfci", "rb").read() == oidx

@@ -251,3 +251,19 @@ def test_file_drivers(tmp_path):
     assert open(op, "rb").read() == O.compress_vcf(h + d)[1]
     assert O.lib().vcfc_oracle_decompress_file(op.encode(), rp.encode()) == 0
     assert open(rp, "rb").read() == h + d
+
+
+def test_config1_exact_file_pins_the_oracle():
+    """BASELINE.json configs[0]: the reference generator's 10k x 2504 file (restated in tests/config1gen.py; its sha256
+    is the one recorded from the reference's own script) compresses to the sha256 the unmodified reference binary wrote
+    (BASELINE.md), and round-trips."""
+    import config1gen
+    vcf = config1gen.generate()
+    assert len(vcf) == config1gen.INPUT_LEN and hashlib.sha256(vcf).hexdigest() == config1gen.INPUT_SHA256
+    hl = vcf.index(b"\n1\t") + 1
+    rc, enc, nl, _ = O.compress_block(vcf[hl:])
+    out = vcf[:hl] + enc
+    assert rc == 0 and nl == 10000 and len(out) == config1gen.VCFC_LEN
+    assert hashlib.sha256(out).hexdigest() == config1gen.VCFC_SHA256
+    rc, txt = O.decompress_vcfc(out)
+    assert rc == 0 and txt == vcf

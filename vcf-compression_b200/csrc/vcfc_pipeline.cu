@@ -17,6 +17,7 @@
 #include <fcntl.h>
 #include <sched.h>
 #include <stdlib.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -136,6 +137,7 @@ struct Chunk {
     int     rc = VCFC_OK;
     bool    last = false;         // decode: the splitter saw the end of the file
     // fused index (encode with P.want_index): per-line fields of this chunk's data lines, offsets relative to the chunk's output
+    std::vector<size_t>* hash = nullptr;   // encode: offsets (in `in`) of the lines that start with '#', found by the reader
     LineIndexOut* idx = nullptr;
     size_t  n_hash = 0;           // '#' lines in the chunk
     bool    hash_after_data = false;
@@ -153,6 +155,9 @@ struct Pipe {
     size_t      data_off = 0;             // decode: first byte after the header region
     size_t      chunk_bytes = 0, slack = 0;
     size_t      out_base = 0;             // file offset of the first chunk's output
+    bool        map_writes = false;       // writers copy into a shared mapping of the output file (needs O_RDWR)
+    std::mutex  grow_mu;
+    size_t      file_size = 0;            // how far the output file has been grown
     std::mutex  mu;
     std::condition_variable cv;
     std::vector<Chunk> chunks;            // encode: sized up front; decode: grows as the splitter advances
@@ -196,13 +201,10 @@ static void encode_chunk(Pipe& P, vcfc_ctx* ctx, Chunk& c) {
             c.n_hash = 0; c.hash_after_data = false;
         }
         while (pos < c.end && rc == VCFC_OK) {
-            size_t h = pos;                                         // next line that starts with '#'
-            for (;;) {
-                const uint8_t* q = (const uint8_t*)memchr(p + h, '#', c.end - h);
-                if (!q) { h = c.end; break; }
-                h = (size_t)(q - p);
-                if (h == c.begin || p[h - 1] == '\n') break;
-                h++;
+            size_t h = c.end;                                       // next line that starts with '#' (found by the reader)
+            if (c.hash) {
+                auto it = std::lower_bound(c.hash->begin(), c.hash->end(), pos);
+                if (it != c.hash->end()) h = *it;
             }
             if (h > pos) {
                 size_t olen = 0, nl = 0;
@@ -295,6 +297,16 @@ static void text_reader(Pipe& P) {
             }
             if (b > e) b = e;
             c.begin = b; c.end = e;
+            for (size_t h = b; h < e;) {                             // lines that start with '#': passed through by the worker
+                const uint8_t* q = (const uint8_t*)memchr(c.in.p + h, '#', e - h);
+                if (!q) break;
+                h = (size_t)(q - c.in.p);
+                if (h == b || c.in.p[h - 1] == '\n') {
+                    if (!c.hash) c.hash = new std::vector<size_t>();
+                    c.hash->push_back(h);
+                }
+                h++;
+            }
             break;
         }
         {
@@ -426,6 +438,32 @@ static void worker(Pipe& P, int g) {
     }
 }
 
+// Buffered pwrite()s to ONE file serialise on its inode lock (one memcpy at a time: ~3 GB/s on tmpfs); copying into a
+// shared mapping of the chunk's range does not, so the writers really run side by side.  The file is grown first
+// (ftruncate up only; the final size is set when the pipeline ends).  Falls back to pwrite where mmap is refused.
+static int write_chunk(Pipe& P, const uint8_t* p, size_t n, size_t off) {
+    if (P.map_writes) {
+        const size_t end = off + n;
+        {
+            std::lock_guard<std::mutex> g(P.grow_mu);
+            if (end > P.file_size) {
+                const size_t want = std::max(end, P.file_size + ((size_t)256 << 20));
+                if (ftruncate(P.ofd, (off_t)want) == 0) P.file_size = want;
+            }
+        }
+        if (end <= P.file_size) {
+            const size_t pg = (size_t)sysconf(_SC_PAGESIZE), lo = off & ~(pg - 1);
+            void* m = mmap(nullptr, end - lo, PROT_READ | PROT_WRITE, MAP_SHARED, P.ofd, (off_t)lo);
+            if (m != MAP_FAILED) {
+                memcpy((uint8_t*)m + (off - lo), p, n);
+                munmap(m, end - lo);
+                return VCFC_OK;
+            }
+        }
+    }
+    return pwrite_all(P.ofd, p, n, off);
+}
+
 static void writer(Pipe& P) {
     for (;;) {
         size_t k;
@@ -442,7 +480,7 @@ static void writer(Pipe& P) {
             k = P.next_write++;
             c = P.chunks[k];
         }
-        int rc = c.out_len ? pwrite_all(P.ofd, c.out.p, c.out_len, c.out_off) : VCFC_OK;
+        int rc = c.out_len ? write_chunk(P, c.out.p, c.out_len, c.out_off) : VCFC_OK;
         pin_put(P.lead, c.out);
         {
             std::lock_guard<std::mutex> g(P.mu);
@@ -526,13 +564,14 @@ static int compress_file_impl(vcfc_ctx** ctxs, int n_ctx, const char* in_path, c
     struct stat st;
     if (fstat(P.ifd, &st) != 0) { close(P.ifd); return VCFC_E_IO; }
     P.file_len = (size_t)st.st_size;
-    P.ofd = open(out_path, O_CREAT | O_TRUNC | (index_path ? O_RDWR : O_WRONLY), 0644);
+    P.ofd = open(out_path, O_CREAT | O_TRUNC | O_RDWR, 0644);
     if (P.ofd < 0) { close(P.ifd); return VCFC_E_IO; }
+    P.map_writes = !getenv("VCFC_NO_MAP_WRITES");
     const int hw = (int)std::max(2u, std::thread::hardware_concurrency());
     const int n_readers = n_threads_default("VCFC_READERS", std::min(8, std::max(2, hw / 2)));
-    const int n_writers = n_threads_default("VCFC_WRITERS", 2);
-    // chunk size: VCFC_FILE_CHUNK_MB (default 64), smaller for small files so that every GPU and reader has work
-    size_t C = env_sz("VCFC_FILE_CHUNK_MB", 64) << 20;
+    const int n_writers = n_threads_default("VCFC_WRITERS", 3);
+    // chunk size: VCFC_FILE_CHUNK_MB (default 16: measured best on tmpfs, tools/file_sweep.py), smaller for small files so that every GPU and reader has work
+    size_t C = env_sz("VCFC_FILE_CHUNK_MB", 16) << 20;
     const size_t per = P.file_len / (size_t)(4 * n_ctx) + 1;
     C = std::max<size_t>((size_t)1 << 20, std::min(C, (per + 4095) & ~(size_t)4095));
     P.chunk_bytes = C;
@@ -562,7 +601,7 @@ static int compress_file_impl(vcfc_ctx** ctxs, int n_ctx, const char* in_path, c
             }
         }
     }
-    for (auto& c : P.chunks) { delete c.idx; c.idx = nullptr; }
+    for (auto& c : P.chunks) { delete c.idx; c.idx = nullptr; delete c.hash; c.hash = nullptr; }
     close(P.ifd);
     if (close(P.ofd) != 0 && rc == VCFC_OK) rc = VCFC_E_IO;
     pin_trim(P.lead, env_sz("VCFC_PIN_KEEP_MB", 4096) << 20);
@@ -588,8 +627,9 @@ int vcfc_decompress_file_multi(vcfc_ctx** ctxs, int n_ctx, const char* in_path, 
     struct stat st;
     if (fstat(P.ifd, &st) != 0) { close(P.ifd); return VCFC_E_IO; }
     P.file_len = (size_t)st.st_size;
-    P.ofd = open(out_path, O_CREAT | O_TRUNC | O_WRONLY, 0644);         // the reference truncates first (compress.cpp:1217)
+    P.ofd = open(out_path, O_CREAT | O_TRUNC | O_RDWR, 0644);           // the reference truncates first (compress.cpp:1217)
     if (P.ofd < 0) { close(P.ifd); return VCFC_E_IO; }
+    P.map_writes = !getenv("VCFC_NO_MAP_WRITES");
     // header region (compress.cpp:1108-1211): read until it parses or the file ends
     int rc = VCFC_OK;
     {
@@ -609,9 +649,10 @@ int vcfc_decompress_file_multi(vcfc_ctx** ctxs, int n_ctx, const char* in_path, 
         if (rc != VCFC_OK) { close(P.ifd); close(P.ofd); return rc; }
         P.data_off = hlen;
         P.out_base = hlen;
+        P.file_size = hlen;
     }
-    const int n_writers = n_threads_default("VCFC_WRITERS", 4);
-    size_t C = env_sz("VCFC_FILE_DCHUNK_MB", 8) << 20;
+    const int n_writers = n_threads_default("VCFC_WRITERS", std::min(12, std::max(2, (int)std::thread::hardware_concurrency() * 3 / 4)));   // the text side is the wide one
+    size_t C = env_sz("VCFC_FILE_DCHUNK_MB", 4) << 20;
     const size_t per = (P.file_len - P.data_off) / (size_t)(4 * n_ctx) + 1;
     C = std::max<size_t>((size_t)256 << 10, std::min(C, (per + 4095) & ~(size_t)4095));
     P.chunk_bytes = C;

@@ -22,7 +22,7 @@ static int usage() {
             "usage: vcfc compress IN.vcf OUT.vcfc | decompress IN.vcfc OUT.vcf | query IN.vcfc REF[:START-END]\n"
             "       vcfc create-binned-index BIN_SIZE IN.vcfc | query-binned-index IN.vcfc REF:START-END\n"
             "       env: VCFC_DEVICE (default 0), VCFC_GPUS (compress / decompress over that many GPUs starting at VCFC_DEVICE,\n"
-            "            default 1, \"all\" = every GPU of the box), VCFC_FILE_CHUNK_MB (default 64),\n"
+            "            default 1, \"all\" = every GPU of the box), VCFC_FILE_CHUNK_MB (default 16),\n"
             "            VCFC_INDEX_BIN=N (compress also writes OUT.vcfci with N lines per bin, in the same pass)\n");
     return 1;
 }
