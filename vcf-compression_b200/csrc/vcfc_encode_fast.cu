@@ -204,10 +204,15 @@ __device__ __forceinline__ void item_emit(const uint8_t* __restrict__ win, const
 }
 
 // ---- the streaming kernel: one warp per tile -------------------------------------------------------------------------
+#ifndef VCFC_ENC_TICKET
+#define VCFC_ENC_TICKET 1
+#endif
 #ifndef VCFC_ENC_STILE
 #define VCFC_ENC_STILE 32768
 #define VCFC_ENC_SWARPS 4
 #define VCFC_ENC_SCTAS 8
+#endif
+#ifndef VCFC_ENC_SSTAGE
 #define VCFC_ENC_SSTAGE 6144
 #endif
 constexpr int kSTile = VCFC_ENC_STILE;          // nominal input bytes per tile
@@ -306,6 +311,19 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
     constexpr int kFlSkip = 1 << 9;
     int cur_ce = 0, cur_fl = 0;             // the tile to encode: end cut (relative to its own base), cut kind | class << 4 | uniform << 8
 
+#if VCFC_ENC_TICKET
+    // Tiles are handed out in increasing order by one atomic counter: a dense tile costs several times a sparse one, and a
+    // fixed round-robin leaves the warps that drew the cheap tiles idle at the end.  Whoever holds ticket t publishes tile t's
+    // look-back record before it waits on anything, so a reader of s1[t - 1] never waits on a warp that has not started.
+    int tile = -1, nt = 0, nn = 0;
+    if (lane == 0) nt = (int)atomicAdd(&ctrl->ticket, 1u);
+    nt = __shfl_sync(0xffffffffu, nt, 0);
+    for (; tile < n_tiles; tile = nt, nt = __shfl_sync(0xffffffffu, nn, 0)) {
+        int n_ce = 0, n_fl = 0;
+        nn = n_tiles;                        // the ticket after nt: asked for now, needed when the iteration ends
+        if (lane == 0 && nt < n_tiles) nn = (int)atomicAdd(&ctrl->ticket, 1u);
+        if (nt < n_tiles) {
+#else
     for (int tile = gw - nw; tile < n_tiles; tile += nw) {
         // ---- ahead: end cut of the next tile and its look-back #1 record -- what the run that leaves the tile looks
         //      like.  A sample is a run head unless it and the word before it are the same coded genotype (line_scan16
@@ -314,6 +332,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
         int n_ce = 0, n_fl = 0;
         if (tile + nw < n_tiles) {
             const int nt = tile + nw;
+#endif
             const int irr_now = irr_seen;
             irr_seen = *((volatile int*)&ctrl->irregular);
             unsigned word = (2u << 30) | ((unsigned)kNone << 8);            // nothing carried out
