@@ -158,22 +158,38 @@ __device__ __forceinline__ int item_count(const Item& it, int ein, uint32_t* cfb
     return n;
 }
 
+// cls_flag of the genotype whose allele bits are bit 16 / bit 0 of y, as a table lookup (PRMT) in the flag constant
+__device__ __forceinline__ uint32_t flag_of(uint32_t y) {
+    const uint32_t c2 = y & 0x00010001u;
+    return __byte_perm(0x80C0A000u, 0u, (c2 >> 15) | c2);           // selector nibble 0 = 2a + b; the other result bytes are not stored
+}
+
 __device__ __forceinline__ void item_emit(const uint8_t* __restrict__ win, const Item& it, uint32_t cfbit, int h,
                                           uint8_t* __restrict__ dst) {
     const uint32_t tok = it.V ? (it.CL | cfbit) : 0u;
     const uint32_t kendbit = it.kend >= 0 ? (1u << it.kend) : 0u;
-    int o = 0;
     // run tokens only (the common case): a tight loop -- unless many lanes of the warp have literals, then one loop for all
     const bool many = __popc(__ballot_sync(0xffffffffu, (it.L | kendbit) != 0u)) > 4;
     if (!(it.L | kendbit) && !many) {
-        for (uint32_t t = tok; t; t &= t - 1) {
-            const int k = __ffs(t) - 1;
-            const uint32_t c = (((it.Ap >> k) & 1u) << 1) | ((it.Bp >> k) & 1u);
-            dst[o++] = (uint8_t)(cls_flag((int)c) | (uint32_t)(k - h));
-            h = k;
+        if (!tok) return;
+        // a token's count is the distance to the token below it (to h for the lowest): walk from the top, so one FLO per token
+        // finds both the next token and this one's count
+        const uint32_t AB = (it.Ap << 16) | (it.Bp & 0xFFFFu);    // tokens sit at bits 0..15 here
+        const uint32_t m0 = tok & (0u - tok);
+        const int k0 = 31 - __clz(m0);
+        dst[0] = (uint8_t)(flag_of(AB >> k0) | (uint32_t)(k0 - h));
+        uint32_t t = tok;
+        uint8_t* d = dst + __popc(tok) - 1;
+        int k = 31 - __clz(t);
+        while (t != m0) {
+            t ^= 1u << k;
+            const int kn = 31 - __clz(t);
+            *d-- = (uint8_t)(flag_of(AB >> k) | (uint32_t)(k - kn));
+            k = kn;
         }
         return;
     }
+    int o = 0;
     uint32_t ev = tok | it.L | kendbit;
     while (ev) {
         const int k = __ffs(ev) - 1;
@@ -201,6 +217,11 @@ __device__ __forceinline__ void item_emit(const uint8_t* __restrict__ win, const
             }
         }
     }
+}
+
+// the same into the log (generic addresses), for the rare second pass of a tile that outgrew its staging area: kept out of line
+__device__ __noinline__ void item_emit_log(const uint8_t* __restrict__ win, Item it, uint32_t cfbit, int h, uint8_t* __restrict__ dst) {
+    item_emit(win, it, cfbit, h, dst);
 }
 
 // ---- the streaming kernel: one warp per tile -------------------------------------------------------------------------
@@ -241,6 +262,15 @@ __device__ __noinline__ uint32_t ldw_edge(const uint8_t* __restrict__ win, int r
 __device__ __forceinline__ uint32_t ldw(const uint8_t* __restrict__ win, int r, int r_lo, int r_hi) {   // r multiple of 4
     if (r >= r_lo && r + 4 <= r_hi) return *reinterpret_cast<const uint32_t*>(win + r);
     return ldw_edge(win, r, r_lo, r_hi, 0u);
+}
+
+// A step that touches the first / last bytes of the input: words outside [r_lo, r_hi) read as 0 (out of line: rare)
+__device__ __noinline__ void step_load_edge(const uint8_t* __restrict__ win, int blk, int r_lo, int r_hi, uint32_t* W) {
+#pragma unroll 1
+    for (int q = 0; q < 18; q++) {
+        const int r = blk - 4 + 4 * q;
+        W[q] = (r >= r_lo && r + 4 <= r_hi) ? *reinterpret_cast<const uint32_t*>(win + r) : ldw_edge(win, r, r_lo, r_hi, 0u);
+    }
 }
 
 // End of the required section of the line that starts at relative offset ls, 512 bytes per round trip (16 per lane):
@@ -305,6 +335,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* const stage = sm.stage[warp];
     const int gw = (int)blockIdx.x * kSWarps + warp, nw = (int)gridDim.x * kSWarps;
+    const size_t lane64 = 64u * (size_t)lane;
     int irr_seen = 0;                       // ctrl->irregular as of one tile ago (the load stays off the critical path)
     // The warp runs one tile AHEAD with the end cut and the look-back #1 record: iteration k publishes the record of
     // this warp's tile k+1 and then encodes tile k, so a record is there a whole tile time before its reader needs it.
@@ -424,6 +455,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
         const int r_lo = gb < 0 ? 64 : 0;                               // valid relative range [r_lo, r_hi)
         const int r_hi = (int)(n - gb < (long long)(1 << 24) ? n - gb : (long long)(1 << 24));
         int irregular = 0;
+        const int pf_lim = min(r_hi, ce + 127), pf_lim2 = min(r_hi, ce + 4095);   // how far the steps' prefetches may reach
         // the first 8 KB of the tile into L2 now; every step asks for the 2 KB that lie 8 KB ahead of it
         {
             const int pr = 64 + 128 * lane;
@@ -485,36 +517,53 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 const int a = cur, wstart = a & ~63, blk = wstart + 64 * lane, phase = a & 3, base = blk + phase;
                 const int bound = min(ce, wstart + kStep);
                 uint32_t W[18];
-                if (blk >= r_lo && blk + 64 <= r_hi) {
+                const uint8_t* const pb = win + blk;
+                if (wstart - 4 >= r_lo && wstart + kStep + 4 <= r_hi) {
+                    // the whole step lies inside the input (warp-uniform, all but the first / last step of the block): every lane
+                    // loads its block and the two words around it itself -- the neighbours' words are L1 hits, cheaper than two
+                    // shuffles plus two divergent edge loads
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        const uint4 v = *reinterpret_cast<const uint4*>(win + blk + 16 * q);
+                        const uint4 v = *reinterpret_cast<const uint4*>(pb + 16 * q);
                         W[4 * q + 1] = v.x; W[4 * q + 2] = v.y; W[4 * q + 3] = v.z; W[4 * q + 4] = v.w;
                     }
+                    W[0] = *reinterpret_cast<const uint32_t*>(pb - 4);
+                    W[17] = *reinterpret_cast<const uint32_t*>(pb + 64);
                 } else {
+                    uint32_t We[18];                       // (in local memory: the address escapes; W itself stays in registers)
+                    step_load_edge(win, blk, r_lo, r_hi, We);
 #pragma unroll
-                    for (int q = 0; q < 16; q++) W[q + 1] = ldw(win, blk + 4 * q, r_lo, r_hi);
+                    for (int q = 0; q < 18; q++) W[q] = We[q];
                 }
-                // the next step's block: a prefetch hint costs no registers and turns its loads into L1 hits
-                if (blk + kStep + 64 <= r_hi && blk + kStep < ce + 64) asm volatile("prefetch.global.L1 [%0];" ::"l"(win + blk + kStep));
-                if (lane < 16 && wstart + 8192 + 2048 <= r_hi && wstart + 8192 < ce + 2048) asm volatile("prefetch.global.L2 [%0];" ::"l"(win + wstart + 8192 + 128 * lane));
-                W[0] = __shfl_up_sync(0xffffffffu, W[16], 1);
-                W[17] = __shfl_down_sync(0xffffffffu, W[1], 1);
-                if (lane == 0) W[0] = ldw(win, blk - 4, r_lo, r_hi);
-                if (lane == 31) W[17] = ldw(win, blk + 64, r_lo, r_hi);
+                // the next step's block: a prefetch hint costs no registers and turns its loads into L1 hits; 8 KB ahead into L2
+                if (blk + kStep + 64 <= pf_lim) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + kStep));
+                if (lane < 16 && wstart + 8192 + 2048 <= pf_lim2) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + lane64 + 8192));
                 const int sh = 8 * phase;
                 const uint32_t sp = __funnelshift_r(W[0], W[1], sh);
                 const uint32_t pc_all = ((sp & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u ? 1u : 0u;
-                uint32_t Craw = 0, accA = sp << 31, accB = (sp >> 16) << 31;   // allele bits are shifted in from the top
+                // X[k] = sample word k ^ "0|0\t": zero but for the two allele bits (bit 0, bit 16) when the sample is "x|y\t" with
+                // x, y in {0,1}.  When every sample of the step is (no literal, no line end, no bytes outside the line) the allele
+                // masks are one sum of shifted words; otherwise per-sample tests, and the allele bits masked before they are summed
+                uint32_t X[16];
 #pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const uint32_t sw = __funnelshift_r(W[k + 1], W[k + 2], sh);
-                    if (((sw & 0xFFFEFFFEu) ^ 0x09307C30u) == 0u) Craw |= 1u << k;      // "x|y\t" with x, y in {0,1}
-                    accA = __funnelshift_r(accA, sw, 1);
-                    accB = __funnelshift_r(accB, sw >> 16, 1);
+                for (int k = 0; k < 16; k++) X[k] = __funnelshift_r(W[k + 1], W[k + 2], sh) ^ 0x09307C30u;
+                uint32_t anyx = 0;
+#pragma unroll
+                for (int k = 0; k < 16; k++) anyx |= X[k];
+                uint32_t Craw = 0xFFFFu, acc = 0;              // acc = second-allele bits << 16 | first-allele bits
+                if (!__any_sync(0xffffffffu, (anyx & 0xFFFEFFFEu) != 0u)) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) acc += X[k] << k;
+                } else {
+                    Craw = 0;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        if ((X[k] & 0xFFFEFFFEu) == 0u) Craw |= 1u << k;
+                        acc += (X[k] & 0x00010001u) << k;
+                    }
                 }
                 Item it;
-                it.base = base; it.Ap = accA >> 15; it.Bp = accB >> 15;
+                it.base = base; it.Ap = ((acc & 0xFFFFu) << 1) | (sp & 1u); it.Bp = ((acc >> 16) << 1) | ((sp >> 16) & 1u);
                 // samples that start in [a, bound)
                 const int rel_a = a - base, rel_b = bound - base;
                 const int klo = rel_a > 0 ? rel_a >> 2 : 0, khi = rel_b >= 64 ? 16 : (rel_b > 0 ? (rel_b + 3) >> 2 : 0);
@@ -606,7 +655,10 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
                 const int step_total = __shfl_sync(0xffffffffu, inc, 31);
                 if (pass == 0 && o + step_total > kSStage) { emit_on = false; overflow = true; }
-                if (emit_on) item_emit(win, it, cf, h0, image + o + inc - n0);
+                if (emit_on) {
+                    if (pass == 0) item_emit(win, it, cf, h0, stage + (o + inc - n0));       // shared-memory stores
+                    else item_emit_log(win, it, cf, h0, image + (o + inc - n0));
+                }
                 o += step_total;
                 first = false;
                 if (endm) { cur = q_end + 1; in_req = true; }
