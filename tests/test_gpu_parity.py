@@ -146,14 +146,19 @@ def test_long_required_sections(codec):
         assert codec.last_path == expect, (info_len, codec.last_reject_reason)
 
 
-def test_short_lines_up_to_62_per_tile(codec):
-    """~0.6 KB lines (up to 62 line starts per 32 KB tile) are still served by the tile kernels; shorter ones by the generic ones."""
+def test_short_lines_many_per_tile(codec):
+    """Short lines (hundreds of line starts per tile) stay on the tile kernels: a log segment is closed after 62 line
+    starts, so a tile's line count is not bounded."""
     _, data = vcfgen.random_vcf_like(600, 140, seed=11)          # ~590-byte lines
     check_block(codec, data, sample_count=140, expect_path=pkg.PATH_FAST)
     _, data = vcfgen.random_vcf_like(600, 30, seed=12)           # ~150-byte lines: more than 62 per tile
-    check_block(codec, data, sample_count=30)
-    codec.compress_block(data)
-    assert codec.last_path == pkg.PATH_GENERIC and codec.last_reject_reason == 3
+    check_block(codec, data, sample_count=30, expect_path=pkg.PATH_FAST)
+    _, data = vcfgen.random_vcf_like(20000, 30, seed=13)         # several tiles of ~200 lines each
+    check_block(codec, data, sample_count=30, expect_path=pkg.PATH_FAST)
+    _, data = vcfgen.random_vcf_like(30000, 1, seed=14)          # one sample per line: ~35-byte lines
+    check_block(codec, data, sample_count=1)                     # (lines under 64 bytes exceed the line table: generic kernels)
+    _, data = vcfgen.random_vcf_like(9000, 12, seed=15, probs=(0.2, 0.3, 0.5))
+    check_block(codec, data, sample_count=12, expect_path=pkg.PATH_FAST)
 
 
 @pytest.mark.parametrize("n_samples", [1, 2, 3, 5, 31, 32, 33, 127, 128, 129, 255, 1000, 3583, 3584, 3585, 4096, 7000, 8180, 8191, 8192, 8193, 20000])

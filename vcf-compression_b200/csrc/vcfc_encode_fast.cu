@@ -2,7 +2,7 @@
 //
 // "Regular" = what a GT-only VCF looks like: '\n'-terminated lines, single tabs, >= 10 columns,
 // every sample column exactly 3 bytes (a|b, a/b, ./. ...), required section (CHROM..FORMAT) of
-// at most kMaxReq bytes, at most kMaxNl (62) line starts per 32 KB tile.  Anything else sets
+// at most kMaxReq bytes.  Anything else sets
 // ctrl->irregular and the caller reruns the block on the generic kernels (vcfc_generic.cu).
 // Output bytes are those of compress_data_line (/root/reference/src/compress.cpp:5-203) for every line.
 //
@@ -24,6 +24,7 @@
 //      k_gather_tiles moves the bytes and k_patch_headers fills in the 4-byte line-length headers
 //      (they need the NEXT line's offset) and the result block.
 #include <algorithm>
+#include <cstdlib>
 
 #include "vcfc_common.cuh"
 #include "vcfc_internal.h"
@@ -33,7 +34,7 @@ namespace enc {
 
 constexpr int kHalo = 1024;             // how far around a nominal tile boundary a cut point is searched
 constexpr int kMaxReq = kHalo - 64;     // longest required section taken by this path
-constexpr int kMaxNl = 62;              // line starts per tile taken by this path (every lane keeps the offsets of two lines)
+constexpr int kMaxNl = 62;              // line starts per log segment (every lane keeps the offsets of two lines)
 
 enum { kCutLine = 0, kCutSample = 1, kCutSampleFirst = 2, kCutEnd = 3, kCutBad = 4 };
 constexpr int kNone = 7;                // "no open run" class
@@ -219,9 +220,36 @@ __device__ __forceinline__ void item_emit(const uint8_t* __restrict__ win, const
     }
 }
 
-// the same into the log (generic addresses), for the rare second pass of a tile that outgrew its staging area: kept out of line
-__device__ __noinline__ void item_emit_log(const uint8_t* __restrict__ win, Item it, uint32_t cfbit, int h, uint8_t* __restrict__ dst) {
-    item_emit(win, it, cfbit, h, dst);
+// Staged bytes -> the log, as one segment of the tile's chain (warp-collective).  Segments are 16-byte aligned: header
+// {u32 bytes, u32 line starts, u64 position of the next segment}, the bytes, and the tile-relative u32 offsets of the line
+// starts that lie in the segment (at most 62: every lane keeps two).  Reserved with one atomicAdd; the previous segment's header learns where this one lies.
+__device__ __noinline__ void flush_segment(const uint8_t* __restrict__ stage, int nbytes, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
+                                           unsigned long long log_cap, int lane, unsigned long long* seg_first,
+                                           unsigned long long* seg_prev, bool* dead, int nl, int my_off, int my_off2) {
+    __syncwarp();
+    const int body = (nbytes + 15) & ~15, trailer = (4 * nl + 15) & ~15;
+    const unsigned long long need = 16ull + (unsigned long long)body + (unsigned long long)trailer;
+    unsigned long long pos = 0ull;
+    if (lane == 0 && !*dead) {
+        pos = atomicAdd(&ctrl->log_cursor, need);
+        if (pos + need > log_cap) { atomicExch(&ctrl->cap_exceeded, 1); pos = ~0ull; }
+    }
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (*dead || pos == ~0ull) { *dead = true; __syncwarp(); return; }
+    uint8_t* const dst = log + pos;
+    if (lane == 0) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4((unsigned)nbytes, (unsigned)nl, 0u, 0u);
+        if (*seg_prev) *reinterpret_cast<unsigned long long*>(log + (*seg_prev - 1ull) + 8) = pos;
+    }
+    const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + 16);
+    for (int k = lane; k < (body >> 4); k += 32) d4[k] = s4[k];
+    uint32_t* tr = reinterpret_cast<uint32_t*>(dst + 16 + body);
+    if (lane < nl) tr[lane] = (uint32_t)my_off;
+    if (lane + 32 < nl) tr[lane + 32] = (uint32_t)my_off2;
+    if (!*seg_first) *seg_first = pos + 1ull;             // (+1: position 0 is a valid one)
+    *seg_prev = pos + 1ull;
+    __syncwarp();
 }
 
 // ---- the streaming kernel: one warp per tile -------------------------------------------------------------------------
@@ -234,15 +262,18 @@ __device__ __noinline__ void item_emit_log(const uint8_t* __restrict__ win, Item
 #define VCFC_ENC_SCTAS 8
 #endif
 #ifndef VCFC_ENC_SSTAGE
-#define VCFC_ENC_SSTAGE 6144
+#define VCFC_ENC_SSTAGE 3200
 #endif
-constexpr int kSTile = VCFC_ENC_STILE;          // nominal input bytes per tile
+constexpr int kSTile = VCFC_ENC_STILE;          // smallest nominal input bytes per tile (the host doubles it for large inputs)
+constexpr int kSTileMax = 131072;
 constexpr int kSWarps = VCFC_ENC_SWARPS;        // warps per CTA (independent of each other)
 constexpr int kSCtas = VCFC_ENC_SCTAS;
-constexpr int kSStage = VCFC_ENC_SSTAGE;        // per-warp staging; a tile that expands beyond it is emitted in a second pass
+constexpr int kSStage = VCFC_ENC_SSTAGE;        // per-warp staging; flushed to the log as a segment whenever the next piece would not fit
 constexpr int kStep = 2048;                     // bytes per step: 32 lanes x 64
 constexpr int kBackRows = 4;                    // rows of 512 bytes per round trip of the look-back's coarse search
+constexpr int kStepMaxOut = 2576;               // most bytes one step can emit: 512 literals of 5 bytes, a chunk token, the line end
 static_assert(kSTile % 64 == 0, "tiles start on block boundaries");
+static_assert(kSStage % 16 == 0 && kSStage >= kStepMaxOut + 512 && kSStage >= 8 + kMaxReq, "a step or a line start must fit the staging area");
 
 struct SmemS {
     alignas(16) uint8_t stage[kSWarps][kSStage + 16];
@@ -329,7 +360,7 @@ __device__ int line_scan16(const uint8_t* __restrict__ win, int ls, int r_lo, in
 __global__ void __launch_bounds__(32 * kSWarps, kSCtas)
 k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
                 unsigned int* __restrict__ s1, unsigned long long* __restrict__ rec_pos, unsigned long long* __restrict__ rec_size,
-                unsigned long long* __restrict__ rec_lines, int n_tiles, unsigned long long log_cap) {
+                unsigned long long* __restrict__ rec_lines, int n_tiles, unsigned long long log_cap, int tile_sz) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemS& sm = *reinterpret_cast<SmemS*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -370,7 +401,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
             if (irr_now) {                  // some tile already gave up: keep the look-back chains alive and move on
                 n_fl = kFlSkip;
             } else {
-                const long long t0 = (long long)nt * kSTile, gb = t0 - 64, t1 = t0 + kSTile;
+                const long long t0 = (long long)nt * tile_sz, gb = t0 - 64, t1 = t0 + tile_sz;
                 const uint8_t* const win = in + gb;
                 const int r_lo = gb < 0 ? 64 : 0;
                 const int r_hi = (int)(n - gb < (long long)(1 << 24) ? n - gb : (long long)(1 << 24));
@@ -449,7 +480,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
         cur_ce = n_ce; cur_fl = n_fl;
         if (tile < 0 || (fl & kFlSkip)) continue;
         // ---- the tile itself ---------------------------------------------------------------------------------------------
-        const long long t0 = (long long)tile * kSTile;
+        const long long t0 = (long long)tile * tile_sz;
         const long long gb = t0 - 64;                                   // tile-relative offsets: r = g - gb (a multiple of 64 apart)
         const uint8_t* const win = in + gb;
         const int r_lo = gb < 0 ? 64 : 0;                               // valid relative range [r_lo, r_hi)
@@ -462,7 +493,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
             if (pr + 128 <= r_hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(win + pr));
             if (pr + 4096 + 128 <= r_hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(win + pr + 4096));
         }
-        if (t0 + kSTile >= n && in[n - 1] != '\n') irregular = 1;        // no final newline: generic path
+        if (t0 + tile_sz >= n && in[n - 1] != '\n') irregular = 1;        // no final newline: generic path
         const int ke = fl & 15, lb_lc = (fl >> 4) & 15, lb_uniform = (fl >> 8) & 1, lb_nsamp = (ce - 64) >> 2;
         if (ke == kCutBad) irregular = 2;
         int ks, cs;
@@ -477,28 +508,29 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
         int pc0 = kNone;
         if (ks == kCutSample && tile > 0 && cs < ce && !irregular) pc0 = gt_class3(win + cs - 4);
         bool need_lb = pc0 < 4;
-        // ---- the tile, line by line; pass 0 emits into the staging area while the output fits, pass 1 (rare) straight
-        //      into the log once the size is known -------------------------------------------------------------------------
-        int total = 0, nl = 0, my_off = 0, my_off2 = 0;
-        unsigned long long pos = 0ull;
-        bool overflow = false, skip_write = false;
-        for (int pass = 0; pass < 2; pass++) {
-            uint8_t* const image = pass == 0 ? stage : log + pos;
-            bool emit_on = !irregular;
+        // ---- the tile, line by line.  Output goes to the staging area; when the next piece (a line start: <= 8 + kMaxReq bytes,
+        //      a step: <= 2.6 KB) would not fit, what is staged is flushed to the log as a SEGMENT: [u32 bytes, u32 0, u64 position
+        //      of the tile's next segment][bytes, padded to 16].  A sparse tile is one segment; a dense one never runs twice ----
+        int nl = 0, nl_seg = 0, my_off = 0, my_off2 = 0;  // line starts of the tile / of the segment being staged, their offsets
+        int flushed = 0;                                  // tile bytes already in the log (o - flushed = staging fill)
+        unsigned long long seg_first = 0ull, seg_prev = 0ull;
+        bool dead = false;                                // the log is full: keep counting, write nothing more
+        {
             int o = 0, cur = cs, ein_carry = ein0;
             bool in_req = ks == kCutLine, first = ks == kCutSampleFirst;
-            nl = 0;
             while (cur < ce && !irregular) {
                 if (in_req) {
                     // ---- a line start: two length headers + the required section (compress.cpp:32-100) ----------------
                     const int ls = cur;
                     const int s0 = line_scan16(win, ls, r_lo, r_hi, lane);
                     if (s0 < 0) { irregular = 4; break; }
-                    if (nl >= kMaxNl) { irregular = 3; break; }
                     const int rq = s0 - ls;
-                    if (pass == 0 && o + 8 + rq > kSStage) { emit_on = false; overflow = true; }
-                    if (emit_on) {
-                        uint8_t* d = image + o;
+                    if (o - flushed + 8 + rq > kSStage || nl_seg >= kMaxNl) {
+                        flush_segment(stage, o - flushed, log, ctrl, log_cap, lane, &seg_first, &seg_prev, &dead, nl_seg, my_off, my_off2);
+                        flushed = o; nl_seg = 0;
+                    }
+                    {
+                        uint8_t* d = stage + (o - flushed);
                         if (lane < 4) d[lane] = lane == 0 ? 0xC0 : 0;                       // line length: patched by k_patch_headers
                         if (lane >= 4 && lane < 8) {
                             const unsigned v = (unsigned)rq;
@@ -506,8 +538,8 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                         }
                         for (int k = lane; k < rq; k += 32) d[8 + k] = win[ls + k];
                     }
-                    if (lane == (nl & 31)) { if (nl < 32) my_off = o; else my_off2 = o; }
-                    nl++;
+                    if (lane == (nl_seg & 31)) { if (nl_seg < 32) my_off = o; else my_off2 = o; }
+                    nl++; nl_seg++;
                     o += 8 + rq;
                     cur = s0;
                     in_req = false; first = true; ein_carry = kNoHead;
@@ -654,50 +686,24 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
                 const int step_total = __shfl_sync(0xffffffffu, inc, 31);
-                if (pass == 0 && o + step_total > kSStage) { emit_on = false; overflow = true; }
-                if (emit_on) {
-                    if (pass == 0) item_emit(win, it, cf, h0, stage + (o + inc - n0));       // shared-memory stores
-                    else item_emit_log(win, it, cf, h0, image + (o + inc - n0));
+                if (o - flushed + step_total > kSStage) {
+                    flush_segment(stage, o - flushed, log, ctrl, log_cap, lane, &seg_first, &seg_prev, &dead, nl_seg, my_off, my_off2);
+                    flushed = o; nl_seg = 0;
                 }
+                item_emit(win, it, cf, h0, stage + (o - flushed + inc - n0));
                 o += step_total;
                 first = false;
                 if (endm) { cur = q_end + 1; in_req = true; }
                 else cur = a + 4 * ((bound - a + 3) >> 2);
             }
-            if (pass == 1) break;
-            // ---- the tile's place in the log: one atomic; the final position comes from the scan over the tile records -------
+            // ---- the tile's last segment, followed by the u32 line offsets; the final position comes from the scan over the
+            //      tile records (k_gather_tiles follows the segment chain) ------------------------------------------------------
             if (irregular) {
                 if (lane == 0 && atomicCAS(&ctrl->irregular, 0, irregular) == 0) ctrl->total_lines = (unsigned long long)tile;   // (diagnostics)
-                o = 0; nl = 0;
+                o = 0; nl = 0; flushed = 0;
             }
-            total = o;
-            const unsigned long long need = (unsigned long long)total + 2ull * (unsigned long long)nl;   // bytes + u16 line offsets
-            if (lane == 0) {
-                pos = need ? atomicAdd(&ctrl->log_cursor, need) : 0ull;
-                rec_pos[tile] = pos; rec_size[tile] = (unsigned long long)total; rec_lines[tile] = (unsigned long long)nl;
-                if (pos + need > log_cap) atomicExch(&ctrl->cap_exceeded, 1);
-            }
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            skip_write = pos + need > log_cap;
-            if (irregular || skip_write || total == 0 || !overflow) break;
-        }
-        if (irregular || skip_write || total == 0) continue;
-        uint8_t* const dst = log + pos;
-        if (lane < nl) { dst[total + 2 * lane] = (uint8_t)my_off; dst[total + 2 * lane + 1] = (uint8_t)((unsigned)my_off >> 8); }
-        if (lane + 32 < nl) { dst[total + 2 * lane + 64] = (uint8_t)my_off2; dst[total + 2 * lane + 65] = (uint8_t)((unsigned)my_off2 >> 8); }
-        if (!overflow) {
-            // staging -> log: aligned 4-byte stores, source words funnel-shifted
-            __syncwarp();
-            const int mis = (int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);      // bytes until dst is 4-byte aligned
-            const int head = min(mis, total);
-            if (lane < head) dst[lane] = stage[lane];
-            const int nwords = (total - head) >> 2;
-            const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage);
-            uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
-            for (int k = lane; k < nwords; k += 32) dw[k] = __funnelshift_r(sw[k], sw[k + 1], 8 * head);
-            const int tail0 = head + 4 * nwords;
-            if (lane < total - tail0) dst[tail0 + lane] = stage[tail0 + lane];
-            __syncwarp();
+            if (o > flushed) flush_segment(stage, o - flushed, log, ctrl, log_cap, lane, &seg_first, &seg_prev, &dead, nl_seg, my_off, my_off2);
+            if (lane == 0) { rec_pos[tile] = seg_first; rec_size[tile] = (unsigned long long)o; rec_lines[tile] = (unsigned long long)nl; }
         }
     }
 }
@@ -708,30 +714,39 @@ __global__ void k_enc_totals(Ctrl* __restrict__ ctrl, unsigned long long out_cap
     if (ctrl->total_lines > ctrl->line_cap && !ctrl->irregular) ctrl->irregular = 8;
 }
 
-// One warp per tile: log[pos .. pos + size) -> out[off ..], line offsets rebased from the tile's trailer.
+// One warp per tile: the tile's segment chain in the log -> out[off ..], line offsets rebased from the trailer behind the last segment.
 __global__ void k_gather_tiles(const uint8_t* __restrict__ log, uint8_t* __restrict__ out, const Ctrl* __restrict__ ctrl,
                                const unsigned long long* __restrict__ rec_pos, const unsigned long long* __restrict__ rec_size,
                                const unsigned long long* __restrict__ rec_lines, const unsigned long long* __restrict__ off_b,
                                const unsigned long long* __restrict__ off_l, unsigned long long* __restrict__ line_offs, int n_tiles) {
     const int t = (int)(((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (t >= n_tiles || ctrl->irregular || ctrl->cap_exceeded) return;
-    const unsigned long long pos = rec_pos[t], ob = off_b[t], ol = off_l[t];
-    const int size = (int)rec_size[t], nl = (int)rec_lines[t];
-    const uint8_t* src = log + pos;
+    const unsigned long long ob = off_b[t], ol = off_l[t];
+    int remaining = (int)rec_size[t];
+    if (remaining == 0 || rec_pos[t] == 0ull) return;
+    unsigned long long pos = rec_pos[t] - 1ull;
     uint8_t* dst = out + ob;
-    const int head = min((int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), size);
-    if (lane < head) dst[lane] = src[lane];
-    const int nwords = (size - head) >> 2;
-    const uintptr_t sa = reinterpret_cast<uintptr_t>(src + head);
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
-    const int sh = 8 * (int)(sa & 3);
-    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
-    for (int k = lane; k < nwords; k += 32) dw[k] = __funnelshift_r(sw[k], sw[k + 1], sh);   // the log has slack behind it
-    const int tail0 = head + 4 * nwords;
-    if (lane < size - tail0) dst[tail0 + lane] = src[tail0 + lane];
-    for (int l = lane; l < nl; l += 32) {
-        const unsigned o16 = (unsigned)src[size + 2 * l] | ((unsigned)src[size + 2 * l + 1] << 8);
-        line_offs[ol + (unsigned long long)l] = ob + (unsigned long long)o16;
+    int lbase = 0;
+    for (;;) {
+        const uint4 hdr = *reinterpret_cast<const uint4*>(log + pos);
+        const int size = (int)hdr.x;
+        const uint8_t* src = log + pos + 16;                  // 16-byte aligned
+        const int head = min((int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), size);
+        if (lane < head) dst[lane] = src[lane];
+        const int nwords = (size - head) >> 2;
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(src);
+        uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+        for (int k = lane; k < nwords; k += 32) dw[k] = __funnelshift_r(sw[k], sw[k + 1], 8 * head);   // (segments are padded: sw[k + 1] exists)
+        const int tail0 = head + 4 * nwords;
+        if (lane < size - tail0) dst[tail0 + lane] = src[tail0 + lane];
+        const int nls = (int)hdr.y;
+        const uint32_t* tr = reinterpret_cast<const uint32_t*>(src + ((size + 15) & ~15));
+        for (int l = lane; l < nls; l += 32) line_offs[ol + (unsigned long long)(lbase + l)] = ob + (unsigned long long)tr[l];
+        lbase += nls;
+        dst += size;
+        remaining -= size;
+        if (remaining <= 0 || size <= 0) break;
+        pos = (unsigned long long)hdr.z | ((unsigned long long)hdr.w << 32);
     }
 }
 
@@ -792,7 +807,15 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         VCFC_CUDA(ctx, cudaFuncSetAttribute(k_encode_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
         ctx->enc_attr_set = 1;
     }
-    const size_t n_tiles = (in_len + kSTile - 1) / kSTile;
+    // tile size (a multiple of 64): large tiles amortise the per-tile work (cuts, look-back record, log reservation), small
+    // inputs need enough tiles to occupy every resident warp several times over
+    size_t tile_sz = kSTile;
+    {
+        const size_t warps = (size_t)ctx->sm_count * kSCtas * kSWarps;
+        while (tile_sz < (size_t)kSTileMax && in_len / (2 * tile_sz) >= 8 * warps) tile_sz *= 2;
+        if (const char* e = getenv("VCFC_ENC_TILE")) { const long v = atol(e); if (v >= 4096 && v <= (1 << 22) && v % 64 == 0) tile_sz = (size_t)v; }
+    }
+    const size_t n_tiles = (in_len + tile_sz - 1) / tile_sz;
     const size_t lines_cap = in_len / 64 + 1024;
     DevBuf &ws = ctx->ws[10], &b_log = ctx->ws[11], &b_scr = ctx->ws[1];
     const size_t off_s1 = 256, off_rec = off_s1 + ((n_tiles * 4 + 255) & ~size_t(255));
@@ -800,7 +823,8 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
     const size_t off_scan = off_zero_end, off_lines = off_scan + 2 * n_tiles * 8, total_ws = off_lines + lines_cap * 8;
     int rc = dev_reserve(ctx, &ws, total_ws);
     if (rc) return rc;
-    const size_t log_cap = out_cap + 2 * lines_cap + 64;
+    // the log holds the output once, plus per segment a 16-byte header and padding, plus 4 bytes per line start
+    const size_t log_cap = out_cap + 4 * lines_cap + 48 * (n_tiles + out_cap / (kSStage - kStepMaxOut) + lines_cap / kMaxNl + 2) + 64;
     if ((rc = dev_reserve(ctx, &b_log, log_cap + 64))) return rc;
     uint8_t* base = (uint8_t*)ws.p;
     Ctrl* ctrl = (Ctrl*)base;
@@ -824,9 +848,9 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         long long a_n = (long long)in_len;
         uint8_t* a_log = (uint8_t*)b_log.p;
         unsigned int* a_s1 = (unsigned int*)(base + off_s1);
-        int a_tiles = (int)n_tiles;
+        int a_tiles = (int)n_tiles, a_tile_sz = (int)tile_sz;
         unsigned long long a_cap = (unsigned long long)log_cap;
-        void* args[] = {&a_in, &a_n, &a_log, &ctrl, &a_s1, &rec_pos, &rec_size, &rec_lines, &a_tiles, &a_cap};
+        void* args[] = {&a_in, &a_n, &a_log, &ctrl, &a_s1, &rec_pos, &rec_size, &rec_lines, &a_tiles, &a_cap, &a_tile_sz};
         VCFC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_encode_stream, dim3(grid), dim3(32 * kSWarps), args, sizeof(SmemS), stream));
     }
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeEncode + 1], stream); ctx->ev_pending[kTimeEncode] = 1; }
