@@ -256,6 +256,12 @@ __device__ __noinline__ void flush_segment(const uint8_t* __restrict__ stage, in
 #ifndef VCFC_ENC_TICKET
 #define VCFC_ENC_TICKET 1
 #endif
+#ifndef VCFC_ENC_LDHINT
+#define VCFC_ENC_LDHINT 0
+#endif
+#ifndef VCFC_ENC_NOPF1
+#define VCFC_ENC_NOPF1 1
+#endif
 #ifndef VCFC_ENC_STILE
 #define VCFC_ENC_STILE 32768
 #define VCFC_ENC_SWARPS 4
@@ -556,7 +562,14 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                     // shuffles plus two divergent edge loads
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        const uint4 v = *reinterpret_cast<const uint4*>(pb + 16 * q);
+                        uint4 v;
+#if VCFC_ENC_LDHINT == 1
+                        asm volatile("ld.global.L1::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(pb + 16 * q));
+#elif VCFC_ENC_LDHINT == 2
+                        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(pb + 16 * q));
+#else
+                        v = *reinterpret_cast<const uint4*>(pb + 16 * q);
+#endif
                         W[4 * q + 1] = v.x; W[4 * q + 2] = v.y; W[4 * q + 3] = v.z; W[4 * q + 4] = v.w;
                     }
                     W[0] = *reinterpret_cast<const uint32_t*>(pb - 4);
@@ -568,7 +581,9 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                     for (int q = 0; q < 18; q++) W[q] = We[q];
                 }
                 // the next step's block: a prefetch hint costs no registers and turns its loads into L1 hits; 8 KB ahead into L2
+#if !VCFC_ENC_NOPF1
                 if (blk + kStep + 64 <= pf_lim) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + kStep));
+#endif
                 if (lane < 16 && wstart + 8192 + 2048 <= pf_lim2) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + lane64 + 8192));
                 const int sh = 8 * phase;
                 const uint32_t sp = __funnelshift_r(W[0], W[1], sh);
