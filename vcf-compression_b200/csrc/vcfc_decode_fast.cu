@@ -657,6 +657,15 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
 // (16-byte stores, no parsing) and then PATCHED: one thread per 16 token bytes walks its chunk from the chunk table's
 // text offset and writes only what differs -- a '1' for the allele bytes of 0|1 / 1|0 / 1|1 runs, literal payloads --
 // plus the required sections and the line ends.  Work is proportional to the COMPRESSED size of the tile.
+#ifndef VCFC_DEC_BULK_LD
+#define VCFC_DEC_BULK_LD 1
+#endif
+#ifndef VCFC_DEC_BULK_ST
+#define VCFC_DEC_BULK_ST 1
+#endif
+#ifndef VCFC_DEC_LINEFILL
+#define VCFC_DEC_LINEFILL 8
+#endif
 #ifndef VCFC_DEC_GTHREADS
 #define VCFC_DEC_GTHREADS 256
 #define VCFC_DEC_GCTAS 5
@@ -669,6 +678,31 @@ constexpr int kCmaxG = VCFC_DEC_GCMAX;      // compressed bytes staged per batch
 constexpr int kChunksG = kCmaxG / 16 + 2 * 32;
 static_assert(kCmaxG >= 2048 && kCmaxG % 16 == 0, "a batch must at least hold a line start (8 + 960 bytes) and some chunks");
 
+// ---- bulk asynchronous copies (sm_90+ / sm_100a): one thread moves a whole buffer, completion on an mbarrier (loads) or a
+//      bulk group (stores); addresses and sizes are multiples of 16 -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 struct SmemG {
     alignas(16) uint8_t stage[kTileG];
     alignas(16) uint8_t cbuf[kCmaxG + 32];
@@ -680,6 +714,7 @@ struct SmemG {
     int n_batch, more, staged, c_first;
     int cut_next;                            // the batch's only line was cut: chunk to continue from (else -1)
     unsigned long long c_lo;
+    alignas(8) unsigned long long bar;       // mbarrier of the compressed-byte bulk load
 };
 
 __global__ void __launch_bounds__(kGThreads, VCFC_DEC_GCTAS)
@@ -698,6 +733,8 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
     unsigned long long k0 = first_line[blockIdx.x];
     unsigned fc_tile = first_chunk[blockIdx.x];         // chunk the batch's first line is staged from (kWholeLine: from its header)
     bool contd = false;                                  // that line was begun by an earlier batch of this tile
+    if (VCFC_DEC_BULK_LD && tid == 0) mbar_init(&sm.bar, 1);                 // (its first use is by this same thread; the others wait behind a barrier)
+    uint32_t parity = 0;
 
     for (;;) {
         // (1) line table entries of the next batch: lines k0 .. k0 + nb - 1 overlap the tile
@@ -752,6 +789,13 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
                 sm.c_first = cont ? (int)fc_tile : -1;
                 sm.staged = staged;
                 sm.cut_next = (nb == 1 && !whole) ? (cont ? (int)fc_tile : 0) + (wb >> 4) : -1;
+                // (2) the batch's compressed bytes: ONE bulk copy, in flight while the tile image is filled.  cbuf keeps the
+                //     source's 16-byte phase, so the copy runs from the aligned address below the first byte
+                if (VCFC_DEC_BULK_LD && nb > 0) {
+                    const uintptr_t ga = reinterpret_cast<uintptr_t>(in + s0);
+                    const uint32_t bytes = (uint32_t)(((ga & 15) + (uintptr_t)staged + 15) & ~uintptr_t(15));
+                    bulk_load(sm.cbuf, reinterpret_cast<const void*>(ga & ~uintptr_t(15)), bytes, &sm.bar);
+                }
             }
         }
         __syncthreads();
@@ -759,9 +803,9 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
         if (nb == 0) break;
         const unsigned long long c_lo = sm.c_lo;
         const int c_first = sm.c_first;
-        // (2) stage the batch's compressed bytes; cbuf keeps the source's 16-byte phase so both sides are aligned
         const int phase = (int)(reinterpret_cast<uintptr_t>(in + c_lo) & 15);
         const int staged = sm.staged;
+#if !VCFC_DEC_BULK_LD
         {
             const uint8_t* src = in + c_lo;
             const int head = min((16 - phase) & 15, staged);
@@ -773,6 +817,7 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
             const int t0 = head + 16 * n16;
             if (tid < staged - t0) sm.cbuf[phase + t0 + tid] = src[t0 + tid];
         }
+#endif
         // (3) chunk tables of the batch's lines (built once per line by k_dec_sizes): line li's entries go to slot
         //     (l_coff >> 4) + li, the global table's rule relative to the batch
         for (int li = warp; li < nb; li += kGWarps) {
@@ -787,15 +832,32 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
         {
             const int f_first = contd ? (nb > 1 ? sm.l_pos[1] : sm.l_end[0]) : sm.l_pos[0];   // a continued line is already filled
             const int f_lo = f_first <= 0 ? 0 : (f_first + 15) >> 4, f_hi = (sm.l_end[nb - 1] + 15) >> 4;
-            int li = 0;
-            for (int u = f_lo + tid; u < f_hi; u += kGThreads) {
-                const int pos = u << 4;
-                while (li + 1 < nb && sm.l_pos[li + 1] <= pos) li++;          // (a thread's units ascend)
-                const int ph = (pos - sm.l_pos[li] - sm.l_rq[li]) & 3;
-                const uint32_t P = __funnelshift_r(0x09307C30u, 0x09307C30u, 8 * ph);
-                *reinterpret_cast<uint4*>(sm.stage + pos) = make_uint4(P, P, P, P);
+            if (nb <= VCFC_DEC_LINEFILL) {
+                // few long lines: line by line, one constant pattern each (a unit belongs to the line it starts in)
+                for (int li = contd ? 1 : 0; li < nb; li++) {
+                    const int lp = sm.l_pos[li];
+                    const int lo = lp <= 0 ? 0 : (lp + 15) >> 4;
+                    const int hi = li + 1 < nb ? min((sm.l_pos[li + 1] + 15) >> 4, f_hi) : f_hi;
+                    const int ph = ((lo << 4) - lp - sm.l_rq[li]) & 3;
+                    const uint32_t P = __funnelshift_r(0x09307C30u, 0x09307C30u, 8 * ph);
+                    const uint4 P4 = make_uint4(P, P, P, P);
+                    for (int u = lo + tid; u < hi; u += kGThreads) *reinterpret_cast<uint4*>(sm.stage + (u << 4)) = P4;
+                }
+            } else {
+                int li = 0;
+                for (int u = f_lo + tid; u < f_hi; u += kGThreads) {
+                    const int pos = u << 4;
+                    while (li + 1 < nb && sm.l_pos[li + 1] <= pos) li++;          // (a thread's units ascend)
+                    const int ph = (pos - sm.l_pos[li] - sm.l_rq[li]) & 3;
+                    const uint32_t P = __funnelshift_r(0x09307C30u, 0x09307C30u, 8 * ph);
+                    *reinterpret_cast<uint4*>(sm.stage + pos) = make_uint4(P, P, P, P);
+                }
             }
         }
+#if VCFC_DEC_BULK_LD
+        mbar_wait(&sm.bar, parity);                        // the compressed bytes have landed
+        parity ^= 1u;
+#endif
         __syncthreads();
         // (5) patch: required sections and line ends (one warp per line) ...
         for (int li = warp; li < nb; li += kGWarps) {
@@ -902,16 +964,25 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
         if (cut_next >= 0) { fc_tile = (unsigned)cut_next; contd = true; }
         else { k0 += (unsigned long long)nb; fc_tile = kWholeLine; contd = false; }
     }
+    if (VCFC_DEC_BULK_ST) fence_async_smem();              // this thread's writes to the tile image, ordered before the bulk store reads them
     __syncthreads();
-    // tile image -> HBM
+    // tile image -> HBM: one bulk store of the 16-byte multiple (tile starts are 16-byte aligned when `out` is), the last
+    // tile's odd bytes by hand
     {
         uint8_t* dst = out + T0;
         if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#if VCFC_DEC_BULK_ST
+            const int nbulk = tile_len & ~15;
+            if (tid == 0 && nbulk) bulk_store(dst, sm.stage, (uint32_t)nbulk);
+            for (int i = nbulk + tid; i < tile_len; i += kGThreads) dst[i] = sm.stage[i];
+            if (tid == 0 && nbulk) bulk_store_wait_read();  // the image must outlive the copy's reads
+#else
             const int n16 = tile_len >> 4;
             const uint4* s4 = reinterpret_cast<const uint4*>(sm.stage);
             uint4* d4 = reinterpret_cast<uint4*>(dst);
             for (int i = tid; i < n16; i += kGThreads) d4[i] = s4[i];
             for (int i = (n16 << 4) + tid; i < tile_len; i += kGThreads) dst[i] = sm.stage[i];
+#endif
         } else {
             for (int i = tid; i < tile_len; i += kGThreads) dst[i] = sm.stage[i];
         }
