@@ -130,13 +130,15 @@ def test_regular_blocks_take_the_tile_kernels(codec):
 
 
 def test_long_required_sections(codec):
-    """INFO columns of 0.5 - 0.9 KB: the 9th tab lies in the line scan's second 512-byte round, and tile boundaries fall
-    inside required sections; beyond 960 bytes the block goes to the generic kernels.  All byte-identical to the oracle."""
+    """INFO columns of 0.5 - 30 KB: the 9th tab lies in a later 512-byte round of the line scan, tile boundaries fall inside
+    required sections, and a required section longer than the staging area goes to the log as its own segment; beyond
+    ~32 KB the block goes to the generic kernels.  All byte-identical to the oracle."""
     rng = __import__("random").Random(17)
     for info_len, n_samples, expect in ((480, 700, pkg.PATH_FAST), (700, 700, pkg.PATH_FAST), (850, 300, pkg.PATH_FAST),
-                                        (1300, 300, pkg.PATH_GENERIC)):
+                                        (1300, 300, pkg.PATH_FAST), (3400, 300, pkg.PATH_FAST), (9000, 40, pkg.PATH_FAST),
+                                        (30000, 100, pkg.PATH_FAST), (40000, 100, pkg.PATH_GENERIC)):
         lines = []
-        for i in range(160):
+        for i in range(160 if info_len < 5000 else 24):
             info = "AC=1;X=" + "".join(rng.choice("ACGT0123456789;=") for _ in range(info_len + rng.randrange(40)))
             gts = "\t".join(rng.choice(("0|0",) * 12 + ("0|1", "1|0", "1|1", "0|2", "./.")) for _ in range(n_samples))
             lines.append(f"7\t{1000 + i}\trs{i}\tA\tC,G\t50\tPASS\t{info}\tGT\t{gts}\n".encode())
@@ -217,6 +219,21 @@ def test_fuzz_blocks(any_path):
             lines.append("%s\t%d\trs%d\tA\tC,G\t%d\tPASS\t%s\tGT\t%s\n" % (
                 rng.choice(["1", "20", "X"]), 100 + 7 * i, i, rng.randrange(1000), info, "\t".join(gts)))
         check_block(any_path, "".join(lines).encode(), sample_count=n_samples)
+
+
+def test_last_line_without_newline(codec):
+    """A last line that ends at EOF (compress.cpp:218 getline) stays on the tile kernels when its last sample is whole;
+    a trailing tab or a cut sample goes to the generic kernels.  Short blocks and blocks of several tiles."""
+    for n_lines, n_samples, seed in ((5, 9, 3), (40, 2504, 4), (3, 30000, 5)):
+        _, data = vcfgen.random_vcf_like(n_lines, n_samples, seed=seed)
+        body = data[:-1]
+        check_block(codec, body, sample_count=n_samples, expect_path=pkg.PATH_FAST)          # ... 0|1<EOF>
+        lit = body[:-3] + b"./."
+        check_block(codec, lit, sample_count=n_samples, expect_path=pkg.PATH_FAST)           # ... ./.<EOF>
+        check_block(codec, body + b"\t")                                                     # trailing tab, no newline
+        check_block(codec, body[:-1])                                                        # cut sample "0|"
+        check_block(codec, body[:-2])
+        check_block(codec, body[:-3])                                                        # ends with a tab
 
 
 def test_ragged_and_empty_inputs(any_path):

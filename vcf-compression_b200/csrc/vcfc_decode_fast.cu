@@ -316,6 +316,19 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
                 // and what the bytes add up to when every one of them is a run token
                 const bool is_last = off + nb == tn;
                 const int nbv = nb - (is_last ? 1 : 0);                  // the line's final '\n' carries no text
+                if (nb == 16 && !is_last) {                              // a full chunk inside the line (most are): no byte masks
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t w = v[j];
+                        const uint32_t lm = w & (w << 1) & (w << 2) & 0x80808080u;
+                        const uint32_t am = lm | zero_bytes(w ^ 0x09090909u) | zero_bytes(w ^ 0x0A0A0A0Au);
+                        lit_any |= lm;
+                        if (am) { set_any = am; set_lit = lm; }
+                        const uint32_t cv = w & (0x7F7F7F7Fu ^ (((w >> 7) & 0x01010101u) * 0x60u));
+                        run_sum = __dp4a(cv, 0x01010101u, run_sum);
+                        run_zero |= zero_bytes(cv);
+                    }
+                } else
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int nj = nb - 4 * j, njv = nbv - 4 * j;
@@ -376,6 +389,7 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
 // that line's sample text, the chunk that holds the tile's first byte: a long line is then staged from that chunk
 // on instead of from its start (kWholeLine otherwise).
 constexpr unsigned kWholeLine = 0xFFFFFFFFu;
+constexpr int kReqDirect = 2048;          // required sections longer than this are copied from global memory, not staged
 __global__ void k_dec_tilemap(const unsigned long long* __restrict__ off, unsigned long long n_lines, unsigned long long total,
                               const unsigned long long* __restrict__ line_start, const unsigned* __restrict__ rq_arr,
                               const unsigned* __restrict__ gtab, unsigned int* __restrict__ first_line,
@@ -392,6 +406,7 @@ __global__ void k_dec_tilemap(const unsigned long long* __restrict__ off, unsign
         first_line[t] = (unsigned int)k;
         const long long xs = (long long)(t * tile - a) - rq;          // text offset of the tile start inside the sample text
         unsigned fc = kWholeLine;
+        if (xs < 0 && 8 + rq > kReqDirect) fc = 0u;                   // a long required section is not staged: tokens from chunk 0
         if (xs >= 0) {
             int lo = 0, hi = nch;
             while (hi - lo > 1) { int mid = (lo + hi) >> 1; if ((long long)(tab[mid] >> 1) <= xs) lo = mid; else hi = mid; }
@@ -578,8 +593,12 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
             const int avail = min(sm.l_coff[li + 1], staged) - coff;  // staged bytes of this line
             const int tpos = lpos + rq;                               // tile position of the first sample's text
             int sp = g_lo;
-            // required section passes through (compress.cpp:788-807)
-            for (; sp < g_hi && sp < tpos; sp++) wr.byte(lp[8 + (sp - lpos)]);
+            // required section passes through (compress.cpp:788-807); one that is not (wholly) staged comes from global memory
+            {
+                const uint8_t* rqp = lp + 8;
+                if (cont || 8 + rq > avail) rqp = in + (li == 0 ? line_start[k0] : c_lo + (unsigned long long)coff) + 8;
+                for (; sp < g_hi && sp < tpos; sp++) wr.byte(rqp[sp - lpos]);
+            }
             if (sp < g_hi) {
                 const int cbase = cont ? c_first : 0;                 // first chunk whose table entry is in smem
                 const unsigned* tab = sm.ctab + (coff >> 4) + li - cbase;
@@ -657,6 +676,12 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
 // (16-byte stores, no parsing) and then PATCHED: one thread per 16 token bytes walks its chunk from the chunk table's
 // text offset and writes only what differs -- a '1' for the allele bytes of 0|1 / 1|0 / 1|1 runs, literal payloads --
 // plus the required sections and the line ends.  Work is proportional to the COMPRESSED size of the tile.
+#ifndef VCFC_DEC_FILLPTR
+#define VCFC_DEC_FILLPTR 0
+#endif
+#ifndef VCFC_DEC_RUNDO
+#define VCFC_DEC_RUNDO 0
+#endif
 #ifndef VCFC_DEC_BULK_LD
 #define VCFC_DEC_BULK_LD 1
 #endif
@@ -841,7 +866,14 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
                     const int ph = ((lo << 4) - lp - sm.l_rq[li]) & 3;
                     const uint32_t P = __funnelshift_r(0x09307C30u, 0x09307C30u, 8 * ph);
                     const uint4 P4 = make_uint4(P, P, P, P);
+#if VCFC_DEC_FILLPTR
+                    uint4* q4 = reinterpret_cast<uint4*>(sm.stage) + lo + tid;
+                    uint4* const e4 = reinterpret_cast<uint4*>(sm.stage) + hi;
+#pragma unroll 4
+                    for (; q4 < e4; q4 += kGThreads) *q4 = P4;
+#else
                     for (int u = lo + tid; u < hi; u += kGThreads) *reinterpret_cast<uint4*>(sm.stage + (u << 4)) = P4;
+#endif
                 }
             } else {
                 int li = 0;
@@ -862,10 +894,14 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
         // (5) patch: required sections and line ends (one warp per line) ...
         for (int li = warp; li < nb; li += kGWarps) {
             const int lpos = sm.l_pos[li], rq = sm.l_rq[li];
-            if (!(li == 0 && c_first >= 0)) {
-                const uint8_t* lp = sm.cbuf + phase + sm.l_coff[li];
+            if (!(li == 0 && contd)) {                                // (a continued line's required section is already there)
+                const bool cont0 = li == 0 && c_first >= 0;
+                const uint8_t* lp = sm.cbuf + phase + sm.l_coff[li] + 8;
+                // not (wholly) staged -- a long required section, or a line staged from its tokens on: from global memory
+                if (cont0 || 8 + rq > min(sm.l_coff[li + 1], staged) - sm.l_coff[li])
+                    lp = in + (li == 0 ? line_start[k0] : c_lo + (unsigned long long)sm.l_coff[li]) + 8;
                 const int i_lo = lpos < 0 ? -lpos : 0, i_hi = min(rq, tile_len - lpos);
-                for (int i = i_lo + lane; i < i_hi; i += 32) sm.stage[lpos + i] = lp[8 + i];
+                for (int i = i_lo + lane; i < i_hi; i += 32) sm.stage[lpos + i] = lp[i];
             }
             const int last = sm.l_last[li];
             if (lane == 0 && last >= 0 && last < tile_len) sm.stage[last] = '\n';
@@ -942,10 +978,19 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
                                 const uint32_t f = b & 0xE0u;
                                 const bool a1 = f != kTok01, b1 = f != kTok10;
                                 const int cnt = (int)(b & 0x1Fu);
+#if VCFC_DEC_RUNDO
+                                const int pe = pos + 4 * cnt;                 // (cnt >= 1: k_dec_sizes rejects empty runs)
+                                do {
+                                    if (a1 && (unsigned)pos < (unsigned)tile_len) sm.stage[pos] = '1';
+                                    if (b1 && (unsigned)(pos + 2) < (unsigned)tile_len) sm.stage[pos + 2] = '1';
+                                    pos += 4;
+                                } while (pos != pe);
+#else
                                 for (int q = 0; q < cnt; q++, pos += 4) {
                                     if (a1 && (unsigned)pos < (unsigned)tile_len) sm.stage[pos] = '1';
                                     if (b1 && (unsigned)(pos + 2) < (unsigned)tile_len) sm.stage[pos + 2] = '1';
                                 }
+#endif
                             }
                         }
                     }

@@ -2,7 +2,7 @@
 //
 // "Regular" = what a GT-only VCF looks like: '\n'-terminated lines, single tabs, >= 10 columns,
 // every sample column exactly 3 bytes (a|b, a/b, ./. ...), required section (CHROM..FORMAT) of
-// at most kMaxReq bytes.  Anything else sets
+// at most kMaxReq bytes (~32 KB: long REF / ALT / INFO columns stay on this path).  Anything else sets
 // ctrl->irregular and the caller reruns the block on the generic kernels (vcfc_generic.cu).
 // Output bytes are those of compress_data_line (/root/reference/src/compress.cpp:5-203) for every line.
 //
@@ -32,7 +32,7 @@
 namespace vcfc {
 namespace enc {
 
-constexpr int kHalo = 1024;             // how far around a nominal tile boundary a cut point is searched
+constexpr int kHalo = 32768;            // how far around a nominal tile boundary a cut point is searched
 constexpr int kMaxReq = kHalo - 64;     // longest required section taken by this path
 constexpr int kMaxNl = 62;              // line starts per log segment (every lane keeps the offsets of two lines)
 
@@ -62,7 +62,7 @@ __device__ long long cut_find(const uint8_t* __restrict__ win, long long wbase, 
     long long p = -1;
     uint32_t sepc = 0;
     long long lim = b - 1 + kMaxReq;
-    for (long long base = b - 1; base < lim; base += 32) {
+    for (long long base = b - 1; base < lim && base < vhi; base += 32) {
         long long g = base + lane;
         uint32_t c = g < vhi ? win[g - wbase] : 0u;
         unsigned m = __ballot_sync(0xffffffffu, is_sep(c));
@@ -73,7 +73,11 @@ __device__ long long cut_find(const uint8_t* __restrict__ win, long long wbase, 
             break;
         }
     }
-    if (p < 0) { *kind = kCutBad; return b; }
+    if (p < 0) {
+        if (vhi >= n && b - 1 + kMaxReq >= n) { *kind = kCutEnd; return n; }   // no unit starts between b and the end of the input
+        *kind = kCutBad;
+        return b;
+    }
     if (sepc == '\n') { *kind = p >= n ? kCutEnd : kCutLine; return p; }
     // backward from p-1 (a tab): count tabs until a newline, the buffer start, or 10 tabs
     int k = 0;
@@ -254,6 +258,39 @@ __device__ __noinline__ void flush_segment(const uint8_t* __restrict__ stage, in
     __syncwarp();
 }
 
+// A line start whose required section does not fit the staging area: a segment of its own, copied from the input
+// (two length headers + rq bytes; one line start at tile offset o).  Rare, byte-wise.
+__device__ __noinline__ void flush_line_start(const uint8_t* __restrict__ src, int rq, int o, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
+                                              unsigned long long log_cap, int lane, unsigned long long* seg_first,
+                                              unsigned long long* seg_prev, bool* dead) {
+    const int nbytes = 8 + rq, body = (nbytes + 15) & ~15;
+    const unsigned long long need = 16ull + (unsigned long long)body + 16ull;
+    unsigned long long pos = 0ull;
+    if (lane == 0 && !*dead) {
+        pos = atomicAdd(&ctrl->log_cursor, need);
+        if (pos + need > log_cap) { atomicExch(&ctrl->cap_exceeded, 1); pos = ~0ull; }
+    }
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (*dead || pos == ~0ull) { *dead = true; return; }
+    uint8_t* const dst = log + pos;
+    if (lane == 0) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4((unsigned)nbytes, 1u, 0u, 0u);
+        if (*seg_prev) *reinterpret_cast<unsigned long long*>(log + (*seg_prev - 1ull) + 8) = pos;
+        *reinterpret_cast<uint32_t*>(dst + 16 + body) = (uint32_t)o;
+    }
+    uint8_t* d = dst + 16;
+    if (lane < 4) d[lane] = lane == 0 ? 0xC0 : 0;                       // line length: patched by k_patch_headers
+    if (lane >= 4 && lane < 8) {
+        const unsigned v = (unsigned)rq;
+        d[lane] = lane == 4 ? (uint8_t)((v >> 24) | 0xC0) : (uint8_t)(v >> (8 * (7 - lane)));
+    }
+    for (int k = lane; k < rq; k += 32) d[8 + k] = src[k];
+    for (int k = nbytes + lane; k < body + 4; k += 32) if (k < body) d[k] = 0;   // (padding: the gather reads whole words)
+    if (!*seg_first) *seg_first = pos + 1ull;
+    *seg_prev = pos + 1ull;
+    __syncwarp();
+}
+
 // ---- the streaming kernel: one warp per tile -------------------------------------------------------------------------
 #ifndef VCFC_ENC_TICKET
 #define VCFC_ENC_TICKET 1
@@ -281,7 +318,7 @@ constexpr int kStep = 2048;                     // bytes per step: 32 lanes x 64
 constexpr int kBackRows = 4;                    // rows of 512 bytes per round trip of the look-back's coarse search
 constexpr int kStepMaxOut = 2576;               // most bytes one step can emit: 512 literals of 5 bytes, a chunk token, the line end
 static_assert(kSTile % 64 == 0, "tiles start on block boundaries");
-static_assert(kSStage % 16 == 0 && kSStage >= kStepMaxOut + 512 && kSStage >= 8 + kMaxReq, "a step or a line start must fit the staging area");
+static_assert(kSStage % 16 == 0 && kSStage >= kStepMaxOut + 512, "a step must fit the staging area (a long line start goes to the log directly)");
 
 struct SmemS {
     alignas(16) uint8_t stage[kSWarps][kSStage + 16];
@@ -290,6 +327,10 @@ struct SmemS {
 // byte / word of the input at tile-relative offset r (win = in + gb); outside [0, n) reads as 0
 __device__ __forceinline__ uint32_t ldb(const uint8_t* __restrict__ win, int r, int r_lo, int r_hi) {
     return (r >= r_lo && r < r_hi) ? win[r] : 0u;
+}
+// the same with the bytes behind the input reading as '\n': a last line without a newline ends at EOF (compress.cpp:218 getline)
+__device__ __forceinline__ uint32_t ldb_nl(const uint8_t* __restrict__ win, int r, int r_lo, int r_hi) {
+    return r >= r_hi ? (uint32_t)'\n' : (r >= r_lo ? win[r] : 0u);
 }
 // (the byte-wise form is needed at the first / last bytes of the input only; inlined at every use it was a quarter of the kernel's code)
 __device__ __noinline__ uint32_t ldw_edge(const uint8_t* __restrict__ win, int r, int r_lo, int r_hi, uint32_t fill) {
@@ -501,7 +542,6 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
             if (pr + 128 <= r_hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(win + pr));
             if (pr + 4096 + 128 <= r_hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(win + pr + 4096));
         }
-        if (t0 + tile_sz >= n && in[n - 1] != '\n') irregular = 1;        // no final newline: generic path
         const int ke = fl & 15, lb_lc = (fl >> 4) & 15, lb_uniform = (fl >> 8) & 1, lb_nsamp = (ce - 64) >> 2;
         if (ke == kCutBad) irregular = 2;
         int ks, cs;
@@ -533,9 +573,19 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                     const int s0 = line_scan16(win, ls, r_lo, r_hi, lane);
                     if (s0 < 0) { irregular = 4; break; }
                     const int rq = s0 - ls;
-                    if (o - flushed + 8 + rq > kSStage || nl_seg >= kMaxNl) {
+                    if ((o - flushed + 8 + rq > kSStage || nl_seg >= kMaxNl) && (o > flushed || nl_seg > 0)) {
                         flush_segment(stage, o - flushed, log, ctrl, log_cap, lane, &seg_first, &seg_prev, &dead, nl_seg, my_off, my_off2);
                         flushed = o; nl_seg = 0;
+                    }
+                    if (8 + rq > kSStage) {
+                        // a required section longer than the staging area (long REF / ALT / INFO): its own segment, input -> log
+                        flush_line_start(win + ls, rq, o, log, ctrl, log_cap, lane, &seg_first, &seg_prev, &dead);
+                        nl++;
+                        o += 8 + rq;
+                        flushed = o;
+                        cur = s0;
+                        in_req = false; first = true; ein_carry = kNoHead;
+                        continue;
                     }
                     {
                         uint8_t* d = stage + (o - flushed);
@@ -632,7 +682,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                         if (look) {
                             const int k = __ffs(rem) - 1;
                             rem &= rem - 1;
-                            if (ldb(win, base + 4 * k + 3, r_lo, r_hi) == '\n') { kend = k; rem = 0u; }
+                            if (ldb_nl(win, base + 4 * k + 3, r_lo, r_hi) == '\n') { kend = k; rem = 0u; }
                         }
                         endm = __ballot_sync(0xffffffffu, kend >= 0);
                         if (endm) le = __ffs(endm) - 1;
@@ -644,9 +694,15 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                     bool irr = false;
                     for (uint32_t t = V & ~Craw; t; t &= t - 1) {
                         const int k = __ffs(t) - 1;
-                        const uint8_t* p = win + base + 4 * k;
-                        const bool inside = base + 4 * k >= r_lo && base + 4 * k + 4 <= r_hi;
-                        const uint32_t b0 = inside ? p[0] : 0u, b1 = inside ? p[1] : 0u, b2 = inside ? p[2] : 0u, b3 = inside ? p[3] : 0u;
+                        const int r0 = base + 4 * k;
+                        uint32_t b0, b1, b2, b3;
+                        if (r0 >= r_lo && r0 + 4 <= r_hi) {
+                            const uint8_t* p = win + r0;
+                            b0 = p[0]; b1 = p[1]; b2 = p[2]; b3 = p[3];
+                        } else {                                  // the input's first / last bytes
+                            b0 = ldb_nl(win, r0, r_lo, r_hi); b1 = ldb_nl(win, r0 + 1, r_lo, r_hi); b2 = ldb_nl(win, r0 + 2, r_lo, r_hi);
+                            b3 = ldb_nl(win, r0 + 3, r_lo, r_hi);
+                        }
                         if (k == kend ? (b3 != '\n') : (b3 != '\t')) irr = true;
                         if (b1 == '|' && (b0 & 0xFEu) == 0x30u && (b2 & 0xFEu) == 0x30u) {
                             Craw |= 1u << k;           // coded sample terminated by the line's newline
@@ -713,6 +769,8 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 if (endm) { cur = q_end + 1; in_req = true; }
                 else cur = a + 4 * ((bound - a + 3) >> 2);
             }
+            // the input ends inside a line that no newline-less last sample closed (a trailing tab, a cut sample): generic path
+            if (!irregular && ke == kCutEnd && cs < ce && !in_req) irregular = 1;
             // ---- the tile's last segment, followed by the u32 line offsets; the final position comes from the scan over the
             //      tile records (k_gather_tiles follows the segment chain) ------------------------------------------------------
             if (irregular) {
@@ -762,8 +820,9 @@ __global__ void k_gather_tiles(const uint8_t* __restrict__ log, uint8_t* __restr
         lbase += nls;
         dst += size;
         remaining -= size;
-        if (remaining <= 0 || size <= 0) break;
+        if (remaining <= 0) break;
         pos = (unsigned long long)hdr.z | ((unsigned long long)hdr.w << 32);
+        if (pos == 0ull && size == 0) break;                   // (a broken chain: never in a block that passed the checks)
     }
 }
 
@@ -841,7 +900,7 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
     int rc = dev_reserve(ctx, &ws, total_ws);
     if (rc) return rc;
     // the log holds the output once, plus per segment a 16-byte header and padding, plus 4 bytes per line start
-    const size_t log_cap = out_cap + 4 * lines_cap + 48 * (n_tiles + out_cap / (kSStage - kStepMaxOut) + lines_cap / kMaxNl + 2) + 64;
+    const size_t log_cap = out_cap + 4 * lines_cap + 48 * (n_tiles + out_cap / (kSStage - kStepMaxOut) + lines_cap / kMaxNl + 2 * (in_len / kSStage) + 4) + 64;
     if ((rc = dev_reserve(ctx, &b_log, log_cap + 64))) return rc;
     uint8_t* base = (uint8_t*)ws.p;
     Ctrl* ctrl = (Ctrl*)base;
