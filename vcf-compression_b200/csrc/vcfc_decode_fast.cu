@@ -261,125 +261,146 @@ __device__ __forceinline__ void chunk_measure(const uint8_t* b, int nb, bool pay
     *out_len = o; *samples = ns; *err = e; *tres = tr;
 }
 
-// ---- D2: per-line validation and text size (one warp per line) ----------------------------------------------
+// ---- D2: per-line validation and text size.  kSzGroup lanes per line (four lines per warp): most token regions of a sparse
+//      file are shorter than 128 bytes, so a whole warp per line would leave most lanes idle -------------------------------------
+#ifndef VCFC_DEC_SZGROUP
+#define VCFC_DEC_SZGROUP 16
+#endif
+constexpr int kSzGroup = VCFC_DEC_SZGROUP;                       // 8, 16 or 32 lanes per line
+constexpr int kSzLines = 32 / kSzGroup;
 __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ line_start,
                             unsigned long long n_lines, unsigned long long sample_count, unsigned long long* __restrict__ sizes,
                             unsigned* __restrict__ ctab, unsigned* __restrict__ rq_arr, Ctrl* __restrict__ ctrl) {
-    const unsigned long long k = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (k >= n_lines) return;
-    const unsigned long long ls = line_start[k], le = line_start[k + 1];
+    const unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, gl = lane & (kSzGroup - 1), g0 = lane & ~(kSzGroup - 1);
+    const unsigned gmask = (kSzGroup == 32 ? 0xFFFFFFFFu : ((1u << kSzGroup) - 1u)) << g0;
+    const unsigned long long k = w * kSzLines + (unsigned long long)(lane / kSzGroup);
+    const bool live = k < n_lines;
+    const unsigned long long ls = live ? line_start[k] : 0ull, le = live ? line_start[k + 1] : 0ull;
     const uint8_t* p = in + ls;
     const long long clen = (long long)(le - ls);
-    const long long rq = (long long)(int)rq_arr[k];          // second length header, read by k_dec_fill (-1: bad tag)
+    const long long rq = live ? (long long)(int)rq_arr[k] : 0ll;   // second length header, read by k_dec_fill (-1: bad tag)
     bool bad = rq < 1 || rq + 9 > clen || clen > 0x7fffffffll;
-    if (lane == 0) rq_arr[k] = (unsigned)(bad ? 0 : rq);
+    if (live && gl == 0) rq_arr[k] = (unsigned)(bad ? 0 : rq);
     // required section: exactly 9 tabs (compress.cpp:820-828; the 8-tab form means no samples -> generic path)
     unsigned tabs = 0;
-    if (!bad) {
-        for (long long o4 = 4ll * lane; o4 < rq; o4 += 128) {          // four bytes per lane: aligned loads, funnel-shifted
-            const uintptr_t ga = reinterpret_cast<uintptr_t>(p + 8 + o4);
-            const uint32_t* wp = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
-            const int nv = (int)(rq - o4 < 4 ? rq - o4 : 4);
-            const uint32_t w0 = wp[0], w1 = (nv + (int)(ga & 3) > 4) ? wp[1] : 0u;
-            const uint32_t v = __funnelshift_r(w0, w1, 8 * (int)(ga & 3));
-            const uint32_t bm = nv >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nv)) - 1u);
-            tabs += __popc(zero_bytes((v ^ 0x09090909u) | ~bm));
-        }
-    }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) tabs += __shfl_xor_sync(0xffffffffu, tabs, d);
-    if (tabs != 9) bad = true;
-    unsigned long long total = 0, ns_total = 0;
-    if (!bad) {
-        const long long tb = 8 + rq, tn = clen - tb;            // token region, its last byte is the line's '\n'
-        int carry_kind = 0;                                     // last setter seen so far (0 = none: token state)
-        int err_any = 0, off_grid = rq < 16 ? 1 : 0;
-        for (long long base = 0; base < tn; base += 512) {
-            const long long off = base + 16ll * lane;
-            int nb = (int)(tn - off);
-            nb = nb < 0 ? 0 : (nb > 16 ? 16 : nb);
-            uint8_t b[16];
-            uint32_t lit_any = 0, set_any = 0, set_lit = 0, run_sum = 0, run_zero = 0;
-            if (nb > 0) {       // five aligned 32-bit loads instead of sixteen byte loads; bytes past the line are never used
-                const uintptr_t ga = reinterpret_cast<uintptr_t>(p + tb + off);
+    {
+        const long long rqv = (live && !bad) ? rq : 0ll;
+        for (long long o16 = 16ll * gl; __any_sync(0xffffffffu, o16 < rqv); o16 += 16 * kSzGroup) {   // sixteen bytes per lane
+            if (o16 < rqv) {
+                const uintptr_t ga = reinterpret_cast<uintptr_t>(p + 8 + o16);
                 const uint32_t* wp = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
-                const int sh = 8 * (int)(ga & 3);
-                const int nwd = (nb + (int)(ga & 3) + 3) >> 2;          // aligned words that hold the chunk's nb bytes
-                uint32_t w0 = wp[0], w1 = nwd > 1 ? wp[1] : 0u, w2 = nwd > 2 ? wp[2] : 0u, w3 = nwd > 3 ? wp[3] : 0u,
-                         w4 = nwd > 4 ? wp[4] : 0u;
+                const int nv = (int)(rqv - o16 < 16 ? rqv - o16 : 16), sh = 8 * (int)(ga & 3);
+                const int nwd = (nv + (int)(ga & 3) + 3) >> 2;
+                const uint32_t w0 = wp[0], w1 = nwd > 1 ? wp[1] : 0u, w2 = nwd > 2 ? wp[2] : 0u, w3 = nwd > 3 ? wp[3] : 0u,
+                               w4 = nwd > 4 ? wp[4] : 0u;
                 const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
                                        __funnelshift_r(w3, w4, sh)};
 #pragma unroll
-                for (int i = 0; i < 16; i++) b[i] = (uint8_t)(v[i >> 2] >> (8 * (i & 3)));
-                // word-parallel view of the chunk: is there any literal marker (>= 0xE0) or tab / newline among its bytes,
-                // and what the bytes add up to when every one of them is a run token
-                const bool is_last = off + nb == tn;
-                const int nbv = nb - (is_last ? 1 : 0);                  // the line's final '\n' carries no text
-                if (nb == 16 && !is_last) {                              // a full chunk inside the line (most are): no byte masks
+                for (int j = 0; j < 4; j++) {
+                    const int nj = nv - 4 * j;
+                    const uint32_t bm = nj >= 4 ? 0xFFFFFFFFu : (nj <= 0 ? 0u : ((1u << (8 * nj)) - 1u));
+                    tabs += __popc(zero_bytes((v[j] ^ 0x09090909u) | ~bm));
+                }
+            }
+        }
+    }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t w = v[j];
-                        const uint32_t lm = w & (w << 1) & (w << 2) & 0x80808080u;
-                        const uint32_t am = lm | zero_bytes(w ^ 0x09090909u) | zero_bytes(w ^ 0x0A0A0A0Au);
-                        lit_any |= lm;
-                        if (am) { set_any = am; set_lit = lm; }
-                        const uint32_t cv = w & (0x7F7F7F7Fu ^ (((w >> 7) & 0x01010101u) * 0x60u));
-                        run_sum = __dp4a(cv, 0x01010101u, run_sum);
-                        run_zero |= zero_bytes(cv);
-                    }
-                } else
+    for (int d = kSzGroup / 2; d; d >>= 1) tabs += __shfl_xor_sync(0xffffffffu, tabs, d);
+    if (tabs != 9) bad = true;
+    unsigned long long total = 0, ns_total = 0;
+    const long long tb = 8 + rq, tn = (live && !bad) ? clen - tb : 0ll;   // token region, its last byte is the line's '\n'
+    int carry_kind = 0;                                         // last setter seen so far (0 = none: token state)
+    int err_any = 0, off_grid = (live && !bad && rq < 16) ? 1 : 0;
+    for (long long base = 0; __any_sync(0xffffffffu, base < tn); base += 16 * kSzGroup) {
+        const long long off = base + 16ll * gl;
+        int nb = (int)(tn - off < 0 ? 0 : (tn - off > 16 ? 16 : tn - off));
+        if (base >= tn) nb = 0;
+        uint8_t b[16];
+        uint32_t lit_any = 0, set_any = 0, set_lit = 0, run_sum = 0, run_zero = 0;
+        if (nb > 0) {       // five aligned 32-bit loads instead of sixteen byte loads; bytes past the line are never used
+            const uintptr_t ga = reinterpret_cast<uintptr_t>(p + tb + off);
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
+            const int sh = 8 * (int)(ga & 3);
+            const int nwd = (nb + (int)(ga & 3) + 3) >> 2;          // aligned words that hold the chunk's nb bytes
+            uint32_t w0 = wp[0], w1 = nwd > 1 ? wp[1] : 0u, w2 = nwd > 2 ? wp[2] : 0u, w3 = nwd > 3 ? wp[3] : 0u,
+                     w4 = nwd > 4 ? wp[4] : 0u;
+            const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                                   __funnelshift_r(w3, w4, sh)};
+#pragma unroll
+            for (int i = 0; i < 16; i++) b[i] = (uint8_t)(v[i >> 2] >> (8 * (i & 3)));
+            // word-parallel view of the chunk: is there any literal marker (>= 0xE0) or tab / newline among its bytes,
+            // and what the bytes add up to when every one of them is a run token
+            const bool is_last = off + nb == tn;
+            const int nbv = nb - (is_last ? 1 : 0);                  // the line's final '\n' carries no text
+            if (nb == 16 && !is_last) {                              // a full chunk inside the line (most are): no byte masks
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t wv = v[j];
+                    const uint32_t lm = wv & (wv << 1) & (wv << 2) & 0x80808080u;
+                    const uint32_t am = lm | zero_bytes(wv ^ 0x09090909u) | zero_bytes(wv ^ 0x0A0A0A0Au);
+                    lit_any |= lm;
+                    if (am) { set_any = am; set_lit = lm; }
+                    const uint32_t cv = wv & (0x7F7F7F7Fu ^ (((wv >> 7) & 0x01010101u) * 0x60u));
+                    run_sum = __dp4a(cv, 0x01010101u, run_sum);
+                    run_zero |= zero_bytes(cv);
+                }
+            } else {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int nj = nb - 4 * j, njv = nbv - 4 * j;
                     const uint32_t bm = nj >= 4 ? 0xFFFFFFFFu : (nj <= 0 ? 0u : ((1u << (8 * nj)) - 1u));
                     const uint32_t bmv = njv >= 4 ? 0xFFFFFFFFu : (njv <= 0 ? 0u : ((1u << (8 * njv)) - 1u));
-                    const uint32_t w = v[j];
-                    const uint32_t lm = w & (w << 1) & (w << 2) & 0x80808080u & bm;                       // bytes >= 0xE0
-                    const uint32_t am = lm | ((zero_bytes(w ^ 0x09090909u) | zero_bytes(w ^ 0x0A0A0A0Au)) & bm);   // ... or tab / newline
+                    const uint32_t wv = v[j];
+                    const uint32_t lm = wv & (wv << 1) & (wv << 2) & 0x80808080u & bm;                       // bytes >= 0xE0
+                    const uint32_t am = lm | ((zero_bytes(wv ^ 0x09090909u) | zero_bytes(wv ^ 0x0A0A0A0Au)) & bm);   // ... or tab / newline
                     lit_any |= lm;
                     if (am) { set_any = am; set_lit = lm; }                                             // the highest word that has a setter
-                    const uint32_t cv = w & (0x7F7F7F7Fu ^ (((w >> 7) & 0x01010101u) * 0x60u)) & bmv;     // run lengths
+                    const uint32_t cv = wv & (0x7F7F7F7Fu ^ (((wv >> 7) & 0x01010101u) * 0x60u)) & bmv;     // run lengths
                     run_sum = __dp4a(cv, 0x01010101u, run_sum);
                     run_zero |= zero_bytes(cv | ~bmv);
                 }
             }
-            // kind of the chunk's last setter: 1 = a byte >= 0xE0, 2 = tab / newline (kinds of setter above)
-            const int kind = set_any ? (((set_lit >> (31 - __clz(set_any))) & 1u) ? 1 : 2) : 0;
-            // state at chunk start: last setter of the nearest lower lane that has one, else the carry
-            const unsigned has = __ballot_sync(0xffffffffu, kind != 0);
-            const unsigned below = has & ((1u << lane) - 1u);
-            const int src = below ? 31 - __clz(below) : 0;
-            const int k_src = __shfl_sync(0xffffffffu, kind, src);
-            const int k_in = below ? k_src : carry_kind;
-            unsigned o = 0, ns = 0, tres = 0;
-            int e = 0;
-            if (nb > 0) {
-                if (k_in != 1 && !lit_any) { o = 4u * run_sum; ns = run_sum; e = run_zero ? 1 : 0; }   // run tokens only
-                else chunk_measure(b, nb, k_in == 1, off + nb == tn, &o, &ns, &e, &tres);
-            }
-            err_any |= e;
-            // chunk table (text offset << 1 | payload state at the chunk's first byte), consumed by k_dec_expand;
-            // line k owns the slots [(ls >> 4) + k, ...): disjoint between lines, <= clen / 16 + 1 of them
-            unsigned inc = o, n32 = ns;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                unsigned t = __shfl_up_sync(0xffffffffu, inc, d), u = __shfl_up_sync(0xffffffffu, n32, d);
-                if (lane >= d) { inc += t; n32 += u; }
-            }
-            if (nb > 0) ctab[(ls >> 4) + k + (unsigned long long)(off >> 4)] = (((unsigned)total + inc - o) << 1) | (k_in == 1 ? 1u : 0u);
-            // every literal must end on the 4-byte sample grid for the fill-and-patch kernel (k_dec_expand_grid)
-            if (tres & ~(1u << ((4u - ((unsigned)total + inc - o)) & 3u))) off_grid = 1;
-            total += __shfl_sync(0xffffffffu, inc, 31);
-            ns_total += __shfl_sync(0xffffffffu, n32, 31);
-            if (has) carry_kind = __shfl_sync(0xffffffffu, kind, 31 - __clz(has));
         }
-        err_any = __any_sync(0xffffffffu, err_any);
-        if (__any_sync(0xffffffffu, off_grid) && lane == 0) atomicExch(&ctrl->not_grid, 1);
-        if (err_any || ns_total != sample_count) bad = true;
+        // kind of the chunk's last setter: 1 = a byte >= 0xE0, 2 = tab / newline (kinds of setter above)
+        const int kind = set_any ? (((set_lit >> (31 - __clz(set_any))) & 1u) ? 1 : 2) : 0;
+        // state at chunk start: last setter of the nearest lower lane of the group that has one, else the carry
+        const unsigned has = __ballot_sync(0xffffffffu, kind != 0) & gmask;
+        const unsigned below = has & ((1u << lane) - 1u);
+        const int src = below ? 31 - __clz(below) : lane;
+        const int k_src = __shfl_sync(0xffffffffu, kind, src);
+        const int k_in = below ? k_src : carry_kind;
+        unsigned o = 0, ns = 0, tres = 0;
+        int e = 0;
+        if (nb > 0) {
+            if (k_in != 1 && !lit_any) { o = 4u * run_sum; ns = run_sum; e = run_zero ? 1 : 0; }   // run tokens only
+            else chunk_measure(b, nb, k_in == 1, off + nb == tn, &o, &ns, &e, &tres);
+        }
+        err_any |= e;
+        // chunk table (text offset << 1 | payload state at the chunk's first byte), consumed by k_dec_expand;
+        // line k owns the slots [(ls >> 4) + k, ...): disjoint between lines, <= clen / 16 + 1 of them
+        unsigned inc = o, n32 = ns;
+#pragma unroll
+        for (int d = 1; d < kSzGroup; d <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, inc, d, kSzGroup), u = __shfl_up_sync(0xffffffffu, n32, d, kSzGroup);
+            if (gl >= d) { inc += t; n32 += u; }
+        }
+        if (nb > 0) ctab[(ls >> 4) + k + (unsigned long long)(off >> 4)] = (((unsigned)total + inc - o) << 1) | (k_in == 1 ? 1u : 0u);
+        // every literal must end on the 4-byte sample grid for the fill-and-patch kernel (k_dec_expand_grid)
+        if (tres & ~(1u << ((4u - ((unsigned)total + inc - o)) & 3u))) off_grid = 1;
+        total += __shfl_sync(0xffffffffu, inc, g0 + kSzGroup - 1);
+        ns_total += __shfl_sync(0xffffffffu, n32, g0 + kSzGroup - 1);
+        const int k_last = __shfl_sync(0xffffffffu, kind, has ? 31 - __clz(has) : lane);
+        if (has) carry_kind = k_last;
+    }
+    const unsigned eg = __ballot_sync(0xffffffffu, err_any != 0) & gmask;
+    if (live && !bad) {
+        if (eg || ns_total != sample_count) bad = true;
         total += (unsigned long long)rq;
     }
-    if (lane == 0) {
+    const unsigned og = __ballot_sync(0xffffffffu, off_grid != 0) & gmask;
+    if (live && gl == 0) {
+        if (og && !bad) atomicExch(&ctrl->not_grid, 1);
         sizes[k] = bad ? 0ull : total;
         if (bad) atomicExch(&ctrl->irregular, 1);
     }
@@ -1098,7 +1119,7 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
     if ((rc = dev_reserve(ctx, &b_rq, (n_lines + 2) * 4))) return rc;
     unsigned long long* line_start = (unsigned long long*)b_ls.p;
     k_dec_fill<<<gs, 128, 0, stream>>>(d_in, n, n_seg, cand, base, line_start, (unsigned*)b_rq.p, n_lines, ctrl);
-    k_dec_sizes<<<(unsigned)((n_lines * 32 + 127) / 128), 128, 0, stream>>>(d_in, line_start, n_lines, sample_count,
+    k_dec_sizes<<<(unsigned)(((n_lines + kSzLines - 1) / kSzLines * 32 + 127) / 128), 128, 0, stream>>>(d_in, line_start, n_lines, sample_count,
                                                                              (unsigned long long*)b_sizes.p, (unsigned*)b_tab.p, (unsigned*)b_rq.p, ctrl);
     ctx->launches += 2;
     if ((rc = scan_exclusive_u64(ctx, (uint64_t*)b_sizes.p, (uint64_t*)b_offs.p, (size_t)n_lines, (uint64_t*)&ctrl->total_out, &b_scr, stream)))
