@@ -697,6 +697,9 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
 // (16-byte stores, no parsing) and then PATCHED: one thread per 16 token bytes walks its chunk from the chunk table's
 // text offset and writes only what differs -- a '1' for the allele bytes of 0|1 / 1|0 / 1|1 runs, literal payloads --
 // plus the required sections and the line ends.  Work is proportional to the COMPRESSED size of the tile.
+#ifndef VCFC_DEC_ASYNC_TAB
+#define VCFC_DEC_ASYNC_TAB 0
+#endif
 #ifndef VCFC_DEC_FILLPTR
 #define VCFC_DEC_FILLPTR 0
 #endif
@@ -872,7 +875,12 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
             const unsigned long long lsk = li == 0 ? line_start[k0] : c_lo + (unsigned long long)coff;
             const unsigned* src = gtab + (lsk >> 4) + (k0 + (unsigned long long)li) + (li == 0 && c_first >= 0 ? c_first : 0);
             unsigned* tab = sm.ctab + (coff >> 4) + li;
+#if VCFC_DEC_ASYNC_TAB
+            for (int i = lane; i < nslots; i += 32)      // asynchronous 4-byte copies: nobody waits for them before the fill
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(tab + i)), "l"(src + i) : "memory");
+#else
             for (int i = lane; i < nslots; i += 32) tab[i] = src[i];
+#endif
         }
         // (4) fill: every 16-byte unit that starts inside the batch's lines gets "0|0\t" in the phase of its line
         {
@@ -907,6 +915,9 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
                 }
             }
         }
+#if VCFC_DEC_ASYNC_TAB
+        asm volatile("cp.async.wait_all;" ::: "memory");   // this thread's chunk-table copies (the barrier below publishes them)
+#endif
 #if VCFC_DEC_BULK_LD
         mbar_wait(&sm.bar, parity);                        // the compressed bytes have landed
         parity ^= 1u;

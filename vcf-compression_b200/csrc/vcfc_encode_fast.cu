@@ -304,7 +304,7 @@ __device__ __noinline__ void flush_line_start(const uint8_t* __restrict__ src, i
 #ifndef VCFC_ENC_STILE
 #define VCFC_ENC_STILE 32768
 #define VCFC_ENC_SWARPS 4
-#define VCFC_ENC_SCTAS 8
+#define VCFC_ENC_SCTAS 7
 #endif
 #ifndef VCFC_ENC_SSTAGE
 #define VCFC_ENC_SSTAGE 3200
