@@ -356,6 +356,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout, where one JSON line is expected
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():

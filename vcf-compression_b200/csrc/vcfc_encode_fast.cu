@@ -171,13 +171,14 @@ __device__ __forceinline__ uint32_t flag_of(uint32_t y) {
     return __byte_perm(0x80C0A000u, 0u, (c2 >> 15) | c2);           // selector nibble 0 = 2a + b; the other result bytes are not stored
 }
 
+// rare (warp-uniform): some lane of the step has a literal or the line's end
 __device__ __forceinline__ void item_emit(const uint8_t* __restrict__ win, const Item& it, uint32_t cfbit, int h,
-                                          uint8_t* __restrict__ dst) {
+                                          uint8_t* __restrict__ dst, bool rare) {
     const uint32_t tok = it.V ? (it.CL | cfbit) : 0u;
     const uint32_t kendbit = it.kend >= 0 ? (1u << it.kend) : 0u;
     // run tokens only (the common case): a tight loop -- unless many lanes of the warp have literals, then one loop for all
-    const bool many = __popc(__ballot_sync(0xffffffffu, (it.L | kendbit) != 0u)) > 4;
-    if (!(it.L | kendbit) && !many) {
+    const bool many = rare && __popc(__ballot_sync(0xffffffffu, (it.L | kendbit) != 0u)) > 4;
+    if (!rare || (!(it.L | kendbit) && !many)) {
         if (!tok) return;
         // a token's count is the distance to the token below it (to h for the lowest): walk from the top, so one FLO per token
         // finds both the next token and this one's count
@@ -673,7 +674,8 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 unsigned endm = 0;
                 int le = 32;
                 uint32_t L = 0;
-                if (__any_sync(0xffffffffu, (V & ~Craw) != 0u)) {
+                const bool rare = __any_sync(0xffffffffu, (V & ~Craw) != 0u);
+                if (rare) {
                     // in rounds, one candidate sample per lane and round: behind the line's end every sample looks odd, and those
                     // lanes must not walk all of theirs -- only lanes in front of the best newline found so far keep looking
                     for (uint32_t rem = V & ~Craw;;) {
@@ -763,7 +765,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                     flush_segment(stage, o - flushed, log, ctrl, log_cap, lane, &seg_first, &seg_prev, &dead, nl_seg, my_off, my_off2);
                     flushed = o; nl_seg = 0;
                 }
-                item_emit(win, it, cf, h0, stage + (o - flushed + inc - n0));
+                item_emit(win, it, cf, h0, stage + (o - flushed + inc - n0), rare);
                 o += step_total;
                 first = false;
                 if (endm) { cur = q_end + 1; in_req = true; }

@@ -10,12 +10,21 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <string>
 #include <vector>
 
 #include "vcfc_gpu.h"
+
+// VCFC_TRACE=1: wall-clock of the process's stages on stderr (context creation dominates a one-shot CLI run)
+static double t_now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+static const double t_start = t_now();
+static void trace(const char* what) {
+    static const bool on = getenv("VCFC_TRACE") != nullptr;
+    if (on) fprintf(stderr, "[vcfc %8.3f s] %s\n", t_now() - t_start, what);
+}
 
 static int usage() {
     fprintf(stderr,
@@ -69,11 +78,13 @@ int main(int argc, char** argv) {
     if (access(in, F_OK) != 0) printf("Input file does not exist: %s\n", in);   // main.cpp:4040-4042
     int dev = getenv("VCFC_DEVICE") ? atoi(getenv("VCFC_DEVICE")) : 0;
     vcfc_ctx* ctx = nullptr;
+    trace("start");
     int rc = vcfc_gpu_init(dev, &ctx);
     if (rc != VCFC_OK) {
         fprintf(stderr, "vcfc: cannot use CUDA device %d: %s (there is no CPU path)\n", dev, vcfc_strerror(rc));
         return 1;
     }
+    trace("context ready");
     if (action == "query" || action == "query-binned-index") {
         rc = action == "query" ? vcfc_query_file(ctx, in, argv[3], STDOUT_FILENO)
                                : vcfc_query_binned_index_file(ctx, in, argv[3], STDOUT_FILENO);
@@ -104,11 +115,13 @@ int main(int argc, char** argv) {
         }
         for (size_t k = 1; k < ctxs.size(); k++) vcfc_gpu_destroy(ctxs[k]);
     }
+    trace("verb done");
     if (rc != VCFC_OK) {
         fprintf(stderr, "vcfc %s: %s", action.c_str(), vcfc_strerror(rc));
         if (rc == VCFC_E_CUDA) fprintf(stderr, " [%s]", vcfc_last_cuda_error(ctx));
         fprintf(stderr, "\n");
     }
     vcfc_gpu_destroy(ctx);
+    trace("context destroyed");
     return rc == VCFC_OK ? 0 : 1;
 }
