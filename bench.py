@@ -464,10 +464,14 @@ def main():
     # DRAM traffic per launch: measured once per round with `ncu --set full` on a 100k-line run of this same
     # workload (profiles/traffic_r1.json: dram__bytes_read.sum + dram__bytes_write.sum next to that run's
     # algorithmic bytes) and scaled by the algorithmic bytes of this launch; null when the file is absent.
-    try:
-        traffic_ref = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
-    except Exception:  # noqa: BLE001
-        traffic_ref = {}
+    # (profiles/traffic_r2.json is this round's capture.)
+    traffic_ref = {}
+    for tf in ("traffic_r2.json", "traffic_r1.json"):          # the latest round's capture
+        try:
+            traffic_ref = json.load(open(os.path.join(ROOT, "profiles", tf)))
+            break
+        except Exception:  # noqa: BLE001
+            pass
 
     def roofline(kms, alg_bytes, step_ms, name, which):
         k = [x for x in kms if x and x > 0]

@@ -80,9 +80,14 @@ int vcfc_encode_block(vcfc_ctx *ctx, const uint8_t *in, size_t in_len,
                       uint64_t *err_line);
 
 /*
- * Device-pointer form, asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
- * context's stream).  d_result (device memory, sizeof(vcfc_result)) is written by the last
- * tile; read it after synchronising, or call vcfc_fetch_result.
+ * Device-pointer form: all work is queued on `stream` (a cudaStream_t passed as void*; NULL = the
+ * context's stream), input and output stay in device memory, and d_result (device memory,
+ * sizeof(vcfc_result)) is written by the last kernel.  The call is NOT fully asynchronous: before
+ * it returns it synchronises `stream` once to read the block's status, because a block outside the
+ * tile kernels' grammar is rerun on the generic kernels inside the same call (the decode form
+ * synchronises twice more to size its line table and tile map).  When it returns, d_result is
+ * final; read it with vcfc_fetch_result or your own copy.  A context is used by one host thread
+ * at a time; use one context per GPU and per concurrent caller.
  */
 int vcfc_encode_block_dev(vcfc_ctx *ctx, const uint8_t *d_in, size_t in_len,
                           uint8_t *d_out, size_t out_cap,

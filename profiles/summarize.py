@@ -58,7 +58,7 @@ if __name__ == "__main__":
     md = [f"# ncu summaries, {tag}\n"]
     t, n = launches(lpath)
     md.append(f"## Launch list ({n} launches; `--metrics gpu__time_duration.sum --clock-control none`)\n\n{t}\n")
-    md.append("## `--set full` captures of the dominant kernels (100k-line run of the bench workload)")
+    md.append("## `--set full` captures of the dominant kernels (400k-line run of the bench workload: 4.07 GB of text, 0.238 GB of .vcfc)")
     for fpath in sys.argv[4:]:
         md.append(full(fpath))
     md.append("\n## bench.py line of the same build\n\n```json\n" + json.dumps(json.load(open(bpath)), indent=1) + "\n```\n")

@@ -808,13 +808,20 @@ __global__ void k_gather_tiles(const uint8_t* __restrict__ log, uint8_t* __restr
         const uint4 hdr = *reinterpret_cast<const uint4*>(log + pos);
         const int size = (int)hdr.x;
         const uint8_t* src = log + pos + 16;                  // 16-byte aligned
-        const int head = min((int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3), size);
+        // bytes until dst is 16-byte aligned, then 16 bytes per lane and round trip: five source words (the segment is 16-byte
+        // aligned and padded) funnel-shifted into one 16-byte store, then the last odd bytes
+        const int head = min((int)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15), size);
         if (lane < head) dst[lane] = src[lane];
-        const int nwords = (size - head) >> 2;
-        const uint32_t* sw = reinterpret_cast<const uint32_t*>(src);
-        uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
-        for (int k = lane; k < nwords; k += 32) dw[k] = __funnelshift_r(sw[k], sw[k + 1], 8 * head);   // (segments are padded: sw[k + 1] exists)
-        const int tail0 = head + 4 * nwords;
+        const int nquads = (size - head) >> 4;
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(src + (head & ~3));
+        const int sh = 8 * (head & 3);
+        uint4* dq = reinterpret_cast<uint4*>(dst + head);
+        for (int k = lane; k < nquads; k += 32) {
+            const uint32_t* q = sw + 4 * k;
+            const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3], w4 = q[4];
+            dq[k] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+        }
+        const int tail0 = head + 16 * nquads;
         if (lane < size - tail0) dst[tail0 + lane] = src[tail0 + lane];
         const int nls = (int)hdr.y;
         const uint32_t* tr = reinterpret_cast<const uint32_t*>(src + ((size + 15) & ~15));
