@@ -236,6 +236,80 @@ def test_last_line_without_newline(codec):
         check_block(codec, body[:-3])                                                        # ends with a tab
 
 
+# ---- samples that are not 3 bytes wide: walked term by term inside the tile kernel (round 2) --------------------------
+def _mutate_samples(data: bytes, rng, rate: float, pool) -> bytes:
+    """Replaces a fraction of the sample columns of every data line by odd-width terms."""
+    out = []
+    for line in data.split(b"\n")[:-1]:
+        cols = line.split(b"\t")
+        for i in range(9, len(cols)):
+            if rng.random() < rate:
+                cols[i] = rng.choice(pool)
+        out.append(b"\t".join(cols))
+    return b"\n".join(out) + b"\n"
+
+
+ODD_TERMS = [b"10|0", b"0|10", b".", b"0", b"1", b"0|0|0", b"0|1:35:99", b"./.:.", b"1|1\r"[:3], b"12", b"0|0:3"]
+
+
+@pytest.mark.parametrize("n_lines,n_samples,rate,seed", [
+    (60, 2504, 0.0005, 1),      # a few odd terms per block of several tiles
+    (60, 2504, 0.02, 2),        # every line has dozens
+    (400, 333, 0.01, 3),
+    (8, 40000, 0.0002, 4),      # long lines: an odd term many tiles away from the line start
+    (3000, 7, 0.05, 5),
+    (12, 2504, 1.0, 6),         # nothing but odd terms (a small block: within the term walker's budget)
+])
+def test_odd_width_samples_stay_on_the_tile_kernel(codec, n_lines, n_samples, rate, seed):
+    """10|0, haploid calls, GT:DP columns ...: the tile kernel walks the rest of such a line term by term (lane 0) and goes on
+    on the 4-byte grid with the next line; bytes equal the oracle's, the block is not rerun on the generic kernels."""
+    rng = __import__("random").Random(seed)
+    _, data = vcfgen.random_vcf_like(n_lines, n_samples, seed=seed)
+    data = _mutate_samples(data, rng, rate, ODD_TERMS)
+    check_block(codec, data, sample_count=n_samples, expect_path=pkg.PATH_FAST)
+    # 1 % irregular LINES in an otherwise regular block
+    _, reg = vcfgen.kg_like(n_lines, n_samples, seed=seed + 50)
+    lines = reg.split(b"\n")[:-1]
+    for i in range(0, len(lines), 100):
+        lines[i] = _mutate_samples(lines[i] + b"\n", rng, 0.3, ODD_TERMS)[:-1]
+    check_block(codec, b"\n".join(lines) + b"\n", sample_count=n_samples, expect_path=pkg.PATH_FAST)
+
+
+def test_odd_width_runs_across_odd_terms(codec):
+    """Runs before / after an odd term, at the 31 / 127 chunk limits, and odd terms at the line's first / last sample."""
+    req = b"7\t123\t.\tA\tC\t.\t.\tDP=1\tGT\t"
+    lines = []
+    for gt, m in ((b"0|0", 127), (b"0|1", 31), (b"1|1", 31)):
+        for n in (1, m - 1, m, m + 1, 2 * m, 2 * m + 1, 700):
+            for odd in (b"10|0", b"0", b"0|0:7"):
+                lines.append(req + b"\t".join([gt] * n + [odd] + [gt] * n) + b"\n")
+                lines.append(req + b"\t".join([odd] + [gt] * n) + b"\n")
+                lines.append(req + b"\t".join([gt] * n + [odd]) + b"\n")
+                lines.append(req + b"\t".join([gt] * n + [odd, odd] + [gt] * 5 + [odd]) + b"\n")
+    data = b"".join(lines)
+    check_block(codec, data, expect_path=pkg.PATH_FAST)
+    # a run that is open when the tile ends inside an odd line, and an odd term right at tile boundaries
+    for n in (8180, 8190, 8191, 8192, 8193, 16383, 16384, 16385, 30000):
+        for gt in (b"0|0", b"1|0"):
+            line = req + b"\t".join([gt] * n + [b"10|0"] + [gt] * n + [b"0"] + [gt] * 3000) + b"\n"
+            check_block(codec, line * 3, expect_path=pkg.PATH_FAST)
+
+
+def test_gt_dp_gq_block(codec):
+    """An all-GT:DP:GQ block (every sample a literal of varying width): walked term by term while the odd-width terms stay
+    under ~3 % of the block (+ 256 KB), handed to the generic kernels beyond that (reject reason 7)."""
+    rng = __import__("random").Random(9)
+    lines = []
+    for i in range(300):
+        gts = "\t".join("%s:%d:%d" % (rng.choice(("0|0", "0|1", "1|1", "./.")), rng.randrange(60), rng.randrange(100)) for _ in range(500))
+        lines.append(f"2\t{500 + i}\t.\tG\tA\t.\tPASS\tDP=9\tGT:DP:GQ\t{gts}\n".encode())
+    check_block(codec, b"".join(lines[:40]), sample_count=500, expect_path=pkg.PATH_FAST)     # 160 KB of odd terms
+    check_block(codec, b"".join(lines) * 3, sample_count=500)
+    codec.compress_block(b"".join(lines) * 3)
+    assert codec.last_path == pkg.PATH_GENERIC and codec.last_reject_reason == 7
+
+
+
 def test_ragged_and_empty_inputs(any_path):
     rc, out, nl, _ = any_path.compress_block(b"")
     assert rc == 0 and out == b"" and nl == 0

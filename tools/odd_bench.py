@@ -1,0 +1,115 @@
+#!/usr/bin/env python3
+"""GPU box: device-resident encode / decode throughput of blocks the 4-byte sample grid does not take as they are --
+(a) a config-2-shaped block with 1 % irregular lines (a few odd-width samples each), (b) an all-GT:DP:GQ block --
+on the default dispatch and on the generic kernels, with the bytes checked against each other and (windows) the oracle.
+
+    python tools/odd_bench.py [--lines 200000]
+"""
+import argparse, importlib, json, os, random, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+import oraclelib as O
+import vcfsynth
+pkg = importlib.import_module("vcf-compression_b200")
+
+
+def timed(codec, d_in, n_in, d_out, cap, d_res, stream, steps=5):
+    codec.encode_dev(d_in.data_ptr(), n_in, d_out.data_ptr(), cap, d_res.data_ptr(), stream)
+    r = codec.fetch_result(d_res.data_ptr(), stream)
+    assert r.status == 0, r.status
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        codec.encode_dev(d_in.data_ptr(), n_in, d_out.data_ptr(), cap, d_res.data_ptr(), stream)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, int(r.out_len), int(r.n_lines), codec.last_path
+
+
+def timed_dec(codec, d_c, n_c, samples, d_txt, d_res, stream, steps=3):
+    codec.decode_dev(d_c.data_ptr(), n_c, samples, d_txt.data_ptr(), d_txt.numel(), d_res.data_ptr(), stream)
+    r = codec.fetch_result(d_res.data_ptr(), stream)
+    assert r.status == 0, r.status
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        codec.decode_dev(d_c.data_ptr(), n_c, samples, d_txt.data_ptr(), d_txt.numel(), d_res.data_ptr(), stream)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, int(r.out_len), codec.last_path
+
+
+def run(name, text: bytes, samples: int, codec, dev, with_generic=True):
+    n = len(text)
+    pad = (-n) % 16
+    d_in = torch.frombuffer(bytearray(text + b"\0" * pad), dtype=torch.uint8).to(dev)
+    cap = int(n * 1.6) + (1 << 20)
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_out2 = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_txt = torch.empty(n + 64, dtype=torch.uint8, device=dev)
+    d_res = torch.zeros(8, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    res = {"workload": name, "bytes": n}
+    codec.force_generic(0)
+    ms, olen, nl, path = timed(codec, d_in, n, d_out, cap, d_res, st)
+    res["encode"] = {"gbs": n / ms / 1e6, "ms": ms, "path": path, "out_bytes": olen, "lines": nl}
+    dms, tlen, dpath = timed_dec(codec, d_out, olen, samples, d_txt, d_res, st)
+    res["decode"] = {"gbs": n / dms / 1e6, "ms": dms, "path": dpath, "round_trip": bool(tlen == n and torch.equal(d_txt[:n], d_in[:n]))}
+    # oracle on the first 2 MB of whole lines
+    k = text.rfind(b"\n", 0, 2 << 20) + 1
+    orc, oout, onl, _ = O.compress_block(text[:k])
+    res["oracle_prefix_ok"] = bool(orc == 0 and bytes(d_out[:len(oout)].cpu().numpy()) == oout)
+    if with_generic:
+        codec.force_generic(1)
+        gms, golen, gnl, gpath = timed(codec, d_in, n, d_out2, cap, d_res, st, steps=2)
+        res["encode_generic"] = {"gbs": n / gms / 1e6, "ms": gms, "path": gpath,
+                                 "same_bytes": bool(golen == olen and torch.equal(d_out[:olen], d_out2[:olen]))}
+        gdms, _, gdpath = timed_dec(codec, d_out, olen, samples, d_txt, d_res, st, steps=1)
+        res["decode_generic"] = {"gbs": n / gdms / 1e6, "ms": gdms, "path": gdpath}
+        codec.force_generic(0)
+    print(json.dumps(res), flush=True)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lines", type=int, default=200000)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    codec = pkg.Codec(0)
+    rng = random.Random(1)
+    odd = [b"10|0", b"0|10", b".", b"0", b"1", b"0|1:35:99", b"./.:."]
+    # (a) config-2 shape, 1 % of the lines carry a few odd-width samples
+    d, lens = vcfsynth.generate("kg", args.lines, 2504, seed=20, device=dev)
+    text = d.cpu().numpy().tobytes()
+    starts = np.concatenate([[0], np.cumsum(lens.cpu().numpy())])
+    pieces, prev = [], 0
+    for li in range(0, args.lines, 100):
+        a, b = int(starts[li]), int(starts[li + 1])
+        cols = text[a:b - 1].split(b"\t")
+        for _ in range(5):
+            cols[rng.randrange(9, len(cols))] = rng.choice(odd)
+        pieces.append(text[prev:a]); pieces.append(b"\t".join(cols) + b"\n"); prev = b
+    pieces.append(text[prev:])
+    mixed = b"".join(pieces)
+    run("regular (config 2 shape)", text, 2504, codec, dev, with_generic=False)
+    run("config 2 shape, 1 % of the lines with 5 odd-width samples each", mixed, 2504, codec, dev)
+    del d, text, mixed, pieces
+    # (b) all GT:DP:GQ
+    L, S = max(1000, args.lines // 4), 1000
+    g = np.random.default_rng(3)
+    gt = np.array([list(b"0|0"), list(b"0|1"), list(b"1|0"), list(b"1|1")], dtype=np.uint8)[g.integers(0, 4, (L, S))]
+    cell = np.empty((L, S, 10), dtype=np.uint8)
+    cell[:, :, 0:3] = gt; cell[:, :, 3] = ord(":")
+    dp = g.integers(10, 100, (L, S)); cell[:, :, 4] = 48 + dp // 10; cell[:, :, 5] = 48 + dp % 10; cell[:, :, 6] = ord(":")
+    gq = g.integers(10, 100, (L, S)); cell[:, :, 7] = 48 + gq // 10; cell[:, :, 8] = 48 + gq % 10; cell[:, :, 9] = 9
+    cell[:, S - 1, 9] = 10
+    rows = [b"3\t%d\t.\tC\tT\t.\tPASS\tDP=100\tGT:DP:GQ\t" % (1000 + i) for i in range(L)]
+    body = cell.reshape(L, S * 10)
+    gtdp = b"".join(r + body[i].tobytes() for i, r in enumerate(rows))
+    run("all GT:DP:GQ (1000 samples per line)", gtdp, S, codec, dev)
+
+
+main()

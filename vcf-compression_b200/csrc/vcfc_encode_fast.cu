@@ -48,6 +48,7 @@ struct Ctrl {                           // one per launch, zeroed by the host
     unsigned long long total_bytes, total_lines;
     unsigned long long line_cap;
     unsigned long long log_cursor, log_cap;   // the tile log: tile outputs in arrival order, gathered by k_gather_tiles
+    unsigned long long serial_bytes;          // input bytes walked term by term (odd-width samples); too many: generic kernels
 };
 
 __device__ __forceinline__ bool is_sep(uint32_t c) { return c == '\t' || c == '\n'; }
@@ -292,7 +293,23 @@ __device__ __noinline__ void flush_line_start(const uint8_t* __restrict__ src, i
     __syncwarp();
 }
 
+// Look-back #1, read side (one lane): samples in the open chunk of the run that enters `tile`, 1..M.  Waits for the
+// predecessors' records (each is published by its ticket holder before it waits on anything).
+__device__ __noinline__ int lookback_count(const unsigned int* s1, int tile, int pc0) {
+    int acc = 0;
+    for (int j = tile - 1;; j--) {
+        unsigned v = *((volatile const unsigned*)&s1[j]);
+        while ((v >> 30) == 0) { __nanosleep(64); v = *((volatile const unsigned*)&s1[j]); }
+        acc += (int)(v & 0xFFu);
+        if ((v >> 30) == 2u || j == 0) break;
+    }
+    return mod_chunk(acc - 1 + 127 * 31, pc0 == 0) + 1;
+}
+
 // ---- the streaming kernel: one warp per tile -------------------------------------------------------------------------
+#ifndef VCFC_ENC_NOSERIAL
+#define VCFC_ENC_NOSERIAL 0
+#endif
 #ifndef VCFC_ENC_TICKET
 #define VCFC_ENC_TICKET 1
 #endif
@@ -320,9 +337,11 @@ constexpr int kBackRows = 4;                    // rows of 512 bytes per round t
 constexpr int kStepMaxOut = 2576;               // most bytes one step can emit: 512 literals of 5 bytes, a chunk token, the line end
 static_assert(kSTile % 64 == 0, "tiles start on block boundaries");
 static_assert(kSStage % 16 == 0 && kSStage >= kStepMaxOut + 512, "a step must fit the staging area (a long line start goes to the log directly)");
+static_assert(kSStage >= 1024 + 1024 + 64, "the term walker splits the staging area into an output part and an input window");
 
 struct SmemS {
     alignas(16) uint8_t stage[kSWarps][kSStage + 16];
+    int ce_true[kSWarps];                        // the tile's end cut, while `ce` is lowered for a redone step
 };
 
 // byte / word of the input at tile-relative offset r (win = in + gb); outside [0, n) reads as 0
@@ -407,10 +426,181 @@ __device__ int line_scan16(const uint8_t* __restrict__ win, int ls, int r_lo, in
     return -1;
 }
 
+// The lane's first valid sample (offset) that is not 3 bytes + separator: the tests of the step's validation loop, run again
+// over all valid samples on the rare steps that hold such a sample (kept out of the hot loop).
+__device__ __noinline__ int first_odd_sample(const uint8_t* __restrict__ win, int base, uint32_t valid, int kend, int r_lo, int r_hi) {
+    for (uint32_t t = valid; t; t &= t - 1) {
+        const int k = __ffs(t) - 1, r0 = base + 4 * k;
+        const uint32_t b0 = ldb_nl(win, r0, r_lo, r_hi), b1 = ldb_nl(win, r0 + 1, r_lo, r_hi), b2 = ldb_nl(win, r0 + 2, r_lo, r_hi),
+                       b3 = ldb_nl(win, r0 + 3, r_lo, r_hi);
+        if (k == kend ? (b3 != '\n') : (b3 != '\t')) return r0;
+        if (is_sep(b0) || is_sep(b1) || is_sep(b2)) return r0;
+    }
+    return 0x7fffffff;
+}
+
+// The rest of a line whose samples are not all 3 bytes wide, from term start `pos` to the line's end or the tile's end cut
+// `ce` (a term start): compress_data_line's sample loop (compress.cpp:124-190) term by term, by lane 0.  The warp stages the
+// next kSerWin input bytes in the upper part of its staging area (lane 0 then walks shared memory, not global memory); output
+// goes to the lower part and is flushed to the log when it fills up (both warp-collective, hence the outer loop).
+// rc / rn: the run that is open at pos.  The walker stops behind an odd-width term when the next term is 3 bytes wide (the grid
+// takes over again), at the line's end (*ended = 1) or at ce; it returns the offset where the caller goes on, -1 for an empty term.
+constexpr int kSerWin = 1024;                               // input window of the term walker
+__device__ __noinline__ int serial_portion(const uint8_t* __restrict__ win, int pos, int ce, int r_hi, int rc, int rn,
+                                           uint8_t* __restrict__ stage, int* o_io, int* flushed_io, uint8_t* __restrict__ log,
+                                           Ctrl* __restrict__ ctrl, unsigned long long log_cap, int lane, unsigned long long* seg_first,
+                                           unsigned long long* seg_prev, bool* dead, int* nl_seg, int my_off, int my_off2, int* ended) {
+    constexpr int kOutCap = kSStage - kSerWin - 16;         // output part of the staging area while the walker runs
+    uint8_t* const ibuf = stage + (kSStage - kSerWin);      // 16-byte aligned (kSStage and kSerWin are multiples of 16)
+    int o = *o_io, flushed = *flushed_io;
+    if (o - flushed > kOutCap - 8) {                        // what the grid steps staged does not leave room: flush first
+        flush_segment(stage, o - flushed, log, ctrl, log_cap, lane, seg_first, seg_prev, dead, *nl_seg, my_off, my_off2);
+        flushed = o; *nl_seg = 0;
+    }
+    int lit_src = 0, lit_rem = 0, lit_tab = 0;             // a literal that is being copied, a tab owed behind it
+    int result = 0;                                         // 0: running / portion done; > 0: line done; -1: error
+    bool done = false, line_end = false, stop_after = false;
+    while (!done) {
+        int giveup = 0;                                     // the block is going to the generic kernels anyway (one lane looks: uniform)
+        if (lane == 0) giveup = *((volatile int*)&ctrl->irregular);
+        if (__shfl_sync(0xffffffffu, giveup, 0)) { result = -2; break; }
+        // the window [w0, w0 + kSerWin) around the walker's position; bytes behind the input read as '\n' (EOF ends the line)
+        const int at = lit_rem > 0 ? lit_src : pos;
+        const int w0 = at & ~15;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < kSerWin / 512; q++) {
+            const int r = w0 + 512 * q + 16 * lane;
+            uint4 v;
+            if (r + 16 <= r_hi) v = *reinterpret_cast<const uint4*>(win + r);
+            else {
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) w[j] = ldw_edge(win, r + 4 * j, 0, r_hi, (uint32_t)'\n');
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            *reinterpret_cast<uint4*>(ibuf + 512 * q + 16 * lane) = v;
+        }
+        __syncwarp();
+        const int w1 = w0 + kSerWin;
+        int fill = o - flushed;
+        bool refill = false;
+        if (lane == 0) {
+            while (!done && !refill && fill <= kOutCap - 8) {
+                if (lit_rem > 0) {
+                    int n = min(lit_rem, kOutCap - 8 - fill + 1);
+                    n = min(n, w1 - lit_src);
+                    if (n <= 0) { refill = true; break; }
+                    for (int i = 0; i < n; i++) stage[fill + i] = ibuf[lit_src - w0 + i];
+                    fill += n; lit_src += n; lit_rem -= n;
+                    continue;
+                }
+                if (lit_tab) { stage[fill++] = '\t'; lit_tab = 0; continue; }
+                if (stop_after) { result = pos; done = true; break; }
+                if (line_end) {
+                    if (rc >= 0) stage[fill++] = (uint8_t)(cls_flag(rc) | (uint32_t)rn);
+                    stage[fill++] = '\n';
+                    done = true;
+                    break;
+                }
+                if (pos >= ce) { result = ce; done = true; break; }   // the tile ends inside the line (behind an odd term: no run is open)
+                int e = pos;
+                uint32_t ch = 0;
+                if (pos - w0 < 16) {                         // a term at the window's start may be longer than the window: global reads behind it
+                    for (;; e++) { ch = e >= r_hi ? (uint32_t)'\n' : (e < w1 ? (uint32_t)ibuf[e - w0] : (uint32_t)win[e]); if (ch == '\t' || ch == '\n') break; }
+                } else {
+                    for (; e < w1; e++) { ch = ibuf[e - w0]; if (ch == '\t' || ch == '\n') break; }
+                    if (e >= w1) { refill = true; break; }   // the term's end is not in the window: move the window to the term
+                }
+                const int len = e - pos;
+                const bool last = ch == '\n';
+                if (len == 0) { result = -1; done = true; break; }
+                int c = 4;
+                if (len == 3) c = gt_class3(ibuf + (pos - w0));   // (3 bytes from the window: pos + 3 = e < w1 or pos - w0 < 16)
+                if (rc >= 0 && (c != rc || rn == (rc == 0 ? 127 : 31))) {
+                    stage[fill++] = (uint8_t)(cls_flag(rc) | (uint32_t)rn);
+                    rc = -1;
+                }
+                if (c == 4) {
+                    stage[fill++] = (uint8_t)(kTokLit | 1u);
+                    lit_src = pos; lit_rem = len; lit_tab = last ? 0 : 1;
+                } else if (rc < 0) {
+                    rc = c; rn = 1;
+                } else {
+                    rn++;
+                }
+                pos = e + 1;
+                if (last) { line_end = true; result = pos; }
+                else if (c == 4 && len != 3 && pos < ce && pos + 4 <= w1) {
+                    // behind an odd-width term: when the next term is 3 bytes wide the grid takes over again (once the literal is out)
+                    const uint8_t* nx = ibuf + (pos - w0);
+                    if (!is_sep(nx[0]) && !is_sep(nx[1]) && !is_sep(nx[2]) && is_sep(nx[3])) stop_after = true;
+                }
+            }
+        }
+        done = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
+        fill = __shfl_sync(0xffffffffu, fill, 0);
+        lit_rem = __shfl_sync(0xffffffffu, lit_rem, 0);
+        lit_src = __shfl_sync(0xffffffffu, lit_src, 0);
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        o = flushed + fill;
+        if (!done && fill > kOutCap - 8) {                   // the output part is full: flush and go on
+            flush_segment(stage, fill, log, ctrl, log_cap, lane, seg_first, seg_prev, dead, *nl_seg, my_off, my_off2);
+            flushed = o; *nl_seg = 0;
+        }
+    }
+    result = __shfl_sync(0xffffffffu, result, 0);
+    *ended = __shfl_sync(0xffffffffu, (int)line_end, 0);
+    *o_io = o; *flushed_io = flushed;
+    return result;
+}
+
+// What to do with a step that holds a sample column that is not 3 bytes + separator.  Everything before the first such column q
+// is regular: the step is redone up to q (kOddRedo, cur = q).  When q is the step's first sample, lane 0 walks the odd-width
+// terms one by one (serial_portion) with the run that is open there, and the grid goes on behind them, in whatever phase that is.
+struct OddOut { int cur, o, flushed, nl_seg, ein0, flags; };
+enum { kOddLineEnd = 1, kOddEmpty = 2, kOddGiveUp = 4, kOddRedo = 8, kOddLookedBack = 16 };
+__device__ __noinline__ OddOut odd_step(const uint8_t* __restrict__ win, int base, uint32_t nc0, int kend, bool irr, int a, int ce, int cs,
+                                        int r_lo, int r_hi, bool first, bool need_lb, int ein_carry, int pc0, int tile,
+                                        const unsigned int* s1, uint8_t* __restrict__ stage, int o, int flushed, int nl_seg, int my_off,
+                                        int my_off2, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl, unsigned long long log_cap,
+                                        unsigned long long serial_budget, int lane, unsigned long long* seg_first,
+                                        unsigned long long* seg_prev, bool* dead) {
+    OddOut out = {a, o, flushed, nl_seg, 0, 0};
+    const int q = __reduce_min_sync(0xffffffffu, irr ? first_odd_sample(win, base, nc0, kend, r_lo, r_hi) : 0x7fffffff);
+    if (q > a) { out.cur = q; out.flags = kOddRedo; return out; }
+    int rcl = -1, rcn = 0;                               // open run: class, samples in its open chunk (1..M)
+    if (!first) {
+        if (need_lb) {                                   // (the tile's first step: the entering run's chunk count)
+            int cnt_in = 0;
+            if (lane == 0) cnt_in = lookback_count(s1, tile, pc0);
+            cnt_in = __shfl_sync(0xffffffffu, cnt_in, 0);
+            ein_carry = cs - 4 * cnt_in;
+            out.ein0 = ein_carry; out.flags |= kOddLookedBack;
+        }
+        const int pcl = win[a - 5] == '\t' ? gt_class3(win + a - 4) : 4;
+        if (pcl < 4 && ein_carry != kNoHead) {
+            rcl = pcl;
+            rcn = (int)mod_chunk(((a - ein_carry) >> 2) - 1, pcl == 0) + 1;
+        }
+    }
+    int ended = 0;
+    const int r = serial_portion(win, a, ce, r_hi, rcl, rcn, stage, &out.o, &out.flushed, log, ctrl, log_cap, lane, seg_first, seg_prev, dead,
+                                 &out.nl_seg, my_off, my_off2, &ended);
+    if (r < 0) { out.flags |= r == -1 ? kOddEmpty : kOddGiveUp; return out; }   // an empty sample column / the block is given up
+    int over = 0;
+    if (lane == 0 && atomicAdd(&ctrl->serial_bytes, (unsigned long long)(r - a)) > serial_budget) over = 1;
+    if (__shfl_sync(0xffffffffu, over, 0)) { out.flags |= kOddGiveUp; return out; }   // mostly odd-width samples: generic kernels
+    out.cur = r;
+    if (ended) out.flags |= kOddLineEnd;
+    return out;
+}
+
 __global__ void __launch_bounds__(32 * kSWarps, kSCtas)
 k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
                 unsigned int* __restrict__ s1, unsigned long long* __restrict__ rec_pos, unsigned long long* __restrict__ rec_size,
-                unsigned long long* __restrict__ rec_lines, int n_tiles, unsigned long long log_cap, int tile_sz) {
+                unsigned long long* __restrict__ rec_lines, int n_tiles, unsigned long long log_cap, int tile_sz,
+                unsigned long long serial_budget) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemS& sm = *reinterpret_cast<SmemS*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -461,7 +651,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 int lc = kNone, uniform = 0;
                 if (ke == kCutSample) {
                     const int lo = 64 > r_lo + 4 ? 64 : r_lo + 4;             // sample starts below t0 belong to the previous tile
-                    lc = gt_class3(win + ce - 4);
+                    lc = win[ce - 5] == '\t' ? gt_class3(win + ce - 4) : 4;      // "10|0" ends like "0|0": the term must be 3 bytes
                     word = (2u << 30) | ((unsigned)lc << 8);
                     if (lc < 4) {
                         int found = -1;
@@ -514,6 +704,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                             }
                         }
                         if (found >= 0) {
+                            if (win[found - 1] != '\t') found += 4;               // the earliest word is the tail of a longer term
                             word |= (unsigned)mod_chunk(((ce - found) >> 2) - 1, lc == 0) + 1u;
                         } else {                                                 // the entering run covers the whole tile
                             uniform = 1;
@@ -526,7 +717,8 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
             }
             if (lane == 0) *((volatile unsigned*)&s1[nt]) = word;
         }
-        const int ce = cur_ce, fl = cur_fl;
+        int ce = cur_ce;                                 // (lowered for a while when a step is redone up to an odd-width sample)
+        const int fl = cur_fl;
         cur_ce = n_ce; cur_fl = n_fl;
         if (tile < 0 || (fl & kFlSkip)) continue;
         // ---- the tile itself ---------------------------------------------------------------------------------------------
@@ -536,6 +728,8 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
         const int r_lo = gb < 0 ? 64 : 0;                               // valid relative range [r_lo, r_hi)
         const int r_hi = (int)(n - gb < (long long)(1 << 24) ? n - gb : (long long)(1 << 24));
         int irregular = 0;
+        if (lane == 0) sm.ce_true[warp] = ce;
+        __syncwarp();
         const int pf_lim = min(r_hi, ce + 127), pf_lim2 = min(r_hi, ce + 4095);   // how far the steps' prefetches may reach
         // the first 8 KB of the tile into L2 now; every step asks for the 2 KB that lie 8 KB ahead of it
         {
@@ -555,7 +749,11 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
         //      the first byte count), so the predecessor's record is normally there already -------------------------------
         int ein0 = kNoHead;
         int pc0 = kNone;
-        if (ks == kCutSample && tile > 0 && cs < ce && !irregular) pc0 = gt_class3(win + cs - 4);
+        bool prev_lit = false;                           // the tile starts inside a line, behind a term that is not a coded genotype
+        if (ks == kCutSample && tile > 0 && cs < ce && !irregular) {
+            pc0 = win[cs - 5] == '\t' ? gt_class3(win + cs - 4) : 4;
+            prev_lit = pc0 == 4;
+        }
         bool need_lb = pc0 < 4;
         // ---- the tile, line by line.  Output goes to the staging area; when the next piece (a line start: <= 8 + kMaxReq bytes,
         //      a step: <= 2.6 KB) would not fit, what is staged is flushed to the log as a SEGMENT: [u32 bytes, u32 0, u64 position
@@ -566,7 +764,11 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
         bool dead = false;                                // the log is full: keep counting, write nothing more
         {
             int o = 0, cur = cs, ein_carry = ein0;
-            bool in_req = ks == kCutLine, first = ks == kCutSampleFirst;
+            bool in_req = ks == kCutLine, first = ks == kCutSampleFirst || prev_lit;    // first: no run is open before the next sample
+            bool odd_pending = false, odd_irr = false;       // a step that met an odd-width sample column (rare): see odd_step
+            int odd_a = 0, odd_base = 0, odd_kend = 0;
+            uint32_t odd_nc0 = 0;
+            for (;;) {
             while (cur < ce && !irregular) {
                 if (in_req) {
                     // ---- a line start: two length headers + the required section (compress.cpp:32-100) ----------------
@@ -713,7 +915,14 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                             L |= 1u << k;
                         }
                     }
-                    if (__any_sync(0xffffffffu, irr)) { irregular = 6; break; }    // a sample column that is not 3 bytes + separator
+#if VCFC_ENC_NOSERIAL
+                    if (__any_sync(0xffffffffu, irr)) { irregular = 6; break; }
+#else
+                    if (__any_sync(0xffffffffu, irr)) {      // a sample column that is not 3 bytes + separator: handled behind the loop
+                        odd_pending = true; odd_a = a; odd_base = base; odd_nc0 = V; odd_kend = kend; odd_irr = irr;
+                        break;
+                    }
+#endif
                 }
                 const uint32_t F = (first && lane == 0) ? (1u << klo) : 0u;
                 const uint32_t Cprev = (Craw << 1) | pc_all;
@@ -727,14 +936,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 if (need_lb) {
                     int cnt_in = 0;
                     if (lane == 0) {
-                        int acc = 0;
-                        for (int j = tile - 1;; j--) {
-                            unsigned v = *((volatile unsigned*)&s1[j]);
-                            while ((v >> 30) == 0) { __nanosleep(64); v = *((volatile unsigned*)&s1[j]); }
-                            acc += (int)(v & 0xFFu);
-                            if ((v >> 30) == 2u || j == 0) break;
-                        }
-                        cnt_in = mod_chunk(acc - 1 + 127 * 31, pc0 == 0) + 1;        // open chunk count before the tile, 1..M
+                        cnt_in = lookback_count(s1, tile, pc0);                      // open chunk count before the tile, 1..M
                         if (lb_uniform)
                             *((volatile unsigned*)&s1[tile]) =
                                 (2u << 30) | ((unsigned)lb_lc << 8) | ((unsigned)mod_chunk(cnt_in + lb_nsamp - 1, lb_lc == 0) + 1u);
@@ -770,6 +972,22 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 first = false;
                 if (endm) { cur = q_end + 1; in_req = true; }
                 else cur = a + 4 * ((bound - a + 3) >> 2);
+            }
+            if (!odd_pending) {
+                if (ce != sm.ce_true[warp] && !irregular) { ce = sm.ce_true[warp]; continue; }   // the capped redo is done: on to the odd sample
+                break;
+            }
+            {   // (out of the hot loop: the grid steps' register allocation does not see this)
+                odd_pending = false;
+                const OddOut r = odd_step(win, odd_base, odd_nc0, odd_kend, odd_irr, odd_a, ce, cs, r_lo, r_hi, first, need_lb, ein_carry, pc0, tile, s1,
+                                          stage, o, flushed, nl_seg, my_off, my_off2, log, ctrl, log_cap, serial_budget, lane, &seg_first, &seg_prev, &dead);
+                if (r.flags & kOddRedo) { ce = r.cur; continue; }         // redo the step up to the odd sample: ce is the cap meanwhile
+                if (r.flags & (kOddEmpty | kOddGiveUp)) { irregular = (r.flags & kOddEmpty) ? 6 : 7; break; }
+                o = r.o; flushed = r.flushed; nl_seg = r.nl_seg; cur = r.cur;
+                if (r.flags & kOddLookedBack) { ein0 = r.ein0; need_lb = false; }
+                if (r.flags & kOddLineEnd) in_req = true;                 // behind the line's newline
+                first = true; ein_carry = kNoHead;                        // (the walker stops behind an odd term: no run is open)
+            }
             }
             // the input ends inside a line that no newline-less last sample closed (a trailing tab, a cut sample): generic path
             if (!irregular && ke == kCutEnd && cs < ce && !in_req) irregular = 1;
@@ -935,7 +1153,8 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         unsigned int* a_s1 = (unsigned int*)(base + off_s1);
         int a_tiles = (int)n_tiles, a_tile_sz = (int)tile_sz;
         unsigned long long a_cap = (unsigned long long)log_cap;
-        void* args[] = {&a_in, &a_n, &a_log, &ctrl, &a_s1, &rec_pos, &rec_size, &rec_lines, &a_tiles, &a_cap, &a_tile_sz};
+        unsigned long long a_budget = (unsigned long long)(in_len / 32 + (1u << 18));  // odd-width terms beyond ~3 % of the block: generic kernels
+        void* args[] = {&a_in, &a_n, &a_log, &ctrl, &a_s1, &rec_pos, &rec_size, &rec_lines, &a_tiles, &a_cap, &a_tile_sz, &a_budget};
         VCFC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_encode_stream, dim3(grid), dim3(32 * kSWarps), args, sizeof(SmemS), stream));
     }
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeEncode + 1], stream); ctx->ev_pending[kTimeEncode] = 1; }
