@@ -171,6 +171,14 @@ int vcfc_last_reject_reason(const vcfc_ctx *ctx);
  * decoder use its span-walking expansion kernel even when the fill-and-patch kernel applies; 0 = automatic. */
 int vcfc_force_generic(vcfc_ctx *ctx, int on);
 
+/* sparsify_file(in, out), src/sparse.cpp:290-580 (verb sparsify, main.cpp:4073-4085): every compressed line is copied to
+ * offset (300,000,000 + POS) * 16384 behind the header of a holey file, with previous / next distance links.  Host only. */
+int vcfc_sparsify_file(const char *vcfc_path, const char *sparse_path);
+/* query_sparse_file_fd(in, query), src/main.cpp:235-582 (verb sparse-query, main.cpp:4086-4096): "REF:START-END" on a
+ * sparsified file; a single position is looked up directly, a range follows the next links from the first record at
+ * or behind START.  The lines found are decoded in one GPU block call and written to out_fd. */
+int vcfc_sparse_query_file(vcfc_ctx *ctx, const char *sparse_path, const char *region, int out_fd);
+
 #ifdef __cplusplus
 }
 #endif

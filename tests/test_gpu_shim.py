@@ -82,3 +82,31 @@ def test_binned_index_verbs(main_gpu, tmp_path):
                 continue
             r = run(main_gpu, "query-binned-index", cp, region)
             assert r.returncode == 0 and hashlib.sha256(r.stdout).hexdigest() == q["sha256"], key
+
+
+def test_sparse_verbs(main_gpu, tmp_path):
+    """sparsify / sparse-query / create-sparse-index / query-sparse-index (sparse.cpp:290-580, main.cpp:235-582, 854-1281) stay
+    the reference's host code (lseek / SEEK_DATA over a ~4.9 TB holey file); every header walk and every decoded line goes
+    through the shim into libvcfc_gpu.so.  Pinned by what the unmodified reference binary produced (oracle/make_golden_sparse.py)."""
+    man = json.load(open(os.path.join(goldenlib.GOLDEN, "sparse", "MANIFEST.json")))
+    for name, e in man.items():
+        fp, sp = str(tmp_path / (name + ".vcfc")), str(tmp_path / (name + ".sparse"))
+        open(fp, "wb").write(goldenlib.read(name + ".vcfc"))
+        r = run(main_gpu, "sparsify", fp, sp)
+        assert r.returncode == e["sparsify_rc"], (name, r.stderr[-300:])
+        assert goldenlib.sparse_digest(sp) == e["sparse"], name
+        for q, c in e["queries"].items():
+            r = run(main_gpu, "sparse-query", sp, q)
+            assert r.returncode == c["rc"], (name, q, r.stderr[-300:])
+            if c["rc"] == 0:
+                assert len(r.stdout) == c["len"] and hashlib.sha256(r.stdout).hexdigest() == c["sha256"], (name, q)
+        r = run(main_gpu, "create-sparse-index", fp)
+        assert r.returncode == e["index_rc"], (name, r.stderr[-300:])
+        assert goldenlib.sparse_digest(fp + ".vcfci-sparse") == e["index"], name
+        for q, c in e["index_queries"].items():
+            r = run(main_gpu, "query-sparse-index", fp, q)
+            assert r.returncode == c["rc"], (name, q, r.stderr[-300:])
+            if c["rc"] == 0:
+                assert len(r.stdout) == c["len"] and hashlib.sha256(r.stdout).hexdigest() == c["sha256"], (name, q)
+        for x in (sp, fp + ".vcfci-sparse"):
+            os.remove(x)

@@ -4,7 +4,7 @@
 set -e
 name=$1; shift; defs="$*"
 root=$(cd "$(dirname "$0")/.." && pwd); src=$root/vcf-compression_b200/csrc; out=$root/vcf-compression_b200/variants; mkdir -p $out/obj_$name
-for f in vcfc_api vcfc_files vcfc_generic vcfc_encode_fast vcfc_decode_fast vcfc_index vcfc_pipeline; do
+for f in vcfc_api vcfc_files vcfc_generic vcfc_encode_fast vcfc_decode_fast vcfc_index vcfc_pipeline vcfc_sparse; do
   nvcc $defs -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wno-unused-function --expt-relaxed-constexpr -c $src/$f.cu -o $out/obj_$name/$f.o 2>/dev/null &
 done
 wait

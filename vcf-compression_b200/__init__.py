@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
         "vcfc_decompress_file_multi": (i, [C.POINTER(vp), i, C.c_char_p, C.c_char_p]),
         "vcfc_compress_index_file_multi": (i, [C.POINTER(vp), i, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]),
         "vcfc_query_file": (i, [vp, C.c_char_p, C.c_char_p, i]),
+        "vcfc_sparsify_file": (i, [C.c_char_p, C.c_char_p]),
+        "vcfc_sparse_query_file": (i, [vp, C.c_char_p, C.c_char_p, i]),
         "vcfc_create_binned_index_file": (i, [vp, C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]),
         "vcfc_query_binned_index_file": (i, [vp, C.c_char_p, C.c_char_p, i]),
         "vcfc_set_timing": (i, [vp, i]),
@@ -85,6 +87,11 @@ def lib() -> C.CDLL:
         fn.restype, fn.argtypes = res, args
     _lib = L
     return L
+
+
+def sparsify(vcfc_path: str, sparse_path: str) -> int:
+    """.vcfc -> holey file addressed by position (sparsify_file, sparse.cpp:290-580); host only."""
+    return lib().vcfc_sparsify_file(vcfc_path.encode(), sparse_path.encode())
 
 
 def strerror(code: int) -> str:
@@ -276,6 +283,10 @@ class Codec:
 
     def query(self, in_path: str, region: str, out_fd: int) -> int:
         return lib().vcfc_query_file(self._ctx, in_path.encode(), region.encode(), out_fd)
+
+    def sparse_query(self, sparse_path: str, region: str, out_fd: int) -> int:
+        """REF:START-END on a sparsified file (query_sparse_file_fd, main.cpp:235-582)."""
+        return lib().vcfc_sparse_query_file(self._ctx, sparse_path.encode(), region.encode(), out_fd)
 
     def query_binned_index(self, vcfc_path: str, region: str, out_fd: int) -> int:
         """Indexed range query (query_binned_index_binarysearch, main.cpp:2974-3350); the index is vcfc_path + '.vcfci'."""

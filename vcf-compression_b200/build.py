@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libvcfc_gpu.so")
 CLI = os.path.join(HERE, "vcfc")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-CU = ["vcfc_api.cu", "vcfc_files.cu", "vcfc_generic.cu", "vcfc_encode_fast.cu", "vcfc_decode_fast.cu", "vcfc_index.cu", "vcfc_pipeline.cu"]
+CU = ["vcfc_api.cu", "vcfc_files.cu", "vcfc_generic.cu", "vcfc_encode_fast.cu", "vcfc_decode_fast.cu", "vcfc_index.cu", "vcfc_pipeline.cu", "vcfc_sparse.cu"]
 FLAGS = (["-DVCFC_DEBUG"] if os.environ.get("VCFC_DEBUG") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr"]
 

@@ -5,6 +5,7 @@
 //     vcfc query      IN.vcfc REF[:START-END]
 //     vcfc create-binned-index BIN_SIZE IN.vcfc          (writes IN.vcfc.vcfci, main.cpp:4097-4115)
 //     vcfc query-binned-index  IN.vcfc REF:START-END     (reads IN.vcfc.vcfci, main.cpp:4117-4143)
+//     vcfc sparsify IN.vcfc OUT.sparse | sparse-query IN.sparse REF:START-END   (main.cpp:4073-4096)
 // Host C++ only; all coding work is done by libvcfc_gpu.so through its C ABI.  Where the
 // reference lets an exception escape (abort, exit 134) this prints the reason and exits 1.
 #include <stdio.h>
@@ -30,6 +31,7 @@ static int usage() {
     fprintf(stderr,
             "usage: vcfc compress IN.vcf OUT.vcfc | decompress IN.vcfc OUT.vcf | query IN.vcfc REF[:START-END]\n"
             "       vcfc create-binned-index BIN_SIZE IN.vcfc | query-binned-index IN.vcfc REF:START-END\n"
+            "       vcfc sparsify IN.vcfc OUT.sparse | sparse-query IN.sparse REF:START-END\n"
             "       env: VCFC_DEVICE (default 0), VCFC_GPUS (compress / decompress over that many GPUs starting at VCFC_DEVICE,\n"
             "            default 1, \"all\" = every GPU of the box), VCFC_FILE_CHUNK_MB (default 16),\n"
             "            VCFC_INDEX_BIN=N (compress also writes OUT.vcfci with N lines per bin, in the same pass)\n");
@@ -39,12 +41,23 @@ static int usage() {
 int main(int argc, char** argv) {
     if (argc < 2) return usage();
     std::string action(argv[1]);
-    const char* verbs_elsewhere[] = {"gap-analysis", "sparsify", "sparse-query", "create-sparse-index", "query-sparse-index"};
+    const char* verbs_elsewhere[] = {"gap-analysis", "create-sparse-index", "query-sparse-index"};
     for (const char* v : verbs_elsewhere)
         if (action == v) {
             fprintf(stderr, "vcfc: verb '%s' is outside the GPU hot path; use the reference binary for it\n", v);
             return 2;
         }
+    if (action == "sparsify") {                                  // main.cpp:4073-4085 (host only: no device needed)
+        if (argc < 4) return usage();
+        if (strcmp(argv[2], argv[3]) == 0) {
+            fprintf(stderr, "input and output file are the same\n");
+            return 1;
+        }
+        if (access(argv[2], F_OK) != 0) printf("Input file does not exist: %s\n", argv[2]);
+        const int src = vcfc_sparsify_file(argv[2], argv[3]);
+        if (src != VCFC_OK) fprintf(stderr, "vcfc sparsify: %s\n", vcfc_strerror(src));
+        return src == VCFC_OK ? 0 : 1;
+    }
     if (action == "create-binned-index") {
         if (argc != 4) {
             printf("Usage: ./main create-binned-index <bin-size> <compressed-filename>\n");   // main.cpp:4098-4101
@@ -69,7 +82,7 @@ int main(int argc, char** argv) {
         vcfc_gpu_destroy(ictx);
         return irc == VCFC_OK ? 0 : 1;
     }
-    if (action != "compress" && action != "decompress" && action != "query" && action != "query-binned-index") {
+    if (action != "compress" && action != "decompress" && action != "query" && action != "query-binned-index" && action != "sparse-query") {
         printf("Unknown action name: %s\n", action.c_str());   // main.cpp:4181-4183
         return 0;
     }
@@ -85,9 +98,10 @@ int main(int argc, char** argv) {
         return 1;
     }
     trace("context ready");
-    if (action == "query" || action == "query-binned-index") {
+    if (action == "query" || action == "query-binned-index" || action == "sparse-query") {
         rc = action == "query" ? vcfc_query_file(ctx, in, argv[3], STDOUT_FILENO)
-                               : vcfc_query_binned_index_file(ctx, in, argv[3], STDOUT_FILENO);
+             : action == "sparse-query" ? vcfc_sparse_query_file(ctx, in, argv[3], STDOUT_FILENO)     // main.cpp:4086-4096
+                                        : vcfc_query_binned_index_file(ctx, in, argv[3], STDOUT_FILENO);
         if (rc == VCFC_E_QUERY) printf("Failed to parse query string: %s\n", argv[3]);   // main.cpp:4064-4067
     } else {
         if (strcmp(in, argv[3]) == 0) {
