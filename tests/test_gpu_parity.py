@@ -296,18 +296,27 @@ def test_odd_width_runs_across_odd_terms(codec):
 
 
 def test_gt_dp_gq_block(codec):
-    """An all-GT:DP:GQ block (every sample a literal of varying width): walked term by term while the odd-width terms stay
-    under ~3 % of the block (+ 256 KB), handed to the generic kernels beyond that (reject reason 7)."""
+    """An all-GT:DP:GQ block (every sample a literal of varying width), and haploid / diploid mixes: after eight odd-width
+    terms in a row all 32 lanes walk the rest of the line portion (parallel_portion)."""
     rng = __import__("random").Random(9)
     lines = []
     for i in range(300):
         gts = "\t".join("%s:%d:%d" % (rng.choice(("0|0", "0|1", "1|1", "./.")), rng.randrange(60), rng.randrange(100)) for _ in range(500))
         lines.append(f"2\t{500 + i}\t.\tG\tA\t.\tPASS\tDP=9\tGT:DP:GQ\t{gts}\n".encode())
-    check_block(codec, b"".join(lines[:40]), sample_count=500, expect_path=pkg.PATH_FAST)     # 160 KB of odd terms
-    check_block(codec, b"".join(lines) * 3, sample_count=500)
-    codec.compress_block(b"".join(lines) * 3)
-    assert codec.last_path == pkg.PATH_GENERIC and codec.last_reject_reason == 7
-
+    check_block(codec, b"".join(lines[:40]), sample_count=500, expect_path=pkg.PATH_FAST)
+    check_block(codec, b"".join(lines) * 3, sample_count=500, expect_path=pkg.PATH_FAST)
+    # haploid calls mixed with diploid ones (chrX): runs of coded terms between odd-width ones, across the lanes' ranges
+    for n_samples, p_hap in ((2504, 0.5), (2504, 0.95), (700, 0.2), (40000, 0.5)):
+        mix = []
+        for i in range(24 if n_samples < 10000 else 3):
+            gts = []
+            while len(gts) < n_samples:
+                g = rng.choice((b"0", b"1", b".")) if rng.random() < p_hap else rng.choice((b"0|0", b"0|0", b"0|0", b"0|1", b"1|1"))
+                gts += [g] * rng.choice((1, 1, 2, 5, 40, 200))
+            mix.append(b"X\t%d\t.\tG\tA\t.\tPASS\tDP=9\tGT\t" % (900 + i) + b"\t".join(gts[:n_samples]) + b"\n")
+        check_block(codec, b"".join(mix), sample_count=n_samples, expect_path=pkg.PATH_FAST)
+    # no newline at the end of an odd-width line, and an odd-width line that ends the input right behind a tile boundary
+    check_block(codec, (b"".join(lines[:5]))[:-1], sample_count=500, expect_path=pkg.PATH_FAST)
 
 
 def test_ragged_and_empty_inputs(any_path):

@@ -169,11 +169,24 @@ int vcfc_encode_block_dev(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uin
     VCFC_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     if (ctx->force_generic != 1) {
-        int rc = encode_fast(ctx, d_in, in_len, d_out, out_cap, d_line_out_offsets, line_cap, d_result, st);
-        if (rc != VCFC_OK) return rc;
-        int status = 0;
-        if ((rc = peek_status(ctx, d_result, st, &status))) return rc;
-        if (status != kStatusIrregular) return VCFC_OK;
+        // Two instantiations of the tile kernel: the regular one gives a block with odd-width sample columns (10|0, haploid calls,
+        // GT:DP:GQ) up at once (reject reason 9) and the one with the term walkers takes it; the context stays with that one until
+        // eight blocks in a row did not need it.
+        for (;;) {
+            int rc = encode_fast(ctx, d_in, in_len, d_out, out_cap, d_line_out_offsets, line_cap, d_result, st);
+            if (rc != VCFC_OK) return rc;
+            int status = 0;
+            if ((rc = peek_status(ctx, d_result, st, &status))) return rc;
+            if (status != kStatusIrregular) {
+                if (ctx->enc_odd && status == VCFC_OK) {
+                    ctx->enc_odd_idle = ctx->h_result[2].reserved ? 0 : ctx->enc_odd_idle + 1;
+                    if (ctx->enc_odd_idle >= 8) { ctx->enc_odd = 0; ctx->enc_odd_idle = 0; }
+                }
+                return VCFC_OK;
+            }
+            if (ctx->last_reject == 9 && !ctx->enc_odd) { ctx->enc_odd = 1; ctx->enc_odd_idle = 0; continue; }
+            break;
+        }
     }
     if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeEncode], st);       // generic: the whole pipeline is "the kernel"
     int rc = encode_generic(ctx, d_in, in_len, d_out, out_cap, d_line_out_offsets, line_cap, d_result, st);

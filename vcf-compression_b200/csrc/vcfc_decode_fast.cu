@@ -700,6 +700,9 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
 #ifndef VCFC_DEC_ASYNC_TAB
 #define VCFC_DEC_ASYNC_TAB 0
 #endif
+#ifndef VCFC_DEC_RUNFN
+#define VCFC_DEC_RUNFN 0
+#endif
 #ifndef VCFC_DEC_FILLPTR
 #define VCFC_DEC_FILLPTR 0
 #endif
@@ -751,6 +754,14 @@ __device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem,
 }
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// a run of 0|1 / 1|0 / 1|1 samples that crosses the tile's first or last byte: every byte tested
+__device__ __noinline__ void patch_run_checked(uint8_t* stage, int pos, int cnt, bool a1, bool b1, int tile_len) {
+    for (int q = 0; q < cnt; q++, pos += 4) {
+        if (a1 && (unsigned)pos < (unsigned)tile_len) stage[pos] = '1';
+        if (b1 && (unsigned)(pos + 2) < (unsigned)tile_len) stage[pos + 2] = '1';
+    }
+}
 
 struct SmemG {
     alignas(16) uint8_t stage[kTileG];
@@ -1010,7 +1021,17 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
                                 const uint32_t f = b & 0xE0u;
                                 const bool a1 = f != kTok01, b1 = f != kTok10;
                                 const int cnt = (int)(b & 0x1Fu);
-#if VCFC_DEC_RUNDO
+#if VCFC_DEC_RUNFN
+                                if ((unsigned)pos <= (unsigned)(tile_len - 4 * cnt)) {     // the whole run lies inside the tile (nearly always)
+                                    for (int q = 0; q < cnt; q++, pos += 4) {
+                                        if (a1) sm.stage[pos] = '1';
+                                        if (b1) sm.stage[pos + 2] = '1';
+                                    }
+                                } else {
+                                    patch_run_checked(sm.stage, pos, cnt, a1, b1, tile_len);   // (out of line: tile edges only)
+                                    pos += 4 * cnt;
+                                }
+#elif VCFC_DEC_RUNDO
                                 const int pe = pos + 4 * cnt;                 // (cnt >= 1: k_dec_sizes rejects empty runs)
                                 do {
                                     if (a1 && (unsigned)pos < (unsigned)tile_len) sm.stage[pos] = '1';

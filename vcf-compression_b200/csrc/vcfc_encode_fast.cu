@@ -307,6 +307,9 @@ __device__ __noinline__ int lookback_count(const unsigned int* s1, int tile, int
 }
 
 // ---- the streaming kernel: one warp per tile -------------------------------------------------------------------------
+#ifndef VCFC_ENC_PARWALK
+#define VCFC_ENC_PARWALK 1
+#endif
 #ifndef VCFC_ENC_NOSERIAL
 #define VCFC_ENC_NOSERIAL 0
 #endif
@@ -459,7 +462,8 @@ __device__ __noinline__ int serial_portion(const uint8_t* __restrict__ win, int 
     }
     int lit_src = 0, lit_rem = 0, lit_tab = 0;             // a literal that is being copied, a tab owed behind it
     int result = 0;                                         // 0: running / portion done; > 0: line done; -1: error
-    bool done = false, line_end = false, stop_after = false;
+    bool done = false, line_end = false, stop_after = false, want_all = false;
+    int n_odd = 0;                                          // odd-width terms walked by this call
     while (!done) {
         int giveup = 0;                                     // the block is going to the generic kernels anyway (one lane looks: uniform)
         if (lane == 0) giveup = *((volatile int*)&ctrl->irregular);
@@ -497,6 +501,7 @@ __device__ __noinline__ int serial_portion(const uint8_t* __restrict__ win, int 
                 }
                 if (lit_tab) { stage[fill++] = '\t'; lit_tab = 0; continue; }
                 if (stop_after) { result = pos; done = true; break; }
+                if (VCFC_ENC_PARWALK && n_odd >= 8 && rc < 0 && !line_end && pos < ce) { result = pos; want_all = true; done = true; break; }   // odd terms in a row: all lanes take over
                 if (line_end) {
                     if (rc >= 0) stage[fill++] = (uint8_t)(cls_flag(rc) | (uint32_t)rn);
                     stage[fill++] = '\n';
@@ -524,6 +529,7 @@ __device__ __noinline__ int serial_portion(const uint8_t* __restrict__ win, int 
                 if (c == 4) {
                     stage[fill++] = (uint8_t)(kTokLit | 1u);
                     lit_src = pos; lit_rem = len; lit_tab = last ? 0 : 1;
+                    if (len != 3) n_odd++;
                 } else if (rc < 0) {
                     rc = c; rn = 1;
                 } else {
@@ -550,9 +556,216 @@ __device__ __noinline__ int serial_portion(const uint8_t* __restrict__ win, int 
         }
     }
     result = __shfl_sync(0xffffffffu, result, 0);
-    *ended = __shfl_sync(0xffffffffu, (int)line_end, 0);
+    *ended = __shfl_sync(0xffffffffu, want_all ? 2 : (int)line_end, 0);      // 2: odd terms go on: parallel_portion takes the rest
     *o_io = o; *flushed_io = flushed;
     return result;
+}
+
+// ---- many odd-width terms in a row (a GT:DP:GQ file, haploid calls): the rest of the line portion, ALL LANES walking ------------
+// The portion [pos, end of line or ce) is cut into 32 ranges of whole terms; every lane walks its range twice with the sample
+// loop of compress_data_line (compress.cpp:124-190): once to size it and to learn the run it begins with / ends with, once to
+// write.  In between, the open run is handed from lane to lane (a lane that is one single run hands on what it got, extended),
+// and what the incoming run costs a lane is closed form: a closing token when the lane's first term differs, chunk-fill
+// tokens every 127 / 31 samples of a leading run that continues it.
+struct LaneWalk {                 // one lane's range, walked without an incoming run
+    int lead_c, lead_n;           // the leading run: class (-1: the range begins with a literal or is empty), samples
+    bool lead_closed;             // a later term of the range ends it (else the whole range is that one run)
+    int rc, rn;                   // the run that is open behind the range when it is not the leading one (-1: none)
+    int sz;                       // bytes behind the leading run's tokens
+    int nterms, err;
+};
+
+// WRITE: emits into d (the caller has put the leading run's tokens there already) and returns the bytes written; else sizes only.
+template <bool WRITE>
+__device__ __forceinline__ LaneWalk lane_walk(const uint8_t* __restrict__ win, int p, int lim, int p_end, bool ended, int r_hi, uint8_t* d) {
+    LaneWalk w = {-1, 0, false, -1, 0, 0, 0, 0};
+    bool in_lead = true;
+    int o = 0;
+    while (p < lim) {
+        int e = p;
+        while (e < p_end) { const uint32_t ch = e >= r_hi ? (uint32_t)'\n' : (uint32_t)win[e]; if (ch == '\t' || ch == '\n') break; e++; }
+        const int len = e - p;
+        if (len == 0) w.err = 1;
+        const int c = len == 3 ? gt_class3(win + p) : 4;
+        const bool is_last = ended && e == p_end;              // the line's last term: its separator is the newline
+        bool normal = true;
+        if (in_lead) {
+            if (c < 4 && (w.lead_c < 0 || c == w.lead_c)) { w.lead_c = c; w.lead_n++; normal = false; }
+            else { in_lead = false; w.lead_closed = w.lead_n > 0; }
+        }
+        if (normal) {
+            if (w.rc >= 0 && (c != w.rc || w.rn == (w.rc == 0 ? 127 : 31))) {
+                if (WRITE) d[o] = (uint8_t)(cls_flag(w.rc) | (uint32_t)w.rn);
+                o++;
+                w.rc = -1;
+            }
+            if (c == 4) {
+                if (WRITE) {
+                    d[o] = (uint8_t)(kTokLit | 1u);
+                    for (int i = 0; i < len; i++) d[o + 1 + i] = win[p + i];
+                    if (!is_last) d[o + 1 + len] = '\t';
+                }
+                o += 1 + len + (is_last ? 0 : 1);
+            } else if (w.rc < 0) {
+                w.rc = c; w.rn = 1;
+            } else {
+                w.rn++;
+            }
+        }
+        w.nterms++;
+        p = e + 1;
+    }
+    w.sz = o;
+    return w;
+}
+
+// Returns the offset where the caller goes on (behind the line's newline: *ended = 1, or ce), -1 for an empty term.
+__device__ __noinline__ int parallel_portion(const uint8_t* __restrict__ win, int pos, int ce, int r_hi, uint8_t* __restrict__ stage,
+                                             int* o_io, int* flushed_io, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
+                                             unsigned long long log_cap, int lane, unsigned long long* seg_first,
+                                             unsigned long long* seg_prev, bool* dead, int* nl_seg, int my_off, int my_off2, int* ended_out,
+                                             int* run_c, int* run_n) {
+    // 1. the portion's end: the line's newline (or the end of the input) when it lies in front of ce -- but at most kParWin
+    //    input bytes per call, so that the output fits the staging area (shared-memory stores, one coalesced flush); the caller
+    //    calls again with the run that is open behind the portion (*run_c, *run_n)
+    constexpr int kParWin = 2048;
+    const int lim_all = min(min(ce, r_hi), pos + kParWin);
+    int p_nl = -1;
+    for (int b0 = pos & ~15; b0 < lim_all && p_nl < 0; b0 += 512) {
+        const int g = b0 + 16 * lane;
+        unsigned nm = 0;
+        if (g + 16 <= r_hi) {
+            const uint4 v = *reinterpret_cast<const uint4*>(win + g);
+            nm = nibble_of(zero_bytes(v.x ^ 0x0A0A0A0Au)) | (nibble_of(zero_bytes(v.y ^ 0x0A0A0A0Au)) << 4) |
+                 (nibble_of(zero_bytes(v.z ^ 0x0A0A0A0Au)) << 8) | (nibble_of(zero_bytes(v.w ^ 0x0A0A0A0Au)) << 12);
+        } else {
+            for (int j = 0; j < 16; j++) if (g + j < r_hi && win[g + j] == '\n') nm |= 1u << j;
+        }
+        if (g < pos) nm &= g + 16 <= pos ? 0u : ~((1u << (pos - g)) - 1u);
+        const unsigned any = __ballot_sync(0xffffffffu, nm != 0u);
+        if (any) {
+            const int l0 = __ffs(any) - 1;
+            p_nl = __shfl_sync(0xffffffffu, g + __ffs(nm) - 1, l0);
+        }
+    }
+    bool ended;
+    int p_end;                                               // index of the separator behind the portion's last term
+    if (p_nl >= 0 && p_nl < lim_all) { ended = true; p_end = p_nl; }
+    else if (lim_all >= r_hi) { ended = true; p_end = r_hi; }          // the input ends without a newline: EOF ends the line
+    else if (lim_all >= ce) { ended = false; p_end = ce - 1; }         // (ce is a term start: the byte in front of it is a tab)
+    else {
+        // the window's last tab; a term longer than the window: up to its end (then the portion gets a log segment of its own)
+        int lt = -1;
+        for (int j = 0; j < kParWin / 32; j++) { const int r = pos + (kParWin / 32) * lane + j; if (win[r] == '\t') lt = r; }
+        lt = __reduce_max_sync(0xffffffffu, lt);
+        ended = false;
+        if (lt >= pos) p_end = lt;
+        else {
+            int e = lim_all;
+            if (lane == 0) { while (e < min(ce, r_hi) && win[e] != '\t' && win[e] != '\n') e++; }
+            e = __shfl_sync(0xffffffffu, e, 0);
+            p_end = e;
+            if (e >= r_hi || win[min(e, r_hi - 1)] == '\n') ended = true;
+        }
+    }
+    // 2. 32 ranges of whole terms: lane L takes the terms that start in [b_L, b_{L+1})
+    const long long span = (long long)(p_end + 1 - pos);
+    int b = pos;
+    if (lane > 0) {
+        int t = pos + (int)(span * lane / 32) - 1;           // the first tab at or behind the nominal start - 1 ends a term
+        if (t < pos) t = pos;
+        while (t < p_end && win[t] != '\t') t++;
+        b = t + 1;                                           // (p_end + 1 when there is no term left)
+    }
+    int b_next = __shfl_down_sync(0xffffffffu, b, 1);
+    if (lane == 31) b_next = p_end + 1;
+    // 3. first walk: sizes and runs
+    const LaneWalk w = lane_walk<false>(win, b, b_next, p_end, ended, r_hi, nullptr);
+    if (__any_sync(0xffffffffu, w.err != 0)) return -1;
+    // 4. the open run, from lane to lane
+    int in_c = *run_c, in_n = *run_n, my_c = -1, my_n = 0;      // (lane 0: the run that is open in front of the portion)
+    if (lane != 0) { in_c = -1; in_n = 0; }
+    for (int L = 0; L < 32; L++) {
+        if (w.nterms == 0) { my_c = in_c; my_n = in_n; }
+        else if (!w.lead_closed && w.lead_c >= 0 && w.rc < 0 && w.lead_n == w.nterms) {      // the whole range is one run
+            const int m = w.lead_c == 0 ? 127 : 31;
+            my_c = w.lead_c;
+            my_n = (((in_c == w.lead_c ? in_n : 0) + w.lead_n - 1) % m) + 1;
+        } else { my_c = w.rc; my_n = w.rn; }
+        const int oc = __shfl_sync(0xffffffffu, my_c, L), on = __shfl_sync(0xffffffffu, my_n, L);
+        if (lane == L + 1) { in_c = oc; in_n = on; }
+    }
+    const int fin_c = __shfl_sync(0xffffffffu, my_c, 31), fin_n = __shfl_sync(0xffffffffu, my_n, 31);
+    // 5. what the incoming run adds in front of the range
+    const bool merged = w.nterms > 0 && w.lead_n > 0 && in_c == w.lead_c;
+    const int c0 = merged ? in_n : 0;
+    const int m_lead = w.lead_c == 0 ? 127 : 31;
+    int pre = 0, fills = 0;
+    if (w.nterms > 0) {
+        if (in_c >= 0 && !merged) pre += 1;                  // my first term ends the incoming run
+        if (w.lead_n > 0) { fills = (c0 + w.lead_n - 1) / m_lead; pre += fills + (w.lead_closed ? 1 : 0); }
+    }
+    const int mine = pre + w.sz;
+    int inc = mine;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, dd); if (lane >= dd) inc += t; }
+    int total = __shfl_sync(0xffffffffu, inc, 31);
+    const int tail = ended ? (fin_c >= 0 ? 2 : 1) : 0;       // the line's last run token and its newline
+    total += tail;
+    // 6. where it goes: the staging area when it fits, else a log segment of its own
+    int o = *o_io, flushed = *flushed_io;
+    if (o - flushed + total > kSStage && (o > flushed || *nl_seg > 0)) {
+        flush_segment(stage, o - flushed, log, ctrl, log_cap, lane, seg_first, seg_prev, dead, *nl_seg, my_off, my_off2);
+        flushed = o; *nl_seg = 0;
+    }
+    uint8_t* dst = stage + (o - flushed);
+    bool own = false;
+    if (o - flushed + total > kSStage) {                     // (the staging area is empty now)
+        own = true;
+        const int body = (total + 15) & ~15;
+        const unsigned long long need = 16ull + (unsigned long long)body;
+        unsigned long long lp = 0ull;
+        if (lane == 0 && !*dead) {
+            lp = atomicAdd(&ctrl->log_cursor, need);
+            if (lp + need > log_cap) { atomicExch(&ctrl->cap_exceeded, 1); lp = ~0ull; }
+        }
+        lp = __shfl_sync(0xffffffffu, lp, 0);
+        if (*dead || lp == ~0ull) { *dead = true; dst = nullptr; }
+        else {
+            dst = log + lp + 16;
+            if (lane == 0) {
+                *reinterpret_cast<uint4*>(log + lp) = make_uint4((unsigned)total, 0u, 0u, 0u);
+                if (*seg_prev) *reinterpret_cast<unsigned long long*>(log + (*seg_prev - 1ull) + 8) = lp;
+            }
+            if (!*seg_first) *seg_first = lp + 1ull;
+            *seg_prev = lp + 1ull;
+        }
+    }
+    // 7. second walk: write
+    if (dst) {
+        uint8_t* d = dst + (inc - mine);
+        int k = 0;
+        if (w.nterms > 0) {
+            if (in_c >= 0 && !merged) d[k++] = (uint8_t)(cls_flag(in_c) | (uint32_t)in_n);
+            if (w.lead_n > 0) {
+                for (int f = 0; f < fills; f++) d[k++] = (uint8_t)(cls_flag(w.lead_c) | (uint32_t)m_lead);
+                if (w.lead_closed) d[k++] = (uint8_t)(cls_flag(w.lead_c) | (uint32_t)(((c0 + w.lead_n - 1) % m_lead) + 1));
+            }
+        }
+        lane_walk<true>(win, b, b_next, p_end, ended, r_hi, d + k);
+        if (ended && lane == 31) {
+            uint8_t* t = dst + (total - tail);
+            if (fin_c >= 0) *t++ = (uint8_t)(cls_flag(fin_c) | (uint32_t)fin_n);
+            *t = '\n';
+        }
+    }
+    __syncwarp();
+    o += total;
+    if (own) flushed = o;
+    *o_io = o; *flushed_io = flushed;
+    *ended_out = ended ? 1 : 0;
+    *run_c = ended ? -1 : fin_c; *run_n = ended ? 0 : fin_n;
+    return p_end + 1;
 }
 
 // What to do with a step that holds a sample column that is not 3 bytes + separator.  Everything before the first such column q
@@ -590,12 +803,27 @@ __device__ __noinline__ OddOut odd_step(const uint8_t* __restrict__ win, int bas
     if (r < 0) { out.flags |= r == -1 ? kOddEmpty : kOddGiveUp; return out; }   // an empty sample column / the block is given up
     int over = 0;
     if (lane == 0 && atomicAdd(&ctrl->serial_bytes, (unsigned long long)(r - a)) > serial_budget) over = 1;
-    if (__shfl_sync(0xffffffffu, over, 0)) { out.flags |= kOddGiveUp; return out; }   // mostly odd-width samples: generic kernels
+    if (__shfl_sync(0xffffffffu, over, 0)) { out.flags |= kOddGiveUp; return out; }   // (a safety valve: generic kernels)
     out.cur = r;
+    if (VCFC_ENC_PARWALK && ended == 2) {                // eight odd-width terms in a row: the rest of the portion with all lanes
+        int run_c = -1, run_n = 0, at = r;
+        ended = 0;
+        while (!ended && at < ce) {
+            at = parallel_portion(win, at, ce, r_hi, stage, &out.o, &out.flushed, log, ctrl, log_cap, lane, seg_first, seg_prev, dead,
+                                  &out.nl_seg, my_off, my_off2, &ended, &run_c, &run_n);
+            if (at < 0) { out.flags |= kOddEmpty; return out; }
+        }
+        out.cur = at;                                    // (at ce with a run open: the next tile's look-back record has it)
+    }
     if (ended) out.flags |= kOddLineEnd;
     return out;
 }
 
+// kOdd = false: the kernel of regular blocks -- a sample column that is not 3 bytes + separator gives the block up with reject
+// reason kRejectOddTerms, and the host launches it again with kOdd = true (the term walkers compiled in; that instantiation is
+// ~4 % slower on regular blocks, which is why there are two).  The context remembers which one its stream of blocks needs.
+constexpr int kRejectOddTerms = 9;
+template <bool kOdd>
 __global__ void __launch_bounds__(32 * kSWarps, kSCtas)
 k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
                 unsigned int* __restrict__ s1, unsigned long long* __restrict__ rec_pos, unsigned long long* __restrict__ rec_size,
@@ -915,14 +1143,11 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                             L |= 1u << k;
                         }
                     }
-#if VCFC_ENC_NOSERIAL
-                    if (__any_sync(0xffffffffu, irr)) { irregular = 6; break; }
-#else
                     if (__any_sync(0xffffffffu, irr)) {      // a sample column that is not 3 bytes + separator: handled behind the loop
+                        if constexpr (!kOdd) { irregular = VCFC_ENC_NOSERIAL ? 6 : kRejectOddTerms; break; }
                         odd_pending = true; odd_a = a; odd_base = base; odd_nc0 = V; odd_kend = kend; odd_irr = irr;
                         break;
                     }
-#endif
                 }
                 const uint32_t F = (first && lane == 0) ? (1u << klo) : 0u;
                 const uint32_t Cprev = (Craw << 1) | pc_all;
@@ -973,11 +1198,12 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 if (endm) { cur = q_end + 1; in_req = true; }
                 else cur = a + 4 * ((bound - a + 3) >> 2);
             }
+            if constexpr (!kOdd) break;
             if (!odd_pending) {
                 if (ce != sm.ce_true[warp] && !irregular) { ce = sm.ce_true[warp]; continue; }   // the capped redo is done: on to the odd sample
                 break;
             }
-            {   // (out of the hot loop: the grid steps' register allocation does not see this)
+            if constexpr (kOdd) {   // (out of the hot loop: the grid steps' register allocation does not see this)
                 odd_pending = false;
                 const OddOut r = odd_step(win, odd_base, odd_nc0, odd_kend, odd_irr, odd_a, ce, cs, r_lo, r_hi, first, need_lb, ein_carry, pc0, tile, s1,
                                           stage, o, flushed, nl_seg, my_off, my_off2, log, ctrl, log_cap, serial_budget, lane, &seg_first, &seg_prev, &dead);
@@ -1077,7 +1303,7 @@ __global__ void k_patch_headers(uint8_t* __restrict__ out, const unsigned long l
         res->err_line = 0;
         if (irregular) { res->status = kStatusIrregular; res->reserved = irregular; res->out_len = 0; res->n_lines = 0; res->err_line = nl; }
         else if (cap)  { res->status = VCFC_E_CAP; res->out_len = total; res->n_lines = 0; }
-        else           { res->status = VCFC_OK; res->out_len = total; res->n_lines = nl; }
+        else           { res->status = VCFC_OK; res->out_len = total; res->n_lines = nl; res->reserved = ctrl->serial_bytes ? 1 : 0; }   // (reserved: term walkers used)
     }
 }
 
@@ -1107,7 +1333,8 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         return VCFC_OK;
     }
     if (!ctx->enc_attr_set) {                                  // per context: one context per (process, device), used by one thread at a time
-        VCFC_CUDA(ctx, cudaFuncSetAttribute(k_encode_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
+        VCFC_CUDA(ctx, cudaFuncSetAttribute(k_encode_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
+        VCFC_CUDA(ctx, cudaFuncSetAttribute(k_encode_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
         ctx->enc_attr_set = 1;
     }
     // tile size (a multiple of 64): large tiles amortise the per-tile work (cuts, look-back record, log reservation), small
@@ -1140,8 +1367,10 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
     VCFC_CUDA(ctx, cudaMemcpyAsync(&ctrl->line_cap, caps, sizeof(caps), cudaMemcpyHostToDevice, stream));
     if (!ctx->enc_resident) {       // CTAs that are guaranteed to be co-resident (look-back #1 spins on its neighbour)
         int per_sm = 0;
-        VCFC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_stream, 32 * kSWarps, sizeof(SmemS)));
-        ctx->enc_resident = std::max(1, per_sm) * ctx->sm_count;
+        int per_sm_odd = 0;
+        VCFC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_stream<false>, 32 * kSWarps, sizeof(SmemS)));
+        VCFC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_odd, k_encode_stream<true>, 32 * kSWarps, sizeof(SmemS)));
+        ctx->enc_resident = std::max(1, std::min(per_sm, per_sm_odd)) * ctx->sm_count;
     }
     const int resident = ctx->enc_resident;
     const unsigned grid = (unsigned)std::min<size_t>((n_tiles + kSWarps - 1) / kSWarps, (size_t)resident);
@@ -1155,7 +1384,8 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         unsigned long long a_cap = (unsigned long long)log_cap;
         unsigned long long a_budget = (unsigned long long)(in_len / 32 + (1u << 18));  // odd-width terms beyond ~3 % of the block: generic kernels
         void* args[] = {&a_in, &a_n, &a_log, &ctrl, &a_s1, &rec_pos, &rec_size, &rec_lines, &a_tiles, &a_cap, &a_tile_sz, &a_budget};
-        VCFC_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_encode_stream, dim3(grid), dim3(32 * kSWarps), args, sizeof(SmemS), stream));
+        const void* kern = ctx->enc_odd ? (const void*)k_encode_stream<true> : (const void*)k_encode_stream<false>;
+        VCFC_CUDA(ctx, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(32 * kSWarps), args, sizeof(SmemS), stream));
     }
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeEncode + 1], stream); ctx->ev_pending[kTimeEncode] = 1; }
     ctx->launches += 1;

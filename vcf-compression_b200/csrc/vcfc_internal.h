@@ -44,6 +44,8 @@ struct vcfc_ctx {
     // launch configuration of the cooperative encoder, per context (= per device)
     int          enc_attr_set = 0;
     int          enc_resident = 0;
+    int          enc_odd = 0;         // the encoder instantiation with the odd-width term walkers is in use (vcfc_encode_block_dev)
+    int          enc_odd_idle = 0;    // blocks in a row that did not need it
     int          dec_attr_set = 0;
     vcfc_result* h_result = nullptr;      // pinned
     vcfc_result* d_result = nullptr;
