@@ -319,6 +319,43 @@ def test_gt_dp_gq_block(codec):
     check_block(codec, (b"".join(lines[:5]))[:-1], sample_count=500, expect_path=pkg.PATH_FAST)
 
 
+def test_odd_stretch_transitions(codec):
+    """parallel_portion's ways out and in: a stretch of odd-width terms followed by thousands of 3-byte terms (the grid takes over
+    with the run that is open, at every chunk phase), a literal longer than the 2 KB window in the middle of odd terms (the term
+    walker takes it), windows that end in 3-byte runs at the 31 / 127 limits, the next line going to the walkers at once, and an
+    empty term inside an odd stretch (rejected like everywhere else)."""
+    rng = __import__("random").Random(77)
+    req = b"X\t55\t.\tA\tC\t.\t.\tDP=1\tGT:DP\t"
+    odd = lambda n: [b"%s:%d" % (rng.choice((b"0|0", b"0|1", b"1|1", b"./.")), rng.randrange(200)) for _ in range(n)]
+    lines = []
+    for gt, m in ((b"0|0", 127), (b"0|1", 31), (b"1|0", 31)):
+        for n_odd in (9, 40, 300, 777):
+            for n_reg in (1, 30, 31, 32, 126, 127, 128, 400, 513, 5000):
+                lines.append(req + b"\t".join(odd(n_odd) + [gt] * n_reg) + b"\n")
+                lines.append(req + b"\t".join(odd(n_odd) + [gt] * n_reg + odd(3) + [gt] * 40) + b"\n")
+                lines.append(req + b"\t".join([gt] * n_reg + odd(n_odd) + [gt] * (n_reg + 1) + odd(n_odd)) + b"\n")
+    check_block(codec, b"".join(lines), expect_path=pkg.PATH_FAST)
+    rng.shuffle(lines)
+    check_block(codec, b"".join(lines), expect_path=pkg.PATH_FAST)
+    # literals of 2 ... 9 KB among odd terms; right behind the line start; as the line's last term
+    for big in (2040, 2048, 2049, 4100, 9000):
+        blob = b"0|1:" + b"7" * big
+        ls = [req + b"\t".join(odd(50) + [blob] + odd(50) + [b"0|0"] * 200) + b"\n",
+              req + b"\t".join([blob] + odd(20)) + b"\n",
+              req + b"\t".join(odd(20) + [blob]) + b"\n",
+              req + b"\t".join(odd(300) + [blob, blob] + [b"1|1"] * 70 + odd(9)) + b"\n"]
+        check_block(codec, b"".join(ls) * 2, expect_path=pkg.PATH_FAST)
+        check_block(codec, (b"".join(ls) * 2)[:-1], expect_path=pkg.PATH_FAST)
+    # haploid calls only (2-byte terms: 32 per block), and 1-byte / 3-byte mixes that end exactly at window ends
+    for n in (1000, 1023, 1024, 1025, 4096, 20000):
+        hap = [rng.choice((b"0", b"1", b".")) for _ in range(n)]
+        mix = [rng.choice((b"0", b"0|0", b"0|0", b"1|1", b"10")) for _ in range(n)]
+        check_block(codec, req + b"\t".join(hap) + b"\n" + req + b"\t".join(mix) + b"\n" + req + b"\t".join(hap), expect_path=pkg.PATH_FAST)
+    # an empty term inside an odd stretch: the reference drops it (utils.cpp:82-116), the tile path hands the block on
+    bad = req + b"\t".join(odd(30) + [b""] + odd(30)) + b"\n"
+    check_block(codec, lines[0] + bad + lines[1])
+
+
 def test_ragged_and_empty_inputs(any_path):
     rc, out, nl, _ = any_path.compress_block(b"")
     assert rc == 0 and out == b"" and nl == 0

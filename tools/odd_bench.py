@@ -53,8 +53,10 @@ def run(name, text: bytes, samples: int, codec, dev, with_generic=True):
     st = torch.cuda.current_stream().cuda_stream
     res = {"workload": name, "bytes": n}
     codec.force_generic(0)
+    codec.set_timing(True)
     ms, olen, nl, path = timed(codec, d_in, n, d_out, cap, d_res, st)
-    res["encode"] = {"gbs": n / ms / 1e6, "ms": ms, "path": path, "out_bytes": olen, "lines": nl}
+    res["encode"] = {"gbs": n / ms / 1e6, "ms": ms, "kernel_ms": codec.last_kernel_ms(0), "path": path, "out_bytes": olen, "lines": nl}
+    codec.set_timing(False)
     dms, tlen, dpath = timed_dec(codec, d_out, olen, samples, d_txt, d_res, st)
     res["decode"] = {"gbs": n / dms / 1e6, "ms": dms, "path": dpath, "round_trip": bool(tlen == n and torch.equal(d_txt[:n], d_in[:n]))}
     # oracle on the first 2 MB of whole lines
@@ -76,17 +78,28 @@ def run(name, text: bytes, samples: int, codec, dev, with_generic=True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lines", type=int, default=200000)
+    ap.add_argument("--every", type=int, default=100, help="one line in this many carries odd-width samples")
+    ap.add_argument("--only-mixed", action="store_true")
+    ap.add_argument("--only-gtdp", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     codec = pkg.Codec(0)
     rng = random.Random(1)
     odd = [b"10|0", b"0|10", b".", b"0", b"1", b"0|1:35:99", b"./.:."]
+    if not args.only_gtdp:
+        mixed_part(args, codec, dev, rng, odd)
+    if args.only_mixed:
+        return
+    gtdp_part(args, codec, dev)
+
+
+def mixed_part(args, codec, dev, rng, odd):
     # (a) config-2 shape, 1 % of the lines carry a few odd-width samples
     d, lens = vcfsynth.generate("kg", args.lines, 2504, seed=20, device=dev)
     text = d.cpu().numpy().tobytes()
     starts = np.concatenate([[0], np.cumsum(lens.cpu().numpy())])
     pieces, prev = [], 0
-    for li in range(0, args.lines, 100):
+    for li in range(0, args.lines, args.every):
         a, b = int(starts[li]), int(starts[li + 1])
         cols = text[a:b - 1].split(b"\t")
         for _ in range(5):
@@ -95,8 +108,15 @@ def main():
     pieces.append(text[prev:])
     mixed = b"".join(pieces)
     run("regular (config 2 shape)", text, 2504, codec, dev, with_generic=False)
-    run("config 2 shape, 1 % of the lines with 5 odd-width samples each", mixed, 2504, codec, dev)
-    del d, text, mixed, pieces
+    os.environ["VCFC_ENC_FORCE_ODD"] = "1"          # the same block on the encoder instantiation that carries the term walkers
+    codec_odd = pkg.Codec(0)
+    del os.environ["VCFC_ENC_FORCE_ODD"]
+    run("regular, on the encoder instantiation with the term walkers", text, 2504, codec_odd, dev, with_generic=False)
+    del codec_odd
+    run("config 2 shape, 1 line in %d with 5 odd-width samples" % args.every, mixed, 2504, codec, dev, with_generic=not args.only_mixed)
+
+
+def gtdp_part(args, codec, dev):
     # (b) all GT:DP:GQ
     L, S = max(1000, args.lines // 4), 1000
     g = np.random.default_rng(3)
@@ -109,7 +129,7 @@ def main():
     rows = [b"3\t%d\t.\tC\tT\t.\tPASS\tDP=100\tGT:DP:GQ\t" % (1000 + i) for i in range(L)]
     body = cell.reshape(L, S * 10)
     gtdp = b"".join(r + body[i].tobytes() for i, r in enumerate(rows))
-    run("all GT:DP:GQ (1000 samples per line)", gtdp, S, codec, dev)
+    run("all GT:DP:GQ (1000 samples per line)", gtdp, S, codec, dev, with_generic=not args.only_gtdp)
 
 
 main()

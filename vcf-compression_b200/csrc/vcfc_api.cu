@@ -70,6 +70,8 @@ int vcfc_gpu_init(int device, vcfc_ctx** out) {
         vcfc_gpu_destroy(ctx);
         return VCFC_E_CUDA;
     }
+    ctx->enc_odd_keep = env_size("VCFC_ENC_FORCE_ODD", 0) != 0;   // (tests / tuning: always the encoder instantiation with the term walkers)
+    ctx->enc_odd = ctx->enc_odd_keep;
     *out = ctx;
     return VCFC_OK;
 }
@@ -180,7 +182,7 @@ int vcfc_encode_block_dev(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uin
             if (status != kStatusIrregular) {
                 if (ctx->enc_odd && status == VCFC_OK) {
                     ctx->enc_odd_idle = ctx->h_result[2].reserved ? 0 : ctx->enc_odd_idle + 1;
-                    if (ctx->enc_odd_idle >= 8) { ctx->enc_odd = 0; ctx->enc_odd_idle = 0; }
+                    if (ctx->enc_odd_idle >= 8 && !ctx->enc_odd_keep) { ctx->enc_odd = 0; ctx->enc_odd_idle = 0; }
                 }
                 return VCFC_OK;
             }

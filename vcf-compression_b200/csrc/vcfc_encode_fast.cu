@@ -25,6 +25,7 @@
 //      (they need the NEXT line's offset) and the result block.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "vcfc_common.cuh"
 #include "vcfc_internal.h"
@@ -49,6 +50,7 @@ struct Ctrl {                           // one per launch, zeroed by the host
     unsigned long long line_cap;
     unsigned long long log_cursor, log_cap;   // the tile log: tile outputs in arrival order, gathered by k_gather_tiles
     unsigned long long serial_bytes;          // input bytes walked term by term (odd-width samples); too many: generic kernels
+    int odd_used;                             // the term walkers ran (the host keeps launching the instantiation that has them)
 };
 
 __device__ __forceinline__ bool is_sep(uint32_t c) { return c == '\t' || c == '\n'; }
@@ -344,7 +346,20 @@ static_assert(kSStage >= 1024 + 1024 + 64, "the term walker splits the staging a
 
 struct SmemS {
     alignas(16) uint8_t stage[kSWarps][kSStage + 16];
-    int ce_true[kSWarps];                        // the tile's end cut, while `ce` is lowered for a redone step
+};
+// (kOdd) Everything the warp knows, parked in shared memory while odd_step runs: a value that is live across that call gets a
+// stack slot for its whole life (few registers survive a call), and the hot loop then reads its state from local memory --
+// measured +33 % on regular steps.  With the state saved here and read back behind the call, nothing is live across it.
+struct OddSave {
+    int o, flushed, nl, nl_seg, cur, ein_carry, ein0, bits, irregular;    // bits: in_req | first << 1 | need_lb << 2
+    int ce, cs, pc0, tile, nt, nn, cur_ce, cur_fl, irr_seen, fl;
+    int odd_a, odd_direct;                       // the step that met an odd-width sample column (direct: see odd_step)
+    int par_mode;                                // the last odd-width stretch ended with odd terms: the next line goes to the walkers at once
+    int action;                                  // what odd_call decided: 0 go on, 2 give the block up
+    int my_off[32], my_off2[32];
+};
+struct SmemSO : SmemS {
+    OddSave odd[kSWarps];
 };
 
 // byte / word of the input at tile-relative offset r (win = in + gb); outside [0, n) reads as 0
@@ -429,25 +444,13 @@ __device__ int line_scan16(const uint8_t* __restrict__ win, int ls, int r_lo, in
     return -1;
 }
 
-// The lane's first valid sample (offset) that is not 3 bytes + separator: the tests of the step's validation loop, run again
-// over all valid samples on the rare steps that hold such a sample (kept out of the hot loop).
-__device__ __noinline__ int first_odd_sample(const uint8_t* __restrict__ win, int base, uint32_t valid, int kend, int r_lo, int r_hi) {
-    for (uint32_t t = valid; t; t &= t - 1) {
-        const int k = __ffs(t) - 1, r0 = base + 4 * k;
-        const uint32_t b0 = ldb_nl(win, r0, r_lo, r_hi), b1 = ldb_nl(win, r0 + 1, r_lo, r_hi), b2 = ldb_nl(win, r0 + 2, r_lo, r_hi),
-                       b3 = ldb_nl(win, r0 + 3, r_lo, r_hi);
-        if (k == kend ? (b3 != '\n') : (b3 != '\t')) return r0;
-        if (is_sep(b0) || is_sep(b1) || is_sep(b2)) return r0;
-    }
-    return 0x7fffffff;
-}
-
-// The rest of a line whose samples are not all 3 bytes wide, from term start `pos` to the line's end or the tile's end cut
-// `ce` (a term start): compress_data_line's sample loop (compress.cpp:124-190) term by term, by lane 0.  The warp stages the
+// A term that is longer than parallel_portion's window (a multi-kilobyte literal), from its start `pos`: compress_data_line's
+// sample loop (compress.cpp:124-190) term by term, by lane 0, until that term is out (*ended = 2: all lanes go on behind it),
+// the line ends (*ended = 1) or the tile's end cut `ce` (a term start) is reached.  The warp stages the
 // next kSerWin input bytes in the upper part of its staging area (lane 0 then walks shared memory, not global memory); output
 // goes to the lower part and is flushed to the log when it fills up (both warp-collective, hence the outer loop).
-// rc / rn: the run that is open at pos.  The walker stops behind an odd-width term when the next term is 3 bytes wide (the grid
-// takes over again), at the line's end (*ended = 1) or at ce; it returns the offset where the caller goes on, -1 for an empty term.
+// rc / rn: the run that is open at pos.  Returns the offset where the caller goes on, -1 for an empty term, -2 when the block
+// has been given up meanwhile.
 constexpr int kSerWin = 1024;                               // input window of the term walker
 __device__ __noinline__ int serial_portion(const uint8_t* __restrict__ win, int pos, int ce, int r_hi, int rc, int rn,
                                            uint8_t* __restrict__ stage, int* o_io, int* flushed_io, uint8_t* __restrict__ log,
@@ -501,7 +504,7 @@ __device__ __noinline__ int serial_portion(const uint8_t* __restrict__ win, int 
                 }
                 if (lit_tab) { stage[fill++] = '\t'; lit_tab = 0; continue; }
                 if (stop_after) { result = pos; done = true; break; }
-                if (VCFC_ENC_PARWALK && n_odd >= 8 && rc < 0 && !line_end && pos < ce) { result = pos; want_all = true; done = true; break; }   // odd terms in a row: all lanes take over
+                if (n_odd >= 1 && rc < 0 && !line_end && pos < ce) { result = pos; want_all = true; done = true; break; }   // the long term is out: all lanes again
                 if (line_end) {
                     if (rc >= 0) stage[fill++] = (uint8_t)(cls_flag(rc) | (uint32_t)rn);
                     stage[fill++] = '\n';
@@ -562,30 +565,42 @@ __device__ __noinline__ int serial_portion(const uint8_t* __restrict__ win, int 
 }
 
 // ---- many odd-width terms in a row (a GT:DP:GQ file, haploid calls): the rest of the line portion, ALL LANES walking ------------
-// The portion [pos, end of line or ce) is cut into 32 ranges of whole terms; every lane walks its range twice with the sample
-// loop of compress_data_line (compress.cpp:124-190): once to size it and to learn the run it begins with / ends with, once to
-// write.  In between, the open run is handed from lane to lane (a lane that is one single run hands on what it got, extended),
-// and what the incoming run costs a lane is closed form: a closing token when the lane's first term differs, chunk-fill
-// tokens every 127 / 31 samples of a leading run that continues it.
-struct LaneWalk {                 // one lane's range, walked without an incoming run
+// A window of 2 KB (32 blocks of 64 bytes, one per lane): every lane turns its block into a 64-bit separator mask (word-parallel
+// byte tests) and owns the terms that START in its block; a term's end is the next set bit of the mask (its own, or the first
+// one of the lanes behind it).  Every lane walks its terms twice with the sample loop of compress_data_line
+// (compress.cpp:124-190): once to size them and to learn the run it begins with / ends with, once to write.  In between, the
+// open run is handed from lane to lane (a lane that is one single run hands on what it got, extended), and what the incoming run
+// costs a lane is closed form: a closing token when the lane's first term differs, chunk-fill tokens every 127 / 31 samples of
+// a leading run that continues it.
+struct LaneWalk {                 // one lane's terms, walked without an incoming run
     int lead_c, lead_n;           // the leading run: class (-1: the range begins with a literal or is empty), samples
     bool lead_closed;             // a later term of the range ends it (else the whole range is that one run)
     int rc, rn;                   // the run that is open behind the range when it is not the leading one (-1: none)
     int sz;                       // bytes behind the leading run's tokens
-    int nterms, err;
+    int nterms, err, n_odd;       // terms, empty terms, terms that are not 3 bytes wide
 };
 
-// WRITE: emits into d (the caller has put the leading run's tokens there already) and returns the bytes written; else sizes only.
+__device__ __forceinline__ unsigned long long bits_from(int k) {     // mask of the bit positions >= k (k may be < 0 or > 63)
+    return k <= 0 ? ~0ull : (k >= 64 ? 0ull : (~0ull << k));
+}
+
+// T: the block's term starts, S: its separators (bit i = byte B + i); nxt: first separator behind the block.
+// WRITE: emits into d (the caller has put the leading run's tokens there already); else sizes only.
 template <bool WRITE>
-__device__ __forceinline__ LaneWalk lane_walk(const uint8_t* __restrict__ win, int p, int lim, int p_end, bool ended, int r_hi, uint8_t* d) {
-    LaneWalk w = {-1, 0, false, -1, 0, 0, 0, 0};
+__device__ __forceinline__ LaneWalk lane_walk(const uint8_t* __restrict__ win, int B, unsigned long long T, unsigned long long S, int nxt,
+                                              int p_end, bool ended, uint8_t* d) {
+    LaneWalk w = {-1, 0, false, -1, 0, 0, 0, 0, 0};
     bool in_lead = true;
     int o = 0;
-    while (p < lim) {
-        int e = p;
-        while (e < p_end) { const uint32_t ch = e >= r_hi ? (uint32_t)'\n' : (uint32_t)win[e]; if (ch == '\t' || ch == '\n') break; e++; }
+    while (T) {
+        const int i = __ffsll((long long)T) - 1;
+        T &= T - 1ull;
+        const unsigned long long sm = S >> i;
+        const int p = B + i;
+        const int e = sm ? p + __ffsll((long long)sm) - 1 : nxt;
         const int len = e - p;
         if (len == 0) w.err = 1;
+        if (len != 3) w.n_odd++;
         const int c = len == 3 ? gt_class3(win + p) : 4;
         const bool is_last = ended && e == p_end;              // the line's last term: its separator is the newline
         bool normal = true;
@@ -602,7 +617,7 @@ __device__ __forceinline__ LaneWalk lane_walk(const uint8_t* __restrict__ win, i
             if (c == 4) {
                 if (WRITE) {
                     d[o] = (uint8_t)(kTokLit | 1u);
-                    for (int i = 0; i < len; i++) d[o + 1 + i] = win[p + i];
+                    for (int k = 0; k < len; k++) d[o + 1 + k] = win[p + k];
                     if (!is_last) d[o + 1 + len] = '\t';
                 }
                 o += 1 + len + (is_last ? 0 : 1);
@@ -613,87 +628,105 @@ __device__ __forceinline__ LaneWalk lane_walk(const uint8_t* __restrict__ win, i
             }
         }
         w.nterms++;
-        p = e + 1;
     }
     w.sz = o;
     return w;
 }
 
-// Returns the offset where the caller goes on (behind the line's newline: *ended = 1, or ce), -1 for an empty term.
+// Returns the offset where the caller goes on (behind the line's newline: *ended_out = 1, or ce), -1 for an empty term, -2 when
+// the term at pos is longer than the window (the term walker takes it).  *odd_out: terms of the portion that are not 3 bytes wide.
 __device__ __noinline__ int parallel_portion(const uint8_t* __restrict__ win, int pos, int ce, int r_hi, uint8_t* __restrict__ stage,
                                              int* o_io, int* flushed_io, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
                                              unsigned long long log_cap, int lane, unsigned long long* seg_first,
                                              unsigned long long* seg_prev, bool* dead, int* nl_seg, int my_off, int my_off2, int* ended_out,
-                                             int* run_c, int* run_n) {
-    // 1. the portion's end: the line's newline (or the end of the input) when it lies in front of ce -- but at most kParWin
-    //    input bytes per call, so that the output fits the staging area (shared-memory stores, one coalesced flush); the caller
-    //    calls again with the run that is open behind the portion (*run_c, *run_n)
+                                             int* run_c, int* run_n, int* odd_out) {
+    // 1. separator masks of the window's 32 blocks; bytes behind the input read as '\n' (EOF ends the line)
     constexpr int kParWin = 2048;
-    const int lim_all = min(min(ce, r_hi), pos + kParWin);
-    int p_nl = -1;
-    for (int b0 = pos & ~15; b0 < lim_all && p_nl < 0; b0 += 512) {
-        const int g = b0 + 16 * lane;
-        unsigned nm = 0;
-        if (g + 16 <= r_hi) {
-            const uint4 v = *reinterpret_cast<const uint4*>(win + g);
-            nm = nibble_of(zero_bytes(v.x ^ 0x0A0A0A0Au)) | (nibble_of(zero_bytes(v.y ^ 0x0A0A0A0Au)) << 4) |
-                 (nibble_of(zero_bytes(v.z ^ 0x0A0A0A0Au)) << 8) | (nibble_of(zero_bytes(v.w ^ 0x0A0A0A0Au)) << 12);
-        } else {
-            for (int j = 0; j < 16; j++) if (g + j < r_hi && win[g + j] == '\n') nm |= 1u << j;
+    const int wstart = pos & ~63, wend = wstart + kParWin, B = wstart + 64 * lane;
+    uint32_t s_lo = 0, s_hi = 0, nl_any = 0;
+    if (B + 64 <= r_hi) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 v = *reinterpret_cast<const uint4*>(win + B + 16 * q);
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+            uint32_t nib = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t zn = zero_bytes(wv[j] ^ 0x0A0A0A0Au);
+                nl_any |= zn;
+                nib |= nibble_of(zero_bytes(wv[j] ^ 0x09090909u) | zn) << (4 * j);
+            }
+            if (q < 2) s_lo |= nib << (16 * q); else s_hi |= nib << (16 * (q - 2));
         }
-        if (g < pos) nm &= g + 16 <= pos ? 0u : ~((1u << (pos - g)) - 1u);
-        const unsigned any = __ballot_sync(0xffffffffu, nm != 0u);
-        if (any) {
-            const int l0 = __ffs(any) - 1;
-            p_nl = __shfl_sync(0xffffffffu, g + __ffs(nm) - 1, l0);
+    } else {
+#pragma unroll 1
+        for (int q = 0; q < 16; q++) {
+            const uint32_t wv = ldw_edge(win, B + 4 * q, 0, r_hi, 0x0A0A0A0Au);
+            const uint32_t zn = zero_bytes(wv ^ 0x0A0A0A0Au);
+            nl_any |= zn;
+            const uint32_t nib = nibble_of(zero_bytes(wv ^ 0x09090909u) | zn);
+            if (q < 8) s_lo |= nib << (4 * q); else s_hi |= nib << (4 * (q - 8));
         }
     }
+    const unsigned long long S = (unsigned long long)s_lo | ((unsigned long long)s_hi << 32);
+    const unsigned long long Sp = S & bits_from(pos - B);      // separators at or behind pos
+    // 2. the portion's end: the line's newline (or the end of the input) when it lies in front of ce, else ce, else the window's
+    //    last separator (the caller calls again with the run that is open there: *run_c, *run_n)
+    int my_nl = -1;
+    if (nl_any) {
+        for (unsigned long long c = Sp; c; c &= c - 1ull) {
+            const int g = B + __ffsll((long long)c) - 1;
+            if (g >= r_hi || win[g] == '\n') { my_nl = g; break; }
+        }
+    }
+    const unsigned nlm = __ballot_sync(0xffffffffu, my_nl >= 0);
+    const int p_nl = nlm ? __shfl_sync(0xffffffffu, my_nl, __ffs(nlm) - 1) : -1;
     bool ended;
     int p_end;                                               // index of the separator behind the portion's last term
-    if (p_nl >= 0 && p_nl < lim_all) { ended = true; p_end = p_nl; }
-    else if (lim_all >= r_hi) { ended = true; p_end = r_hi; }          // the input ends without a newline: EOF ends the line
-    else if (lim_all >= ce) { ended = false; p_end = ce - 1; }         // (ce is a term start: the byte in front of it is a tab)
-    else {
-        // the window's last tab; a term longer than the window: up to its end (then the portion gets a log segment of its own)
-        int lt = -1;
-        for (int j = 0; j < kParWin / 32; j++) { const int r = pos + (kParWin / 32) * lane + j; if (win[r] == '\t') lt = r; }
-        lt = __reduce_max_sync(0xffffffffu, lt);
+    if (p_nl >= 0 && (p_nl < ce || ce >= r_hi)) { ended = true; p_end = p_nl; }
+    else if (ce <= wend) {
+        if (ce >= r_hi) { ended = true; p_end = r_hi; }      // the input ends without a newline: EOF ends the line
+        else { ended = false; p_end = ce - 1; }              // (ce is a term start: the byte in front of it is a tab)
+    } else {
+        const unsigned hm = __ballot_sync(0xffffffffu, Sp != 0ull);
+        if (!hm) return -2;                                  // no separator in the window: one long term
+        const int lt = B + 63 - __clzll((long long)Sp);
         ended = false;
-        if (lt >= pos) p_end = lt;
-        else {
-            int e = lim_all;
-            if (lane == 0) { while (e < min(ce, r_hi) && win[e] != '\t' && win[e] != '\n') e++; }
-            e = __shfl_sync(0xffffffffu, e, 0);
-            p_end = e;
-            if (e >= r_hi || win[min(e, r_hi - 1)] == '\n') ended = true;
-        }
+        p_end = __shfl_sync(0xffffffffu, lt, 31 - __clz(hm));
     }
-    // 2. 32 ranges of whole terms: lane L takes the terms that start in [b_L, b_{L+1})
-    const long long span = (long long)(p_end + 1 - pos);
-    int b = pos;
-    if (lane > 0) {
-        int t = pos + (int)(span * lane / 32) - 1;           // the first tab at or behind the nominal start - 1 ends a term
-        if (t < pos) t = pos;
-        while (t < p_end && win[t] != '\t') t++;
-        b = t + 1;                                           // (p_end + 1 when there is no term left)
-    }
-    int b_next = __shfl_down_sync(0xffffffffu, b, 1);
-    if (lane == 31) b_next = p_end + 1;
-    // 3. first walk: sizes and runs
-    const LaneWalk w = lane_walk<false>(win, b, b_next, p_end, ended, r_hi, nullptr);
+    // 3. term starts of the block: the byte behind a separator, and pos itself; the first separator behind the block
+    const unsigned prev_hi = __shfl_up_sync(0xffffffffu, s_hi >> 31, 1);
+    unsigned long long T = ((S << 1) | (unsigned long long)(lane > 0 ? (prev_hi & 1u) : 0u)) & bits_from(pos - B);
+    if (pos >= B && pos < B + 64) T |= 1ull << (pos - B);
+    T &= ~bits_from(p_end + 1 - B);
+    int nxt = S ? B + __ffsll((long long)S) - 1 : 0x7fffffff;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) { const int t = __shfl_down_sync(0xffffffffu, nxt, dd); if (lane + dd < 32) nxt = min(nxt, t); }
+    nxt = __shfl_down_sync(0xffffffffu, nxt, 1);
+    if (lane == 31 || nxt > p_end) nxt = p_end;
+    // first walk: sizes and runs
+    const LaneWalk w = lane_walk<false>(win, B, T, S, nxt, p_end, ended, nullptr);
     if (__any_sync(0xffffffffu, w.err != 0)) return -1;
+    *odd_out = __reduce_add_sync(0xffffffffu, w.n_odd);
     // 4. the open run, from lane to lane
     int in_c = *run_c, in_n = *run_n, my_c = -1, my_n = 0;      // (lane 0: the run that is open in front of the portion)
     if (lane != 0) { in_c = -1; in_n = 0; }
-    for (int L = 0; L < 32; L++) {
-        if (w.nterms == 0) { my_c = in_c; my_n = in_n; }
-        else if (!w.lead_closed && w.lead_c >= 0 && w.rc < 0 && w.lead_n == w.nterms) {      // the whole range is one run
-            const int m = w.lead_c == 0 ? 127 : 31;
-            my_c = w.lead_c;
-            my_n = (((in_c == w.lead_c ? in_n : 0) + w.lead_n - 1) % m) + 1;
-        } else { my_c = w.rc; my_n = w.rn; }
-        const int oc = __shfl_sync(0xffffffffu, my_c, L), on = __shfl_sync(0xffffffffu, my_n, L);
-        if (lane == L + 1) { in_c = oc; in_n = on; }
+    const bool one_run = !w.lead_closed && w.lead_c >= 0 && w.rc < 0 && w.lead_n == w.nterms;   // the whole range is one run
+    if (!__any_sync(0xffffffffu, w.nterms == 0 || one_run)) {   // every lane leaves a run of its own making (or none) behind
+        my_c = w.rc; my_n = w.rn;
+        const int oc = __shfl_up_sync(0xffffffffu, my_c, 1), on = __shfl_up_sync(0xffffffffu, my_n, 1);
+        if (lane > 0) { in_c = oc; in_n = on; }
+    } else {
+        for (int L = 0; L < 32; L++) {
+            if (w.nterms == 0) { my_c = in_c; my_n = in_n; }
+            else if (one_run) {
+                const int m = w.lead_c == 0 ? 127 : 31;
+                my_c = w.lead_c;
+                my_n = (((in_c == w.lead_c ? in_n : 0) + w.lead_n - 1) % m) + 1;
+            } else { my_c = w.rc; my_n = w.rn; }
+            const int oc = __shfl_sync(0xffffffffu, my_c, L), on = __shfl_sync(0xffffffffu, my_n, L);
+            if (lane == L + 1) { in_c = oc; in_n = on; }
+        }
     }
     const int fin_c = __shfl_sync(0xffffffffu, my_c, 31), fin_n = __shfl_sync(0xffffffffu, my_n, 31);
     // 5. what the incoming run adds in front of the range
@@ -752,7 +785,7 @@ __device__ __noinline__ int parallel_portion(const uint8_t* __restrict__ win, in
                 if (w.lead_closed) d[k++] = (uint8_t)(cls_flag(w.lead_c) | (uint32_t)(((c0 + w.lead_n - 1) % m_lead) + 1));
             }
         }
-        lane_walk<true>(win, b, b_next, p_end, ended, r_hi, d + k);
+        lane_walk<true>(win, B, T, S, nxt, p_end, ended, d + k);
         if (ended && lane == 31) {
             uint8_t* t = dst + (total - tail);
             if (fin_c >= 0) *t++ = (uint8_t)(cls_flag(fin_c) | (uint32_t)fin_n);
@@ -768,22 +801,22 @@ __device__ __noinline__ int parallel_portion(const uint8_t* __restrict__ win, in
     return p_end + 1;
 }
 
-// What to do with a step that holds a sample column that is not 3 bytes + separator.  Everything before the first such column q
-// is regular: the step is redone up to q (kOddRedo, cur = q).  When q is the step's first sample, lane 0 walks the odd-width
-// terms one by one (serial_portion) with the run that is open there, and the grid goes on behind them, in whatever phase that is.
-struct OddOut { int cur, o, flushed, nl_seg, ein0, flags; };
-enum { kOddLineEnd = 1, kOddEmpty = 2, kOddGiveUp = 4, kOddRedo = 8, kOddLookedBack = 16 };
-__device__ __noinline__ OddOut odd_step(const uint8_t* __restrict__ win, int base, uint32_t nc0, int kend, bool irr, int a, int ce, int cs,
-                                        int r_lo, int r_hi, bool first, bool need_lb, int ein_carry, int pc0, int tile,
-                                        const unsigned int* s1, uint8_t* __restrict__ stage, int o, int flushed, int nl_seg, int my_off,
-                                        int my_off2, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl, unsigned long long log_cap,
-                                        unsigned long long serial_budget, int lane, unsigned long long* seg_first,
-                                        unsigned long long* seg_prev, bool* dead) {
-    OddOut out = {a, o, flushed, nl_seg, 0, 0};
-    const int q = __reduce_min_sync(0xffffffffu, irr ? first_odd_sample(win, base, nc0, kend, r_lo, r_hi) : 0x7fffffff);
-    if (q > a) { out.cur = q; out.flags = kOddRedo; return out; }
+struct OddOut { int cur, o, flushed, nl_seg, ein0, flags, ein_carry; };
+enum { kOddLineEnd = 1, kOddEmpty = 2, kOddGiveUp = 4, kOddLookedBack = 16, kOddRunOpen = 32, kOddParMode = 64 };
+constexpr int kOddDense = 8;      // odd-width terms per 2 KB window from which on the walkers keep the line (and take the next one at once)
+// A step [a, ...) that holds a sample column that is not 3 bytes + separator: all lanes walk the window that begins at a
+// (parallel_portion; the samples in front of the odd one included), and the windows behind it while they are dense in odd
+// terms; then the grid goes on, in whatever phase that is, with the run that is open there.  A term that is longer than the
+// window goes to the term walker (serial_portion, lane 0).
+// direct: the previous line ended in a dense window -- this one (a line start: no run is open) comes here without the grid's attempt.
+__device__ __noinline__ OddOut odd_step(const uint8_t* __restrict__ win, int a, int ce, int cs, int r_lo, int r_hi, bool first, bool need_lb,
+                                        int ein_carry, int pc0, int tile, const unsigned int* s1, uint8_t* __restrict__ stage, int o,
+                                        int flushed, int nl_seg, int my_off, int my_off2, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
+                                        unsigned long long log_cap, unsigned long long serial_budget, int lane,
+                                        unsigned long long* seg_first, unsigned long long* seg_prev, bool* dead, bool direct) {
+    OddOut out = {a, o, flushed, nl_seg, 0, 0, kNoHead};
     int rcl = -1, rcn = 0;                               // open run: class, samples in its open chunk (1..M)
-    if (!first) {
+    if (!direct && !first) {
         if (need_lb) {                                   // (the tile's first step: the entering run's chunk count)
             int cnt_in = 0;
             if (lane == 0) cnt_in = lookback_count(s1, tile, pc0);
@@ -797,45 +830,90 @@ __device__ __noinline__ OddOut odd_step(const uint8_t* __restrict__ win, int bas
             rcn = (int)mod_chunk(((a - ein_carry) >> 2) - 1, pcl == 0) + 1;
         }
     }
-    int ended = 0;
-    const int r = serial_portion(win, a, ce, r_hi, rcl, rcn, stage, &out.o, &out.flushed, log, ctrl, log_cap, lane, seg_first, seg_prev, dead,
-                                 &out.nl_seg, my_off, my_off2, &ended);
-    if (r < 0) { out.flags |= r == -1 ? kOddEmpty : kOddGiveUp; return out; }   // an empty sample column / the block is given up
-    int over = 0;
-    if (lane == 0 && atomicAdd(&ctrl->serial_bytes, (unsigned long long)(r - a)) > serial_budget) over = 1;
-    if (__shfl_sync(0xffffffffu, over, 0)) { out.flags |= kOddGiveUp; return out; }   // (a safety valve: generic kernels)
-    out.cur = r;
-    if (VCFC_ENC_PARWALK && ended == 2) {                // eight odd-width terms in a row: the rest of the portion with all lanes
-        int run_c = -1, run_n = 0, at = r;
-        ended = 0;
-        while (!ended && at < ce) {
-            at = parallel_portion(win, at, ce, r_hi, stage, &out.o, &out.flushed, log, ctrl, log_cap, lane, seg_first, seg_prev, dead,
-                                  &out.nl_seg, my_off, my_off2, &ended, &run_c, &run_n);
-            if (at < 0) { out.flags |= kOddEmpty; return out; }
+    if (lane == 0) ctrl->odd_used = 1;
+    int at = a, ended = 0, n_odd = 0;
+    while (!ended && at < ce) {
+        const int nx = parallel_portion(win, at, ce, r_hi, stage, &out.o, &out.flushed, log, ctrl, log_cap, lane, seg_first, seg_prev, dead,
+                                        &out.nl_seg, my_off, my_off2, &ended, &rcl, &rcn, &n_odd);
+        if (nx == -1) { out.flags |= kOddEmpty; return out; }
+        if (nx == -2) {
+            // the term at `at` is longer than the window: the term walker writes it (with the run that is open in front of it)
+            const int r = serial_portion(win, at, ce, r_hi, rcl, rcn, stage, &out.o, &out.flushed, log, ctrl, log_cap, lane, seg_first, seg_prev,
+                                         dead, &out.nl_seg, my_off, my_off2, &ended);
+            if (r < 0) { out.flags |= r == -1 ? kOddEmpty : kOddGiveUp; return out; }   // an empty sample column / the block is given up
+            int over = 0;
+            if (lane == 0 && atomicAdd(&ctrl->serial_bytes, (unsigned long long)(r - at)) > serial_budget) over = 1;
+            if (__shfl_sync(0xffffffffu, over, 0)) { out.flags |= kOddGiveUp; return out; }   // (a safety valve: generic kernels)
+            at = r;
+            rcl = -1; rcn = 0;                           // (the walker stops behind an odd term or at the line's end: no run is open)
+            n_odd = kOddDense;
+            ended = ended == 1 ? 1 : 0;
+            continue;
         }
-        out.cur = at;                                    // (at ce with a run open: the next tile's look-back record has it)
+        at = nx;
+        if (n_odd < kOddDense) break;                    // few odd-width terms: the grid takes over again
     }
+    if (n_odd >= kOddDense) out.flags |= kOddParMode;
+    if (!ended && at < ce && rcl >= 0) { out.flags |= kOddRunOpen; out.ein_carry = at - 4 * rcn; }   // (a virtual head: rcn samples back)
+    out.cur = at;                                        // (at ce with a run open: the next tile's look-back record has it)
     if (ended) out.flags |= kOddLineEnd;
     return out;
+}
+
+// The call of odd_step with everything read from / written back to the warp's OddSave (see there).
+__device__ __noinline__ void odd_call(OddSave* S, const uint8_t* __restrict__ in, long long n, int tile_sz, const unsigned int* s1,
+                                      uint8_t* __restrict__ stage, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
+                                      unsigned long long log_cap, unsigned long long serial_budget, int lane,
+                                      unsigned long long* seg_first, unsigned long long* seg_prev, bool* dead) {
+    const int tile = S->tile;
+    const long long gb = (long long)tile * tile_sz - 64;
+    const uint8_t* const win = in + gb;
+    const int r_lo = gb < 0 ? 64 : 0;
+    const int r_hi = (int)(n - gb < (long long)(1 << 24) ? n - gb : (long long)(1 << 24));
+    const int a = S->odd_a;
+    const int bits = S->bits;
+    const OddOut r = odd_step(win, a, S->ce, S->cs, r_lo, r_hi, (bits & 2) != 0, (bits & 4) != 0, S->ein_carry, S->pc0, tile, s1, stage, S->o,
+                              S->flushed, S->nl_seg, S->my_off[lane], S->my_off2[lane], log, ctrl, log_cap, serial_budget, lane, seg_first, seg_prev,
+                              dead, S->odd_direct != 0);
+    __syncwarp();
+    if (lane == 0) {
+        if (r.flags & (kOddEmpty | kOddGiveUp)) { S->irregular = (r.flags & kOddEmpty) ? 6 : 7; S->action = 2; }
+        else {
+            int b = bits;
+            S->o = r.o; S->flushed = r.flushed; S->nl_seg = r.nl_seg; S->cur = r.cur;
+            S->par_mode = (r.flags & kOddParMode) ? 1 : 0;
+            if (r.flags & kOddLookedBack) { S->ein0 = r.ein0; b &= ~4; }
+            if (r.flags & kOddLineEnd) b |= 1;                            // behind the line's newline
+            if (r.flags & kOddRunOpen) { b &= ~2; S->ein_carry = r.ein_carry; }   // all lanes walked a stretch of 3-byte terms: its run is open
+            else { b |= 2; S->ein_carry = kNoHead; }                      // (the walkers stop behind an odd term: no run is open)
+            S->bits = b;
+            S->action = 0;
+        }
+    }
 }
 
 // kOdd = false: the kernel of regular blocks -- a sample column that is not 3 bytes + separator gives the block up with reject
 // reason kRejectOddTerms, and the host launches it again with kOdd = true (the term walkers compiled in; that instantiation is
 // ~4 % slower on regular blocks, which is why there are two).  The context remembers which one its stream of blocks needs.
 constexpr int kRejectOddTerms = 9;
+#ifndef VCFC_ENC_SCTAS_ODD
+#define VCFC_ENC_SCTAS_ODD VCFC_ENC_SCTAS
+#endif
 template <bool kOdd>
-__global__ void __launch_bounds__(32 * kSWarps, kSCtas)
+__global__ void __launch_bounds__(32 * kSWarps, kOdd ? VCFC_ENC_SCTAS_ODD : kSCtas)
 k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict__ log, Ctrl* __restrict__ ctrl,
                 unsigned int* __restrict__ s1, unsigned long long* __restrict__ rec_pos, unsigned long long* __restrict__ rec_size,
                 unsigned long long* __restrict__ rec_lines, int n_tiles, unsigned long long log_cap, int tile_sz,
                 unsigned long long serial_budget) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    SmemS& sm = *reinterpret_cast<SmemS*>(smem_raw);
+    using Smem = typename std::conditional<kOdd, SmemSO, SmemS>::type;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* const stage = sm.stage[warp];
     const int gw = (int)blockIdx.x * kSWarps + warp, nw = (int)gridDim.x * kSWarps;
     const size_t lane64 = 64u * (size_t)lane;
     int irr_seen = 0;                       // ctrl->irregular as of one tile ago (the load stays off the critical path)
+    if constexpr (kOdd) { if (lane == 0) sm.odd[warp].par_mode = 0; __syncwarp(); }
     // The warp runs one tile AHEAD with the end cut and the look-back #1 record: iteration k publishes the record of
     // this warp's tile k+1 and then encodes tile k, so a record is there a whole tile time before its reader needs it.
     constexpr int kFlSkip = 1 << 9;
@@ -945,27 +1023,26 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
             }
             if (lane == 0) *((volatile unsigned*)&s1[nt]) = word;
         }
-        int ce = cur_ce;                                 // (lowered for a while when a step is redone up to an odd-width sample)
-        const int fl = cur_fl;
+        int ce = cur_ce;
+        int fl = cur_fl;
         cur_ce = n_ce; cur_fl = n_fl;
         if (tile < 0 || (fl & kFlSkip)) continue;
         // ---- the tile itself ---------------------------------------------------------------------------------------------
-        const long long t0 = (long long)tile * tile_sz;
-        const long long gb = t0 - 64;                                   // tile-relative offsets: r = g - gb (a multiple of 64 apart)
-        const uint8_t* const win = in + gb;
-        const int r_lo = gb < 0 ? 64 : 0;                               // valid relative range [r_lo, r_hi)
-        const int r_hi = (int)(n - gb < (long long)(1 << 24) ? n - gb : (long long)(1 << 24));
+        // (not const: the kOdd instantiation sets them again behind the call of odd_step, see OddSave)
+        long long t0 = (long long)tile * tile_sz;
+        long long gb = t0 - 64;                                         // tile-relative offsets: r = g - gb (a multiple of 64 apart)
+        const uint8_t* win = in + gb;
+        int r_lo = gb < 0 ? 64 : 0;                                     // valid relative range [r_lo, r_hi)
+        int r_hi = (int)(n - gb < (long long)(1 << 24) ? n - gb : (long long)(1 << 24));
         int irregular = 0;
-        if (lane == 0) sm.ce_true[warp] = ce;
-        __syncwarp();
-        const int pf_lim = min(r_hi, ce + 127), pf_lim2 = min(r_hi, ce + 4095);   // how far the steps' prefetches may reach
+        int pf_lim = min(r_hi, ce + 127), pf_lim2 = min(r_hi, ce + 4095);   // how far the steps' prefetches may reach
         // the first 8 KB of the tile into L2 now; every step asks for the 2 KB that lie 8 KB ahead of it
         {
             const int pr = 64 + 128 * lane;
             if (pr + 128 <= r_hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(win + pr));
             if (pr + 4096 + 128 <= r_hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(win + pr + 4096));
         }
-        const int ke = fl & 15, lb_lc = (fl >> 4) & 15, lb_uniform = (fl >> 8) & 1, lb_nsamp = (ce - 64) >> 2;
+        int ke = fl & 15, lb_lc = (fl >> 4) & 15, lb_uniform = (fl >> 8) & 1, lb_nsamp = (ce - 64) >> 2;
         if (ke == kCutBad) irregular = 2;
         int ks, cs;
         {
@@ -993,9 +1070,7 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
         {
             int o = 0, cur = cs, ein_carry = ein0;
             bool in_req = ks == kCutLine, first = ks == kCutSampleFirst || prev_lit;    // first: no run is open before the next sample
-            bool odd_pending = false, odd_irr = false;       // a step that met an odd-width sample column (rare): see odd_step
-            int odd_a = 0, odd_base = 0, odd_kend = 0;
-            uint32_t odd_nc0 = 0;
+            bool odd_pending = false;                        // a step that met an odd-width sample column (rare): see odd_step
             for (;;) {
             while (cur < ce && !irregular) {
                 if (in_req) {
@@ -1016,6 +1091,13 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                         flushed = o;
                         cur = s0;
                         in_req = false; first = true; ein_carry = kNoHead;
+                        if constexpr (kOdd) {
+                            if (sm.odd[warp].par_mode) {
+                                if (lane == 0) { sm.odd[warp].odd_a = cur; sm.odd[warp].odd_direct = 1; }
+                                odd_pending = true;
+                                break;
+                            }
+                        }
                         continue;
                     }
                     {
@@ -1032,6 +1114,13 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                     o += 8 + rq;
                     cur = s0;
                     in_req = false; first = true; ein_carry = kNoHead;
+                    if constexpr (kOdd) {
+                        if (sm.odd[warp].par_mode) {
+                                if (lane == 0) { sm.odd[warp].odd_a = cur; sm.odd[warp].odd_direct = 1; }
+                                odd_pending = true;
+                                break;
+                            }
+                    }
                     continue;
                 }
                 // ---- a step of samples: those that start in [cur, bound), up to the line's end ---------------------------
@@ -1145,8 +1234,11 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                     }
                     if (__any_sync(0xffffffffu, irr)) {      // a sample column that is not 3 bytes + separator: handled behind the loop
                         if constexpr (!kOdd) { irregular = VCFC_ENC_NOSERIAL ? 6 : kRejectOddTerms; break; }
-                        odd_pending = true; odd_a = a; odd_base = base; odd_nc0 = V; odd_kend = kend; odd_irr = irr;
-                        break;
+                        else {
+                            if (lane == 0) { sm.odd[warp].odd_a = a; sm.odd[warp].odd_direct = 0; }
+                            odd_pending = true;
+                            break;
+                        }
                     }
                 }
                 const uint32_t F = (first && lane == 0) ? (1u << klo) : 0u;
@@ -1199,20 +1291,36 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 else cur = a + 4 * ((bound - a + 3) >> 2);
             }
             if constexpr (!kOdd) break;
-            if (!odd_pending) {
-                if (ce != sm.ce_true[warp] && !irregular) { ce = sm.ce_true[warp]; continue; }   // the capped redo is done: on to the odd sample
-                break;
-            }
-            if constexpr (kOdd) {   // (out of the hot loop: the grid steps' register allocation does not see this)
+            if (!odd_pending) break;
+            if constexpr (kOdd) {   // (out of the hot loop; nothing is live across the call: see OddSave)
                 odd_pending = false;
-                const OddOut r = odd_step(win, odd_base, odd_nc0, odd_kend, odd_irr, odd_a, ce, cs, r_lo, r_hi, first, need_lb, ein_carry, pc0, tile, s1,
-                                          stage, o, flushed, nl_seg, my_off, my_off2, log, ctrl, log_cap, serial_budget, lane, &seg_first, &seg_prev, &dead);
-                if (r.flags & kOddRedo) { ce = r.cur; continue; }         // redo the step up to the odd sample: ce is the cap meanwhile
-                if (r.flags & (kOddEmpty | kOddGiveUp)) { irregular = (r.flags & kOddEmpty) ? 6 : 7; break; }
-                o = r.o; flushed = r.flushed; nl_seg = r.nl_seg; cur = r.cur;
-                if (r.flags & kOddLookedBack) { ein0 = r.ein0; need_lb = false; }
-                if (r.flags & kOddLineEnd) in_req = true;                 // behind the line's newline
-                first = true; ein_carry = kNoHead;                        // (the walker stops behind an odd term: no run is open)
+                OddSave& S = sm.odd[warp];
+                if (lane == 0) {
+                    S.o = o; S.flushed = flushed; S.nl = nl; S.nl_seg = nl_seg; S.cur = cur; S.ein_carry = ein_carry; S.ein0 = ein0;
+                    S.bits = (in_req ? 1 : 0) | (first ? 2 : 0) | (need_lb ? 4 : 0); S.irregular = 0;
+                    S.ce = ce; S.cs = cs; S.pc0 = pc0; S.tile = tile; S.cur_ce = cur_ce; S.cur_fl = cur_fl; S.irr_seen = irr_seen; S.fl = fl;
+#if VCFC_ENC_TICKET
+                    S.nt = nt; S.nn = nn;
+#endif
+                }
+                S.my_off[lane] = my_off; S.my_off2[lane] = my_off2;
+                __syncwarp();
+                odd_call(&S, in, n, tile_sz, s1, stage, log, ctrl, log_cap, serial_budget, lane, &seg_first, &seg_prev, &dead);
+                __syncwarp();
+                o = S.o; flushed = S.flushed; nl = S.nl; nl_seg = S.nl_seg; cur = S.cur; ein_carry = S.ein_carry; ein0 = S.ein0;
+                in_req = (S.bits & 1) != 0; first = (S.bits & 2) != 0; need_lb = (S.bits & 4) != 0;
+                ce = S.ce; cs = S.cs; pc0 = S.pc0; tile = S.tile; cur_ce = S.cur_ce; cur_fl = S.cur_fl; irr_seen = S.irr_seen; fl = S.fl;
+#if VCFC_ENC_TICKET
+                nt = S.nt; nn = S.nn;
+#endif
+                my_off = S.my_off[lane]; my_off2 = S.my_off2[lane];
+                t0 = (long long)tile * tile_sz; gb = t0 - 64; win = in + gb;
+                r_lo = gb < 0 ? 64 : 0;
+                r_hi = (int)(n - gb < (long long)(1 << 24) ? n - gb : (long long)(1 << 24));
+                pf_lim = min(r_hi, ce + 127); pf_lim2 = min(r_hi, ce + 4095);
+                ke = fl & 15; lb_lc = (fl >> 4) & 15; lb_uniform = (fl >> 8) & 1; lb_nsamp = (ce - 64) >> 2;
+                const int action = S.action;
+                if (action == 2) { irregular = S.irregular; break; }
             }
             }
             // the input ends inside a line that no newline-less last sample closed (a trailing tab, a cut sample): generic path
@@ -1303,7 +1411,7 @@ __global__ void k_patch_headers(uint8_t* __restrict__ out, const unsigned long l
         res->err_line = 0;
         if (irregular) { res->status = kStatusIrregular; res->reserved = irregular; res->out_len = 0; res->n_lines = 0; res->err_line = nl; }
         else if (cap)  { res->status = VCFC_E_CAP; res->out_len = total; res->n_lines = 0; }
-        else           { res->status = VCFC_OK; res->out_len = total; res->n_lines = nl; res->reserved = ctrl->serial_bytes ? 1 : 0; }   // (reserved: term walkers used)
+        else           { res->status = VCFC_OK; res->out_len = total; res->n_lines = nl; res->reserved = ctrl->odd_used ? 1 : 0; }   // (reserved: term walkers used)
     }
 }
 
@@ -1334,7 +1442,7 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
     }
     if (!ctx->enc_attr_set) {                                  // per context: one context per (process, device), used by one thread at a time
         VCFC_CUDA(ctx, cudaFuncSetAttribute(k_encode_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
-        VCFC_CUDA(ctx, cudaFuncSetAttribute(k_encode_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemS)));
+        VCFC_CUDA(ctx, cudaFuncSetAttribute(k_encode_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSO)));
         ctx->enc_attr_set = 1;
     }
     // tile size (a multiple of 64): large tiles amortise the per-tile work (cuts, look-back record, log reservation), small
@@ -1369,7 +1477,7 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         int per_sm = 0;
         int per_sm_odd = 0;
         VCFC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_stream<false>, 32 * kSWarps, sizeof(SmemS)));
-        VCFC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_odd, k_encode_stream<true>, 32 * kSWarps, sizeof(SmemS)));
+        VCFC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_odd, k_encode_stream<true>, 32 * kSWarps, sizeof(SmemSO)));
         ctx->enc_resident = std::max(1, std::min(per_sm, per_sm_odd)) * ctx->sm_count;
     }
     const int resident = ctx->enc_resident;
@@ -1385,7 +1493,7 @@ int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_ou
         unsigned long long a_budget = (unsigned long long)(in_len / 32 + (1u << 18));  // odd-width terms beyond ~3 % of the block: generic kernels
         void* args[] = {&a_in, &a_n, &a_log, &ctrl, &a_s1, &rec_pos, &rec_size, &rec_lines, &a_tiles, &a_cap, &a_tile_sz, &a_budget};
         const void* kern = ctx->enc_odd ? (const void*)k_encode_stream<true> : (const void*)k_encode_stream<false>;
-        VCFC_CUDA(ctx, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(32 * kSWarps), args, sizeof(SmemS), stream));
+        VCFC_CUDA(ctx, cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(32 * kSWarps), args, ctx->enc_odd ? sizeof(SmemSO) : sizeof(SmemS), stream));
     }
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeEncode + 1], stream); ctx->ev_pending[kTimeEncode] = 1; }
     ctx->launches += 1;

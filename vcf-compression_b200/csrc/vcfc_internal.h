@@ -46,6 +46,7 @@ struct vcfc_ctx {
     int          enc_resident = 0;
     int          enc_odd = 0;         // the encoder instantiation with the odd-width term walkers is in use (vcfc_encode_block_dev)
     int          enc_odd_idle = 0;    // blocks in a row that did not need it
+    int          enc_odd_keep = 0;    // VCFC_ENC_FORCE_ODD: never go back to the regular instantiation
     int          dec_attr_set = 0;
     vcfc_result* h_result = nullptr;      // pinned
     vcfc_result* d_result = nullptr;
