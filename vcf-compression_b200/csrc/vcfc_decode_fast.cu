@@ -270,7 +270,7 @@ constexpr int kSzGroup = VCFC_DEC_SZGROUP;                       // 8, 16 or 32 
 constexpr int kSzLines = 32 / kSzGroup;
 __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long long* __restrict__ line_start,
                             unsigned long long n_lines, unsigned long long sample_count, unsigned long long* __restrict__ sizes,
-                            unsigned* __restrict__ ctab, unsigned* __restrict__ rq_arr, Ctrl* __restrict__ ctrl) {
+                            unsigned* __restrict__ ctab, unsigned* __restrict__ rq_arr, uint8_t* __restrict__ lflag, Ctrl* __restrict__ ctrl) {
     const unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31, gl = lane & (kSzGroup - 1), g0 = lane & ~(kSzGroup - 1);
     const unsigned gmask = (kSzGroup == 32 ? 0xFFFFFFFFu : ((1u << kSzGroup) - 1u)) << g0;
@@ -400,6 +400,7 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
     }
     const unsigned og = __ballot_sync(0xffffffffu, off_grid != 0) & gmask;
     if (live && gl == 0) {
+        lflag[k] = (og && !bad) ? 1 : 0;           // the line is off the 4-byte grid: its tiles go to the span-walking kernel
         if (og && !bad) atomicExch(&ctrl->not_grid, 1);
         sizes[k] = bad ? 0ull : total;
         if (bad) atomicExch(&ctrl->irregular, 1);
@@ -414,11 +415,15 @@ constexpr int kReqDirect = 2048;          // required sections longer than this 
 __global__ void k_dec_tilemap(const unsigned long long* __restrict__ off, unsigned long long n_lines, unsigned long long total,
                               const unsigned long long* __restrict__ line_start, const unsigned* __restrict__ rq_arr,
                               const unsigned* __restrict__ gtab, unsigned int* __restrict__ first_line,
-                              unsigned int* __restrict__ first_chunk, const unsigned long long tile) {
+                              unsigned int* __restrict__ first_chunk, const unsigned long long tile,
+                              const uint8_t* __restrict__ lflag, uint8_t* __restrict__ gflag, const unsigned long long gtile) {
     const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_lines) return;
     const unsigned long long a = off[k], b = k + 1 < n_lines ? off[k + 1] : total;
     if (b == a) return;
+    // a block that holds lines off the 4-byte sample grid: the fill-and-patch tiles (gtile bytes) such a line overlaps are
+    // left to the span-walking kernel, all others stay with k_dec_expand_grid
+    if (gflag && lflag[k]) for (unsigned long long t = a / gtile; t * gtile < b; t++) gflag[t] = 1;
     const unsigned long long ls = line_start[k];
     const long long rq = rq_arr[k];
     const int nch = (int)(((long long)(line_start[k + 1] - ls) - 8 - rq + 15) >> 4);
@@ -516,10 +521,11 @@ k_dec_expand(const uint8_t* __restrict__ in, const unsigned long long* __restric
              const unsigned long long* __restrict__ off, unsigned long long n_lines, unsigned long long total,
              const unsigned int* __restrict__ first_line, const unsigned int* __restrict__ first_chunk,
              const unsigned* __restrict__ rq_arr, const unsigned* __restrict__ gtab, uint8_t* __restrict__ out,
-             const Ctrl* __restrict__ ctrl) {
+             const Ctrl* __restrict__ ctrl, const uint8_t* __restrict__ gflag, unsigned per_g) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     if (ctrl->irregular) return;
+    if (gflag && !gflag[blockIdx.x / per_g]) return;    // (a mixed block: this tile belongs to k_dec_expand_grid)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long T0 = (unsigned long long)blockIdx.x * kTile;
     const int tile_len = (int)(total - T0 < (unsigned long long)kTile ? total - T0 : (unsigned long long)kTile);
@@ -782,16 +788,19 @@ k_dec_expand_grid(const uint8_t* __restrict__ in, const unsigned long long* __re
                   const unsigned long long* __restrict__ off, unsigned long long n_lines, unsigned long long total,
                   const unsigned int* __restrict__ first_line, const unsigned int* __restrict__ first_chunk,
                   const unsigned* __restrict__ rq_arr, const unsigned* __restrict__ gtab, uint8_t* __restrict__ out,
-                  const Ctrl* __restrict__ ctrl) {
+                  const Ctrl* __restrict__ ctrl, const uint8_t* __restrict__ gflag, unsigned per_g) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemG& sm = *reinterpret_cast<SmemG*>(smem_raw);
     if (ctrl->irregular) return;
+    // a mixed block: the tile map has one entry per tile of the span-walking kernel (per_g of them in one of these tiles), and
+    // the tiles that a line off the 4-byte grid overlaps are that kernel's
+    if (gflag && gflag[blockIdx.x]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long T0 = (unsigned long long)blockIdx.x * kTileG;
     const int tile_len = (int)(total - T0 < (unsigned long long)kTileG ? total - T0 : (unsigned long long)kTileG);
     const unsigned long long T1 = T0 + (unsigned long long)tile_len;
-    unsigned long long k0 = first_line[blockIdx.x];
-    unsigned fc_tile = first_chunk[blockIdx.x];         // chunk the batch's first line is staged from (kWholeLine: from its header)
+    unsigned long long k0 = first_line[blockIdx.x * per_g];
+    unsigned fc_tile = first_chunk[blockIdx.x * per_g]; // chunk the batch's first line is staged from (kWholeLine: from its header)
     bool contd = false;                                  // that line was begun by an earlier batch of this tile
     if (VCFC_DEC_BULK_LD && tid == 0) mbar_init(&sm.bar, 1);                 // (its first use is by this same thread; the others wait behind a barrier)
     uint32_t parity = 0;
@@ -1148,11 +1157,12 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
     if ((rc = dev_reserve(ctx, &b_sizes, (n_lines + 1) * 8))) return rc;
     if ((rc = dev_reserve(ctx, &b_offs, (n_lines + 1) * 8))) return rc;
     if ((rc = dev_reserve(ctx, &b_tab, ((size_t)in_len / 16 + n_lines + 8) * 4))) return rc;
-    if ((rc = dev_reserve(ctx, &b_rq, (n_lines + 2) * 4))) return rc;
+    if ((rc = dev_reserve(ctx, &b_rq, (n_lines + 2) * 4 + n_lines + 64))) return rc;
+    uint8_t* lflag = (uint8_t*)b_rq.p + (n_lines + 2) * 4;       // per line: off the 4-byte sample grid
     unsigned long long* line_start = (unsigned long long*)b_ls.p;
     k_dec_fill<<<gs, 128, 0, stream>>>(d_in, n, n_seg, cand, base, line_start, (unsigned*)b_rq.p, n_lines, ctrl);
     k_dec_sizes<<<(unsigned)(((n_lines + kSzLines - 1) / kSzLines * 32 + 127) / 128), 128, 0, stream>>>(d_in, line_start, n_lines, sample_count,
-                                                                             (unsigned long long*)b_sizes.p, (unsigned*)b_tab.p, (unsigned*)b_rq.p, ctrl);
+                                                                             (unsigned long long*)b_sizes.p, (unsigned*)b_tab.p, (unsigned*)b_rq.p, lflag, ctrl);
     ctx->launches += 2;
     if ((rc = scan_exclusive_u64(ctx, (uint64_t*)b_sizes.p, (uint64_t*)b_offs.p, (size_t)n_lines, (uint64_t*)&ctrl->total_out, &b_scr, stream)))
         return rc;
@@ -1170,21 +1180,32 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
         ctx->launches++;
         return VCFC_OK;
     }
-    const bool walk = h.not_grid || ctx->force_generic == 2;       // the span-walking kernel takes what is off the 4-byte grid
-    const unsigned long long tile = walk ? kTile : kTileG;
-    const unsigned long long n_tiles = (total + tile - 1) / tile;
-    if ((rc = dev_reserve(ctx, &b_tiles, n_tiles * 8 + 64))) return rc;
+    // Lines off the 4-byte sample grid (odd-width literals, required sections < 16 bytes) need the span-walking kernel; in a
+    // block that has some, only the fill-and-patch tiles such a line overlaps go there (mixed), the rest stays on k_dec_expand_grid
+    static_assert(kTileG % kTile == 0, "a fill-and-patch tile is a whole number of span-walking tiles");
+    const bool walk_all = ctx->force_generic == 2, mixed = h.not_grid && !walk_all;
+    const unsigned per_g = (walk_all || mixed) ? (unsigned)(kTileG / kTile) : 1u;
+    const unsigned long long tile = (walk_all || mixed) ? kTile : kTileG;
+    const unsigned long long n_tiles = (total + tile - 1) / tile, n_gt = (total + kTileG - 1) / kTileG;
+    if ((rc = dev_reserve(ctx, &b_tiles, n_tiles * 8 + n_gt + 128))) return rc;
     unsigned int* first_chunk = (unsigned int*)b_tiles.p + n_tiles;
+    uint8_t* gflag = (uint8_t*)(first_chunk + n_tiles);
+    if (mixed) VCFC_CUDA(ctx, cudaMemsetAsync(gflag, 0, n_gt, stream));
     k_dec_tilemap<<<(unsigned)((n_lines + 255) / 256), 256, 0, stream>>>((unsigned long long*)b_offs.p, n_lines, total, line_start,
                                                                           (const unsigned*)b_rq.p, (const unsigned*)b_tab.p,
-                                                                          (unsigned int*)b_tiles.p, first_chunk, tile);
+                                                                          (unsigned int*)b_tiles.p, first_chunk, tile, lflag,
+                                                                          mixed ? gflag : nullptr, (unsigned long long)kTileG);
     if (ctx->timing) cudaEventRecord(ctx->ev[2 * kTimeDecodeExpand], stream);
-    if (walk)
+    if (!walk_all)
+        k_dec_expand_grid<<<(unsigned)n_gt, kGThreads, sizeof(SmemG), stream>>>(d_in, line_start, (unsigned long long*)b_offs.p, n_lines,
+                                                                               total, (unsigned int*)b_tiles.p, first_chunk, (const unsigned*)b_rq.p, (const unsigned*)b_tab.p, d_out, ctrl,
+                                                                               mixed ? gflag : nullptr, per_g);
+    if (walk_all || mixed) {
         k_dec_expand<<<(unsigned)n_tiles, kXThreads, sizeof(Smem), stream>>>(d_in, line_start, (unsigned long long*)b_offs.p, n_lines,
-                                                                            total, (unsigned int*)b_tiles.p, first_chunk, (const unsigned*)b_rq.p, (const unsigned*)b_tab.p, d_out, ctrl);
-    else
-        k_dec_expand_grid<<<(unsigned)n_tiles, kGThreads, sizeof(SmemG), stream>>>(d_in, line_start, (unsigned long long*)b_offs.p, n_lines,
-                                                                                  total, (unsigned int*)b_tiles.p, first_chunk, (const unsigned*)b_rq.p, (const unsigned*)b_tab.p, d_out, ctrl);
+                                                                            total, (unsigned int*)b_tiles.p, first_chunk, (const unsigned*)b_rq.p, (const unsigned*)b_tab.p, d_out, ctrl,
+                                                                            mixed ? gflag : nullptr, per_g);
+        if (mixed) ctx->launches++;
+    }
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeDecodeExpand + 1], stream); ctx->ev_pending[kTimeDecodeExpand] = 1; }
     k_dec_result<<<1, 1, 0, stream>>>(d_result, ctrl, VCFC_OK, total, n_lines);
     ctx->launches += 3;

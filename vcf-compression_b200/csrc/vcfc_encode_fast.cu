@@ -315,6 +315,9 @@ __device__ __noinline__ int lookback_count(const unsigned int* s1, int tile, int
 #ifndef VCFC_ENC_NOSERIAL
 #define VCFC_ENC_NOSERIAL 0
 #endif
+#ifndef VCFC_ENC_PFW
+#define VCFC_ENC_PFW 0          // 1 / 2: the next step's words are loaded before this step's byte-count scan / token emission
+#endif
 #ifndef VCFC_ENC_TICKET
 #define VCFC_ENC_TICKET 1
 #endif
@@ -1124,10 +1127,22 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                     continue;
                 }
                 // ---- a step of samples: those that start in [cur, bound), up to the line's end ---------------------------
+#if VCFC_ENC_PFW
+                // (consecutive steps of a line run in a loop of their own: the words loaded ahead are live inside it only, and no
+                //  call lies between the load and their use)
+                bool w_ready = false;
+                uint32_t W[18];                              // the step's words; loaded one step ahead when the next step is known
+                for (;;) {
+#endif
                 const int a = cur, wstart = a & ~63, blk = wstart + 64 * lane, phase = a & 3, base = blk + phase;
                 const int bound = min(ce, wstart + kStep);
+#if !VCFC_ENC_PFW
                 uint32_t W[18];
+#endif
                 const uint8_t* const pb = win + blk;
+#if VCFC_ENC_PFW
+                if (w_ready) { w_ready = false; } else
+#endif
                 if (wstart - 4 >= r_lo && wstart + kStep + 4 <= r_hi) {
                     // the whole step lies inside the input (warp-uniform, all but the first / last step of the block): every lane
                     // loads its block and the two words around it itself -- the neighbours' words are L1 hits, cheaper than two
@@ -1276,6 +1291,25 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                 uint32_t cf = 0;
                 int h0 = 0;
                 const int n0 = item_count(it, ein, &cf, &h0);
+#if VCFC_ENC_PFW
+#define VCFC_LOAD_NEXT_STEP()                                                                                                   \
+                if (!endm) {                                                                                                    \
+                    const int a2 = a + 4 * ((bound - a + 3) >> 2), ws2 = a2 & ~63;                                              \
+                    if (a2 < ce && ws2 - 4 >= r_lo && ws2 + kStep + 4 <= r_hi) {                                                \
+                        const uint8_t* const pb2 = win + ws2 + 64 * lane;                                                       \
+                        _Pragma("unroll") for (int q = 0; q < 4; q++) {                                                         \
+                            const uint4 v = *reinterpret_cast<const uint4*>(pb2 + 16 * q);                                      \
+                            W[4 * q + 1] = v.x; W[4 * q + 2] = v.y; W[4 * q + 3] = v.z; W[4 * q + 4] = v.w;                     \
+                        }                                                                                                       \
+                        W[0] = *reinterpret_cast<const uint32_t*>(pb2 - 4);                                                     \
+                        W[17] = *reinterpret_cast<const uint32_t*>(pb2 + 64);                                                   \
+                        w_ready = true;                                                                                         \
+                    }                                                                                                           \
+                }
+#endif
+#if VCFC_ENC_PFW == 1
+                VCFC_LOAD_NEXT_STEP()
+#endif
                 int inc = n0;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
@@ -1284,11 +1318,19 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
                     flush_segment(stage, o - flushed, log, ctrl, log_cap, lane, &seg_first, &seg_prev, &dead, nl_seg, my_off, my_off2);
                     flushed = o; nl_seg = 0;
                 }
+#if VCFC_ENC_PFW == 2
+                VCFC_LOAD_NEXT_STEP()
+#endif
                 item_emit(win, it, cf, h0, stage + (o - flushed + inc - n0), rare);
                 o += step_total;
                 first = false;
                 if (endm) { cur = q_end + 1; in_req = true; }
                 else cur = a + 4 * ((bound - a + 3) >> 2);
+#if VCFC_ENC_PFW
+                if (!w_ready) break;
+                }
+                if (odd_pending) break;
+#endif
             }
             if constexpr (!kOdd) break;
             if (!odd_pending) break;
