@@ -18,7 +18,7 @@ def launches(path):
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
     agg = collections.OrderedDict()
     for r in rows:
-        name = r[4].split("(")[0].replace("vcfc::", "")
+        name = r[4].replace("void ", "").split("(")[0].split("<")[0].replace("vcfc::", "")     # (k_encode_stream<(bool)0> -> k_encode_stream)
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += float(r[-1]) / 1e3
