@@ -316,8 +316,11 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
         const long long off = base + 16ll * gl;
         int nb = (int)(tn - off < 0 ? 0 : (tn - off > 16 ? 16 : tn - off));
         if (base >= tn) nb = 0;
-        uint8_t b[16];
+        uint32_t v[4] = {0u, 0u, 0u, 0u};
         uint32_t lit_any = 0, set_any = 0, set_lit = 0, run_sum = 0, run_zero = 0;
+        const bool is_last = nb > 0 && off + nb == tn;
+        const bool full = nb == 16 && !is_last;                      // a full chunk inside the line (most are): no byte masks
+        const int nbv = nb - (is_last ? 1 : 0);                      // the line's final '\n' carries no text
         if (nb > 0) {       // five aligned 32-bit loads instead of sixteen byte loads; bytes past the line are never used
             const uintptr_t ga = reinterpret_cast<uintptr_t>(p + tb + off);
             const uint32_t* wp = reinterpret_cast<const uint32_t*>(ga & ~uintptr_t(3));
@@ -325,22 +328,15 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
             const int nwd = (nb + (int)(ga & 3) + 3) >> 2;          // aligned words that hold the chunk's nb bytes
             uint32_t w0 = wp[0], w1 = nwd > 1 ? wp[1] : 0u, w2 = nwd > 2 ? wp[2] : 0u, w3 = nwd > 3 ? wp[3] : 0u,
                      w4 = nwd > 4 ? wp[4] : 0u;
-            const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
-                                   __funnelshift_r(w3, w4, sh)};
-#pragma unroll
-            for (int i = 0; i < 16; i++) b[i] = (uint8_t)(v[i >> 2] >> (8 * (i & 3)));
-            // word-parallel view of the chunk: is there any literal marker (>= 0xE0) or tab / newline among its bytes,
-            // and what the bytes add up to when every one of them is a run token
-            const bool is_last = off + nb == tn;
-            const int nbv = nb - (is_last ? 1 : 0);                  // the line's final '\n' carries no text
-            if (nb == 16 && !is_last) {                              // a full chunk inside the line (most are): no byte masks
+            v[0] = __funnelshift_r(w0, w1, sh); v[1] = __funnelshift_r(w1, w2, sh); v[2] = __funnelshift_r(w2, w3, sh);
+            v[3] = __funnelshift_r(w3, w4, sh);
+            // word-parallel view of the chunk: is there any literal marker (>= 0xE0) among its bytes, and what the bytes add up
+            // to when every one of them is a run token
+            if (full) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const uint32_t wv = v[j];
-                    const uint32_t lm = wv & (wv << 1) & (wv << 2) & 0x80808080u;
-                    const uint32_t am = lm | zero_bytes(wv ^ 0x09090909u) | zero_bytes(wv ^ 0x0A0A0A0Au);
-                    lit_any |= lm;
-                    if (am) { set_any = am; set_lit = lm; }
+                    lit_any |= wv & (wv << 1) & (wv << 2) & 0x80808080u;
                     const uint32_t cv = wv & (0x7F7F7F7Fu ^ (((wv >> 7) & 0x01010101u) * 0x60u));
                     run_sum = __dp4a(cv, 0x01010101u, run_sum);
                     run_zero |= zero_bytes(cv);
@@ -352,29 +348,49 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
                     const uint32_t bm = nj >= 4 ? 0xFFFFFFFFu : (nj <= 0 ? 0u : ((1u << (8 * nj)) - 1u));
                     const uint32_t bmv = njv >= 4 ? 0xFFFFFFFFu : (njv <= 0 ? 0u : ((1u << (8 * njv)) - 1u));
                     const uint32_t wv = v[j];
-                    const uint32_t lm = wv & (wv << 1) & (wv << 2) & 0x80808080u & bm;                       // bytes >= 0xE0
-                    const uint32_t am = lm | ((zero_bytes(wv ^ 0x09090909u) | zero_bytes(wv ^ 0x0A0A0A0Au)) & bm);   // ... or tab / newline
-                    lit_any |= lm;
-                    if (am) { set_any = am; set_lit = lm; }                                             // the highest word that has a setter
+                    lit_any |= wv & (wv << 1) & (wv << 2) & 0x80808080u & bm;                                // bytes >= 0xE0
                     const uint32_t cv = wv & (0x7F7F7F7Fu ^ (((wv >> 7) & 0x01010101u) * 0x60u)) & bmv;     // run lengths
                     run_sum = __dp4a(cv, 0x01010101u, run_sum);
                     run_zero |= zero_bytes(cv | ~bmv);
                 }
             }
         }
-        // kind of the chunk's last setter: 1 = a byte >= 0xE0, 2 = tab / newline (kinds of setter above)
-        const int kind = set_any ? (((set_lit >> (31 - __clz(set_any))) & 1u) ? 1 : 2) : 0;
-        // state at chunk start: last setter of the nearest lower lane of the group that has one, else the carry
-        const unsigned has = __ballot_sync(0xffffffffu, kind != 0) & gmask;
-        const unsigned below = has & ((1u << lane) - 1u);
-        const int src = below ? 31 - __clz(below) : lane;
-        const int k_src = __shfl_sync(0xffffffffu, kind, src);
-        const int k_in = below ? k_src : carry_kind;
+        // The chunk's state (token / literal payload) at its first byte.  While no literal marker has been seen in the line -- in
+        // this round or before it (carry_kind) -- every chunk starts in token state and the tabs / newlines among its bytes are
+        // run tokens (counts 9 / 10): nothing to look for.  (A sparse file has a literal in about one line in a hundred.)
+        int kind = 0, k_in = 0;
+        unsigned has = 0;
+        if (__any_sync(0xffffffffu, lit_any != 0u || carry_kind == 1)) {
+            if (nb > 0) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int nj = nb - 4 * j;
+                    const uint32_t bm = nj >= 4 ? 0xFFFFFFFFu : (nj <= 0 ? 0u : ((1u << (8 * nj)) - 1u));
+                    const uint32_t wv = v[j];
+                    const uint32_t lm = wv & (wv << 1) & (wv << 2) & 0x80808080u & bm;
+                    const uint32_t am = lm | ((zero_bytes(wv ^ 0x09090909u) | zero_bytes(wv ^ 0x0A0A0A0Au)) & bm);   // ... or tab / newline
+                    if (am) { set_any = am; set_lit = lm; }                                             // the highest word that has a setter
+                }
+            }
+            // kind of the chunk's last setter: 1 = a byte >= 0xE0, 2 = tab / newline (kinds of setter above)
+            kind = set_any ? (((set_lit >> (31 - __clz(set_any))) & 1u) ? 1 : 2) : 0;
+            // state at chunk start: last setter of the nearest lower lane of the group that has one, else the carry
+            has = __ballot_sync(0xffffffffu, kind != 0) & gmask;
+            const unsigned below = has & ((1u << lane) - 1u);
+            const int src = below ? 31 - __clz(below) : lane;
+            const int k_src = __shfl_sync(0xffffffffu, kind, src);
+            k_in = below ? k_src : carry_kind;
+        }
         unsigned o = 0, ns = 0, tres = 0;
         int e = 0;
         if (nb > 0) {
             if (k_in != 1 && !lit_any) { o = 4u * run_sum; ns = run_sum; e = run_zero ? 1 : 0; }   // run tokens only
-            else chunk_measure(b, nb, k_in == 1, off + nb == tn, &o, &ns, &e, &tres);
+            else {
+                uint8_t b[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) b[i] = (uint8_t)(v[i >> 2] >> (8 * (i & 3)));
+                chunk_measure(b, nb, k_in == 1, is_last, &o, &ns, &e, &tres);
+            }
         }
         err_any |= e;
         // chunk table (text offset << 1 | payload state at the chunk's first byte), consumed by k_dec_expand;
@@ -390,8 +406,10 @@ __global__ void k_dec_sizes(const uint8_t* __restrict__ in, const unsigned long 
         if (tres & ~(1u << ((4u - ((unsigned)total + inc - o)) & 3u))) off_grid = 1;
         total += __shfl_sync(0xffffffffu, inc, g0 + kSzGroup - 1);
         ns_total += __shfl_sync(0xffffffffu, n32, g0 + kSzGroup - 1);
-        const int k_last = __shfl_sync(0xffffffffu, kind, has ? 31 - __clz(has) : lane);
-        if (has) carry_kind = k_last;
+        if (__any_sync(0xffffffffu, has != 0u)) {
+            const int k_last = __shfl_sync(0xffffffffu, kind, has ? 31 - __clz(has) : lane);
+            if (has) carry_kind = k_last;
+        }
     }
     const unsigned eg = __ballot_sync(0xffffffffu, err_any != 0) & gmask;
     if (live && !bad) {
