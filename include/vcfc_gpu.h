@@ -162,10 +162,12 @@ uint64_t vcfc_launch_count(const vcfc_ctx *ctx);
 /* Which kernels served the most recent block call: 1 = single-pass tile kernels (regular GT-only
  * lines), 2 = generic line-serial kernels (any input the reference accepts).  Both run on the GPU. */
 int vcfc_last_path(const vcfc_ctx *ctx);
-/* Why the tile kernels last declined a block (0 = never): 1 no final newline, 2 cut point not found inside the
- * halo (required section > 960 B), 3 more than 62 lines per 32 KB tile, 4 line grammar (empty field, < 10 columns,
- * sample region not a multiple of 4 bytes), 5 too many segments, 6 a sample column that is not 3 bytes wide,
- * 8 line table overflow, 9 follow-up of another tile's reject. */
+/* Why the tile kernels last declined a block (0 = never): 1 the input ends inside a line that nothing closes (a trailing
+ * tab), 2 cut point not found inside the halo (required section > ~32 KB), 4 line grammar (empty field, < 10 columns),
+ * 6 an empty sample column, 7 more than ~3 % of the block walked by the single-lane term walker (literals of many
+ * kilobytes), 8 line table overflow, 9 a sample column that is not 3 bytes wide met by the encoder instantiation for regular
+ * blocks -- not a hand-over to the generic kernels: the block is relaunched on the instantiation that carries the term
+ * walkers, and the context stays with it until eight blocks in a row did not need them. */
 int vcfc_last_reject_reason(const vcfc_ctx *ctx);
 /* Testing aid: on = 1 routes every block through the generic kernels; on = 2 keeps the tile kernels but makes the
  * decoder use its span-walking expansion kernel even when the fill-and-patch kernel applies; 0 = automatic. */
