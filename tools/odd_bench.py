@@ -130,6 +130,22 @@ def gtdp_part(args, codec, dev):
     body = cell.reshape(L, S * 10)
     gtdp = b"".join(r + body[i].tobytes() for i, r in enumerate(rows))
     run("all GT:DP:GQ (1000 samples per line)", gtdp, S, codec, dev, with_generic=not args.only_gtdp)
+    del gtdp, body, cell
+    # (c) chrX outside the pseudo-autosomal regions: the male columns (a fixed half of the samples) are haploid calls
+    L, S = max(1000, args.lines // 2), 2504
+    male = g.random(S) < 0.5
+    width = np.where(male, 2, 4)
+    start = np.concatenate([[0], np.cumsum(width)])[:-1]                  # the layout is the same for every line
+    af = (1.0 / (2 * S)) * (0.5 * 2 * S) ** g.random(L)
+    body = np.empty((L, int(width.sum())), dtype=np.uint8)
+    body[:, start] = (g.random((L, S)) < af[:, None]).astype(np.uint8) + 48
+    fem = start[~male]
+    body[:, fem + 1] = ord("|")
+    body[:, fem + 2] = (g.random((L, len(fem))) < af[:, None]).astype(np.uint8) + 48
+    body[:, start + width - 1] = 9
+    body[:, -1] = 10
+    lines = [b"X\t%d\t.\tC\tT\t.\tPASS\tDP=100\tGT\t" % (2700000 + 37 * i) + body[i].tobytes() for i in range(L)]
+    run("chrX shape: half of the 2504 sample columns haploid", b"".join(lines), S, codec, dev, with_generic=not args.only_gtdp)
 
 
 main()

@@ -599,12 +599,15 @@ __device__ __forceinline__ LaneWalk lane_walk(const uint8_t* __restrict__ win, i
     LaneWalk w = {-1, 0, false, -1, 0, 0, 0, 0, 0};
     bool in_lead = true;
     int o = 0;
-    while (T) {
-        const int i = __ffsll((long long)T) - 1;
+    int i_next = T ? __ffsll((long long)T) - 1 : -1;
+    while (i_next >= 0) {
+        const int i = i_next;
         T &= T - 1ull;
-        const unsigned long long sm = S >> i;
+        i_next = T ? __ffsll((long long)T) - 1 : -1;
         const int p = B + i;
-        const int e = sm ? p + __ffsll((long long)sm) - 1 : nxt;
+        int e;
+        if (i_next >= 0) e = B + i_next - 1;                   // the byte in front of the block's next term start is this term's separator
+        else { const unsigned long long sm = S >> i; e = sm ? p + __ffsll((long long)sm) - 1 : nxt; }
         const int len = e - p;
         if (len == 0) w.err = 1;
         if (len != 3) w.n_odd++;
