@@ -308,36 +308,46 @@ int vcfc::encode_block_host(vcfc_ctx* ctx, const uint8_t* in, size_t in_len, uin
             if ((rc = dev_reserve(ctx, &ctx->ix[2], 2 * per_cap + 32))) return rc;
         }
     }
-    while (pos < in_len && status == VCFC_OK) {
-        int s = i & 1;
-        size_t end = text_chunk_end(in, pos, in_len, chunk), len = end - pos;
+    // Chunk i lives in slot i & 1.  Its upload is queued a whole iteration before the encode call that waits for it (that
+    // call synchronises its stream to read the block's status), so while the host sits in encode(i) the upload of chunk
+    // i + 1 is already running on the other stream: the host -> device direction never idles between chunks.  Per slot and
+    // stream the order is H2D(i), kernels(i), D2H(result, output of i), H2D(i + 2).
+    struct Slot { size_t len; bool loaded; } sl[2] = {{0, false}, {0, false}};
+    auto load = [&](int s) -> int {     // the next chunk goes to slot s: queue its upload
+        sl[s].loaded = false;
+        if (pos >= in_len) return VCFC_OK;
+        const size_t end = text_chunk_end(in, pos, in_len, chunk), len = end - pos;
+        int r = dev_reserve(ctx, &ctx->d_in[s], len + 64);
+        if (r) return r;
+        cudaError_t e = cudaMemcpyAsync(ctx->d_in[s].p, in + pos, len, cudaMemcpyHostToDevice, ctx->copy_stream[s]);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "H2D");
+        sl[s].len = len; sl[s].loaded = true;
+        pos = end;
+        return VCFC_OK;
+    };
+    if ((rc = load(0)) == VCFC_OK) rc = load(1);
+    while (rc == VCFC_OK && status == VCFC_OK) {
+        const int s = i & 1;
+        if (!sl[s].loaded) break;
+        const size_t len = sl[s].len;
         cudaStream_t st = ctx->copy_stream[s];
-        VCFC_CUDA(ctx, cudaStreamSynchronize(st));   // slot s buffers are free once its last D2H is done
         size_t bound = std::min(vcfc_encode_bound(len), out_cap);
-        if ((rc = dev_reserve(ctx, &ctx->d_in[s], len + 64))) break;
         if ((rc = dev_reserve(ctx, &ctx->d_out[s], bound + 64))) break;
-        if ((rc = cudaMemcpyAsync(ctx->d_in[s].p, in + pos, len, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
-            rc = cuda_fail(ctx, (cudaError_t)rc, "H2D");
-            break;
-        }
         uint64_t* d_offs = nullptr;
         size_t cap_s = 0;
         if (want_offs) {
             cap_s = d_lo->cap / 16;
             d_offs = (uint64_t*)d_lo->p + (size_t)s * cap_s;
         }
-        // finish the other slot BEFORE a possibly synchronising encode call would delay its D2H
         if ((rc = vcfc_encode_block_dev(ctx, (const uint8_t*)ctx->d_in[s].p, len, (uint8_t*)ctx->d_out[s].p, bound, d_offs,
                                         cap_s, ctx->d_result + s, st)))
             break;
         VCFC_CUDA(ctx, cudaMemcpyAsync(ctx->h_result + s, ctx->d_result + s, sizeof(vcfc_result), cudaMemcpyDeviceToHost, st));
         pend[s] = {true, len, lines};
-        if ((rc = finish(s ^ 1))) break;
-        pos = end;
+        if ((rc = finish(s))) break;                 // (chunks finish in order: the output position is the running sum)
+        if ((rc = load(s))) break;
         i++;
     }
-    if (rc == VCFC_OK && status == VCFC_OK) rc = finish((i & 1));       // older slot first (keeps byte order)
-    if (rc == VCFC_OK && status == VCFC_OK) rc = finish((i & 1) ^ 1);
     for (int s = 0; s < 2; s++) cudaStreamSynchronize(ctx->copy_stream[s]);
     *out_len = o;
     if (n_lines) *n_lines = lines;
