@@ -2,6 +2,7 @@
 # GPU box: the round's closing measurements into gpurun_out/ (tag = $1): bench lines (kg full size, random), the ncu launch
 # list and one --set full capture of the four largest kernels on a 400k-line run, the odd-width blocks.
 tag=${1:-r2f}
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1 || echo "smoke failed"
 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err || echo "bench failed"
 python bench.py --kind random --no-cpu > gpurun_out/${tag}_bench_random.json 2> gpurun_out/${tag}_bench_random.err || echo "bench random failed"
 python tools/odd_bench.py > gpurun_out/${tag}_odd.jsonl 2> gpurun_out/${tag}_odd.err || echo "odd bench failed"
