@@ -589,6 +589,32 @@ def main():
                 out["decode"]["e2e"] = {"value": sum_over_ranks(float(e2e_in)) / ddt / 1e9, "unit": UNIT,
                                         "h2d_bytes_per_step": e2e_out, "d2h_bytes_per_step": e2e_in, "ms_per_step": ddt * 1e3,
                                         "round_trip_ok": bool(torch.equal(h_txt[:e2e_in], h_in))}
+                # the same bytes as plain copies in the decode direction (D2H of the text, H2D of the .vcfc)
+                try:
+                    s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+                    d_c = torch.empty(e2e_out + 64, dtype=torch.uint8, device=dev)
+
+                    def copies_dec():
+                        with torch.cuda.stream(s_a):
+                            h_txt[:e2e_in].copy_(d_buf[:e2e_in], non_blocking=True)
+                        with torch.cuda.stream(s_b):
+                            d_c[:e2e_out].copy_(h_out[:e2e_out], non_blocking=True)
+                        s_a.synchronize()
+                        s_b.synchronize()
+
+                    copies_dec()
+                    barrier()
+                    t1 = time.perf_counter()
+                    for _ in range(3):
+                        copies_dec()
+                    ct = max_over_ranks((time.perf_counter() - t1) / 3)
+                    barrier()
+                    ceil_d = sum_over_ranks(float(e2e_in)) / ct / 1e9
+                    out["decode"]["e2e"]["copy_ceiling"] = {"value": ceil_d, "unit": UNIT, "what": "pinned D2H of the text + H2D of the .vcfc bytes "
+                                                            "only, all ranks at once, two streams", "frac": out["decode"]["e2e"]["value"] / ceil_d}
+                    del d_c
+                except Exception as e:  # noqa: BLE001
+                    out["decode"]["e2e"]["copy_ceiling"] = {"error": str(e)[:120]}
                 del h_txt
             del h_in, h_out
         except RuntimeError as e:

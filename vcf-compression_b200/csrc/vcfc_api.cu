@@ -35,6 +35,21 @@ int dev_reserve(vcfc_ctx* ctx, DevBuf* b, size_t bytes) {
     return VCFC_OK;
 }
 
+__global__ void k_to_host(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int n) {
+    for (int i = threadIdx.x; i < n; i += 32) dst[i] = src[i];
+    __threadfence_system();
+}
+
+int fetch_small(vcfc_ctx* ctx, const void* d_src, void* h_dst, size_t bytes, cudaStream_t st) {
+    if (bytes > 256 || (bytes & 3)) return VCFC_E_ARG;
+    k_to_host<<<1, 32, 0, st>>>(ctx->d_map, (const uint32_t*)d_src, (int)(bytes / 4));
+    ctx->launches++;
+    VCFC_CUDA(ctx, cudaGetLastError());
+    VCFC_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(h_dst, ctx->h_map, bytes);
+    return VCFC_OK;
+}
+
 static size_t env_size(const char* name, size_t dflt) {
     const char* v = getenv(name);
     if (!v || !*v) return dflt;
@@ -65,6 +80,8 @@ int vcfc_gpu_init(int device, vcfc_ctx** out) {
     for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking);
     for (int i = 0; i < 2 * kTimeSlots && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_result, 4 * sizeof(vcfc_result));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_map, 256, cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&ctx->d_map, ctx->h_map, 0);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_result, 4 * sizeof(vcfc_result));
     if (e != cudaSuccess) {
         vcfc_gpu_destroy(ctx);
@@ -91,6 +108,7 @@ void vcfc_gpu_destroy(vcfc_ctx* ctx) {
     ctx->pin_free.clear();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    if (ctx->h_map) cudaFreeHost(ctx->h_map);
     if (ctx->d_result) cudaFree(ctx->d_result);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -150,16 +168,13 @@ int vcfc_force_generic(vcfc_ctx* ctx, int on) {
 int vcfc_fetch_result(vcfc_ctx* ctx, const vcfc_result* d_result, vcfc_result* h_result, void* stream) {
     if (!ctx || !d_result || !h_result) return VCFC_E_ARG;
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    VCFC_CUDA(ctx, cudaMemcpyAsync(ctx->h_result + 3, d_result, sizeof(vcfc_result), cudaMemcpyDeviceToHost, st));
-    VCFC_CUDA(ctx, cudaStreamSynchronize(st));
-    *h_result = ctx->h_result[3];
-    return VCFC_OK;
+    return fetch_small(ctx, d_result, h_result, sizeof(vcfc_result), st);
 }
 
 // ---- device-pointer forms -----------------------------------------------------------------
 static int peek_status(vcfc_ctx* ctx, const vcfc_result* d_result, cudaStream_t st, int* status) {
-    VCFC_CUDA(ctx, cudaMemcpyAsync(ctx->h_result + 2, d_result, sizeof(vcfc_result), cudaMemcpyDeviceToHost, st));
-    VCFC_CUDA(ctx, cudaStreamSynchronize(st));
+    int rc = fetch_small(ctx, d_result, ctx->h_result + 2, sizeof(vcfc_result), st);
+    if (rc) return rc;
     *status = ctx->h_result[2].status;
     if (*status == kStatusIrregular) ctx->last_reject = ctx->h_result[2].reserved;
     return VCFC_OK;

@@ -1163,8 +1163,7 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
     ctx->launches += 4;
     if ((rc = scan_exclusive_u64(ctx, (const uint64_t*)cnt, (uint64_t*)base, (size_t)n_seg, (uint64_t*)&ctrl->n_lines, &b_scr, stream))) return rc;
     struct { int irregular, n_fix; unsigned long long n_lines, end_pos, total_out; int not_grid, pad; } h;
-    VCFC_CUDA(ctx, cudaMemcpyAsync(&h, ctrl, sizeof(h), cudaMemcpyDeviceToHost, stream));
-    VCFC_CUDA(ctx, cudaStreamSynchronize(stream));
+    if ((rc = fetch_small(ctx, ctrl, &h, sizeof(h), stream))) return rc;
     if (h.irregular || h.n_lines == 0 || h.n_lines >= (1ull << 32)) {
         k_dec_result<<<1, 1, 0, stream>>>(d_result, nullptr, kStatusIrregular, 0, 0);
         ctx->launches++;
@@ -1185,8 +1184,7 @@ int decode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint64_t samp
     if ((rc = scan_exclusive_u64(ctx, (uint64_t*)b_sizes.p, (uint64_t*)b_offs.p, (size_t)n_lines, (uint64_t*)&ctrl->total_out, &b_scr, stream)))
         return rc;
     if (ctx->timing) { cudaEventRecord(ctx->ev[2 * kTimeDecodeScan + 1], stream); ctx->ev_pending[kTimeDecodeScan] = 1; }
-    VCFC_CUDA(ctx, cudaMemcpyAsync(&h, ctrl, sizeof(h), cudaMemcpyDeviceToHost, stream));
-    VCFC_CUDA(ctx, cudaStreamSynchronize(stream));
+    if ((rc = fetch_small(ctx, ctrl, &h, sizeof(h), stream))) return rc;
     if (h.irregular) {
         k_dec_result<<<1, 1, 0, stream>>>(d_result, nullptr, kStatusIrregular, 0, 0);
         ctx->launches++;

@@ -49,6 +49,8 @@ struct vcfc_ctx {
     int          enc_odd_keep = 0;    // VCFC_ENC_FORCE_ODD: never go back to the regular instantiation
     int          dec_attr_set = 0;
     vcfc_result* h_result = nullptr;      // pinned
+    uint32_t*    h_map = nullptr;         // 256 bytes of mapped pinned memory: small results written by a kernel (fetch_small)
+    uint32_t*    d_map = nullptr;         // ... its device address
     vcfc_result* d_result = nullptr;
     // instrumentation
     int          timing      = 0;
@@ -93,6 +95,10 @@ int scan_exclusive_u64(vcfc_ctx* ctx, const uint64_t* d_in, uint64_t* d_out, siz
 // ---- fast (regular GT-only lines; single pass, tile-parallel) path ----
 // Return VCFC_OK with d_result->status == kStatusIrregular when the input needs the generic path.
 constexpr int kStatusIrregular = -100;
+// A few words from device memory to the host WITHOUT the copy engine: a one-warp kernel writes them to mapped pinned memory,
+// then the stream is synchronised.  (A cudaMemcpyAsync of 40 bytes queues behind whatever bulk copy of the same direction is in
+// flight on another stream -- in vcfc_decode_block that is the previous chunk's half gigabyte of text.)  bytes <= 256, multiple of 4.
+int fetch_small(vcfc_ctx* ctx, const void* d_src, void* h_dst, size_t bytes, cudaStream_t st);
 int encode_fast(vcfc_ctx* ctx, const uint8_t* d_in, size_t in_len, uint8_t* d_out, size_t out_cap,
                 uint64_t* d_line_out_offsets, size_t line_cap, vcfc_result* d_result,
                 cudaStream_t stream);
