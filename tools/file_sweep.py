@@ -17,13 +17,13 @@ def best(fn, k=3):
     for _ in range(k):
         t = time.perf_counter(); rc = fn(); ts.append(time.perf_counter() - t); assert rc == 0
     return min(ts)
-for readers, writers, chunk, dchunk in [(8, 2, 64, 8), (8, 2, 16, 8), (12, 4, 32, 8), (16, 8, 32, 4), (4, 2, 32, 8), (8, 8, 32, 16), (8, 12, 32, 2)]:
-    os.environ.update(VCFC_READERS=str(readers), VCFC_WRITERS=str(writers), VCFC_FILE_CHUNK_MB=str(chunk), VCFC_FILE_DCHUNK_MB=str(dchunk))
+for twins, readers, writers, chunk, dchunk in [(0, 8, 3, 16, 4), (1, 8, 3, 16, 4), (1, 8, 3, 32, 4), (1, 12, 3, 16, 4), (1, 12, 3, 32, 8), (1, 16, 4, 32, 4), (0, 12, 3, 32, 4)]:
+    os.environ.update(VCFC_FILE_TWINS=str(twins), VCFC_READERS=str(readers), VCFC_WRITERS=str(writers), VCFC_FILE_CHUNK_MB=str(chunk), VCFC_FILE_DCHUNK_MB=str(dchunk))
     codec.compress(ip, op)
     tc = best(lambda: codec.compress(ip, op))
     codec.decompress2_fd(op, rp)
     td = best(lambda: codec.decompress2_fd(op, rp), 2)
-    print(f"readers {readers:2d} writers {writers:2d} chunk {chunk:3d} MB dchunk {dchunk:2d} MB: compress {n/tc/1e9:6.2f} GB/s  decompress {n/td/1e9:6.2f} GB/s", flush=True)
+    print(f"twins {twins} readers {readers:2d} writers {writers:2d} chunk {chunk:3d} MB dchunk {dchunk:2d} MB: compress {n/tc/1e9:6.2f} GB/s  decompress {n/td/1e9:6.2f} GB/s", flush=True)
 # plain file copy speed of this box's tmpfs (one thread, read + write), for scale
 t = time.perf_counter(); subprocess.run(["cp", ip, rp]); print(f"cp on tmpfs: {n/(time.perf_counter()-t)/1e9:.2f} GB/s; nproc {os.cpu_count()}")
 for x in (ip, op, rp): os.remove(x)

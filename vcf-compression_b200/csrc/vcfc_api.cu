@@ -95,6 +95,7 @@ int vcfc_gpu_init(int device, vcfc_ctx** out) {
 
 void vcfc_gpu_destroy(vcfc_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->twin) { vcfc_gpu_destroy(ctx->twin); ctx->twin = nullptr; }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto& b : ctx->ws) if (b.p) cudaFree(b.p);

@@ -49,6 +49,7 @@ struct vcfc_ctx {
     int          enc_odd_keep = 0;    // VCFC_ENC_FORCE_ODD: never go back to the regular instantiation
     int          dec_attr_set = 0;
     vcfc_result* h_result = nullptr;      // pinned
+    vcfc_ctx*    twin = nullptr;          // a second context on the same device, made by the file verbs (two chunks in flight per GPU)
     uint32_t*    h_map = nullptr;         // 256 bytes of mapped pinned memory: small results written by a kernel (fetch_small)
     uint32_t*    d_map = nullptr;         // ... its device address
     vcfc_result* d_result = nullptr;
