@@ -297,7 +297,25 @@ def index_query_bench(pkg, codec, dev):
     return res
 
 # ------------------------------------------------------------------------------------------------
+_RESULT_FD = None
+
+
+def emit(obj):
+    """The ONE JSON line, on the process's real stdout (see main: fd 1 points at stderr meanwhile)."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def main():
+    # Libraries write to stdout behind Python's back (NCCL's version banner, also when it is switched on in a conf file): fd 1
+    # points at stderr while the bench runs, and only the result line goes to the real stdout.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -336,7 +354,7 @@ def main():
         v = statistics.median(enc)
         desc = (f"first {n_lines} lines ({total / 1e6:.0f} MB) of the workload, sharded by lines over {used} processes of the "
                 f"{'unmodified reference CLI (oracle/_ref/main_release compress)' if kind == 'reference' else 'oracle port'}, files in /dev/shm")
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        emit(({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / v / 1e6,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                           "data": "synthetic", "config": config,
@@ -643,7 +661,7 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
 
 
 if __name__ == "__main__":
