@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Debug aid (GPU box): encode seeded blocks on the CUDA path and on the oracle, print where they first differ.
-    python tools/encdiff.py
+    python tests/encdiff.py
 """
 import importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
