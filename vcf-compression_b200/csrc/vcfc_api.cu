@@ -265,7 +265,10 @@ int vcfc::encode_block_host(vcfc_ctx* ctx, const uint8_t* in, size_t in_len, uin
                             uint64_t* line_out_offsets, size_t line_cap, size_t* n_lines, uint64_t* err_line, LineIndexOut* idx) {
     if (!ctx || (in_len && (!in || !out)) || !out_len) return VCFC_E_ARG;
     VCFC_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t chunk = env_size("VCFC_CHUNK_MB", 256) << 20;
+    // device chunk: 256 MB for large inputs; a sixteenth of the input (at least 32 MB) for smaller ones, so that the first upload --
+    // which nothing overlaps -- stays a small part of the call
+    size_t chunk = env_size("VCFC_CHUNK_MB", 0) << 20;
+    if (!chunk) chunk = std::min<size_t>((size_t)256 << 20, std::max<size_t>((size_t)32 << 20, ((in_len / 16) + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1)));
     size_t pos = 0, o = 0, lines = 0;
     int status = VCFC_OK;
     uint64_t eline = 0;
