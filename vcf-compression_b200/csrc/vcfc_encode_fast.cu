@@ -1,12 +1,11 @@
-// vcfc_encode_fast.cu -- single-pass, tile-parallel encoder for REGULAR data lines (sm_100a).
+// vcfc_encode_fast.cu -- single-pass, tile-parallel encoder for data lines (sm_100a).
 //
-// "Regular" = what a GT-only VCF looks like: '\n'-terminated lines, single tabs, >= 10 columns,
-// every sample column exactly 3 bytes (a|b, a/b, ./. ...), required section (CHROM..FORMAT) of
-// at most kMaxReq bytes (~32 KB: long REF / ALT / INFO columns stay on this path).  Anything else sets
-// ctrl->irregular and the caller reruns the block on the generic kernels (vcfc_generic.cu).
+// Grammar of the tile path: '\n'-terminated lines (the last one may end with the input), single tabs, >= 10 columns, no empty
+// column, required section (CHROM..FORMAT) of at most kMaxReq bytes (~32 KB: long REF / ALT / INFO columns stay on this path).
+// Anything else sets ctrl->irregular and the caller reruns the block on the generic kernels (vcfc_generic.cu).
 // Output bytes are those of compress_data_line (/root/reference/src/compress.cpp:5-203) for every line.
 //
-// k_encode_stream: ONE WARP per tile of 32 KB, no CTA barriers; HBM traffic = input read once + output
+// k_encode_stream<kOdd>: ONE WARP per tile of 32 ... 256 KB, no CTA barriers; HBM traffic = input read once + output
 // written once (+ the tile log, see 6):
 //   1. cut points: a tile owns the units (one sample column, or one whole required section) that
 //      START in [cut(i*T), cut((i+1)*T)); both neighbours derive the shared cut from the same bytes
@@ -15,14 +14,18 @@
 //      tiles back; a tile publishes its record before doing anything else
 //   3. the warp walks its tile line by line: a line start = 9th tab found 512 bytes per round trip,
 //      two length headers + the required section copied through
-//   4. samples in steps of 2 KB: every lane loads one 64-byte block (16 phase-aligned sample words)
-//      straight into registers and classifies it into 16-bit masks: valid / coded / literal / run head /
-//      closing token / allele bits; the line's '\n' ends the step
+//   4. samples in steps of 2 KB on the 4-byte GRID (every sample column 3 bytes + separator): every lane loads one 64-byte
+//      block (16 phase-aligned sample words) straight into registers and classifies it into 16-bit masks: valid / coded /
+//      literal / run head / closing token / allele bits; the line's '\n' ends the step
 //   5. closed-form byte count per lane -> warp scan -> tokens and literals into a per-warp staging area
 //   6. the tile's bytes are appended to a tile log at a position reserved with ONE atomicAdd (no scan
 //      chain); two device scans over the per-tile (bytes, lines) records give the final positions,
 //      k_gather_tiles moves the bytes and k_patch_headers fills in the 4-byte line-length headers
 //      (they need the NEXT line's offset) and the result block.
+// Sample columns that are NOT 3 bytes wide (10|0, haploid calls, GT:DP:GQ ...): <false> gives the block up at once and the host
+// relaunches it on <true>, where odd_step sends the 2 KB window that holds such a column to the term walkers
+// (parallel_portion: all lanes, 64-bit separator masks; literal-only windows in one pass; serial_portion: terms longer than
+// the window) and the grid goes on behind it.  See DESIGN.md, "Odd-width sample columns".
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
@@ -973,7 +976,9 @@ k_encode_stream(const uint8_t* __restrict__ in, long long n, uint8_t* __restrict
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* const stage = sm.stage[warp];
+#if !VCFC_ENC_TICKET
     const int gw = (int)blockIdx.x * kSWarps + warp, nw = (int)gridDim.x * kSWarps;
+#endif
     const size_t lane64 = 64u * (size_t)lane;
     int irr_seen = 0;                       // ctrl->irregular as of one tile ago (the load stays off the critical path)
     if constexpr (kOdd) { if (lane == 0) sm.odd[warp].par_mode = 0; __syncwarp(); }

@@ -283,7 +283,7 @@ int vcfc_query_binned_index_file(vcfc_ctx* ctx, const char* vcfc_path, const cha
     if (rc) return rc;
     HostFile f, x;
     if ((rc = f.load(vcfc_path))) return rc;
-    if ((rc = x.load((std::string(vcfc_path) + ".vcfci").c_str()))) return rc;
+    if ((rc = x.load((std::string(vcfc_path) + ".vcfci").c_str())) != VCFC_OK) return rc;
     size_t hlen = 0;
     uint64_t sc = 0;
     if ((rc = vcfc_parse_headers(f.p, f.n, &hlen, &sc))) return rc;
