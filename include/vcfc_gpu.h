@@ -84,8 +84,11 @@ int vcfc_encode_block(vcfc_ctx *ctx, const uint8_t *in, size_t in_len,
  * context's stream), input and output stay in device memory, and d_result (device memory,
  * sizeof(vcfc_result)) is written by the last kernel.  The call is NOT fully asynchronous: before
  * it returns it synchronises `stream` once to read the block's status, because a block outside the
- * tile kernels' grammar is rerun on the generic kernels inside the same call (the decode form
- * synchronises twice more to size its line table and tile map).  When it returns, d_result is
+ * tile kernels' grammar is rerun on the generic kernels inside the same call, and the first block with
+ * sample columns that are not 3 bytes wide is relaunched once on the encoder instantiation that
+ * carries the term walkers (the context then stays with it; see vcfc_last_reject_reason).  The decode form
+ * synchronises twice more to size its line table and tile map.  The status words travel through mapped
+ * pinned memory, not through the copy engine, so bulk copies on other streams do not delay them.  When it returns, d_result is
  * final; read it with vcfc_fetch_result or your own copy.  A context is used by one host thread
  * at a time; use one context per GPU and per concurrent caller.
  */
