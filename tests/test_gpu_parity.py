@@ -358,38 +358,15 @@ def test_odd_stretch_transitions(codec):
 
 @pytest.mark.parametrize("seed", range(12))
 def test_odd_width_fuzz(codec, seed):
-    """Random blocks of random term mixes against the oracle, both directions: every line draws its own mix of coded genotypes,
-    3-byte literals, odd-width terms of 1 ... 14 bytes and (rarely) literals of kilobytes, in stretches of random length, so that
-    the encoder's grid / all-lane windows / literal-only windows / term walker and the decoder's two tile kernels meet in every
-    order; sample counts from 1 to a few thousand, lines that end at EOF."""
+    """Random blocks of random term mixes against the oracle, both directions (vcfgen.odd_mix_lines: every line draws its own mix
+    of coded genotypes, 3-byte literals, odd-width terms of 1 ... 14 bytes and, rarely, literals of kilobytes, in stretches of
+    random length), so that the encoder's grid / all-lane windows / literal-only windows / term walker and the decoder's two tile
+    kernels meet in every order; sample counts from 1 to a few thousand, lines that end at EOF.  The oracle is pinned on the same
+    generator against the unmodified reference binary (tests/test_oracle.py::test_odd_mix_vs_reference_binary)."""
     rng = __import__("random").Random(1000 + seed)
-    coded = (b"0|0", b"0|0", b"0|0", b"0|1", b"1|0", b"1|1")
-    lit3 = (b"./.", b"0/0", b"0/1", b"2|0", b"1|2", b".|.")
-
-    def term(kind):
-        if kind == 0: return rng.choice(coded)
-        if kind == 1: return rng.choice(lit3)
-        if kind == 2: return bytes(rng.choice(b"01.2") for _ in range(rng.choice((1, 1, 1, 2, 2))))       # haploid calls, "12"
-        if kind == 3: return rng.choice(coded + lit3) + b":" + b":".join(str(rng.randrange(10 ** rng.randrange(1, 4))).encode() for _ in range(rng.randrange(1, 4)))
-        if kind == 4: return rng.choice((b"10|0", b"0|10", b"0|0|0", b"11|12"))
-        return b"0|1:" + bytes(rng.choice(b"0123456789,") for _ in range(rng.choice((300, 2040, 2100, 5000))))
-
     for _ in range(5):
         n_samples = rng.choice((1, 2, 7, 31, 64, 500, 1000, 2504, 6000))
-        lines = []
-        for i in range(rng.choice((1, 3, 20, 60))):
-            weights = [rng.choice((0, 1, 8, 40)), rng.choice((0, 0, 1, 5)), rng.choice((0, 0, 3, 30)), rng.choice((0, 0, 3, 30)),
-                       rng.choice((0, 0, 1)), rng.choice((0, 0, 0, 0.02))]
-            if not any(weights): weights[0] = 1
-            terms = []
-            while len(terms) < n_samples:
-                kind = rng.choices(range(6), weights)[0]
-                if kind == 0 and rng.random() < 0.5:
-                    terms += [rng.choice(coded)] * rng.choice((1, 2, 30, 31, 32, 126, 127, 128, 300))      # runs at the chunk limits
-                else:
-                    terms += [term(kind) for _ in range(rng.choice((1, 1, 3, 9, 40)))]
-            lines.append(b"%d\t%d\t.\tA\tC\t.\tPASS\tDP=%d\tGT\t" % (rng.randrange(1, 23), 100 + i, i) + b"\t".join(terms[:n_samples]) + b"\n")
-        data = b"".join(lines)
+        data = b"".join(vcfgen.odd_mix_lines(rng, n_samples, rng.choice((1, 3, 20, 60))))
         if rng.random() < 0.3:
             data = data[:-1]                                     # the last line ends with the input
         check_block(codec, data, sample_count=n_samples)

@@ -160,6 +160,30 @@ def test_fuzz_vs_reference_binary(tmp_path):
         assert rc == 0 and txt == open(rp, "rb").read(), case
 
 
+@pytest.mark.skipif(not O.have_ref_binary(), reason="oracle/_ref/main_release not built")
+def test_odd_mix_vs_reference_binary(tmp_path):
+    """The generator of the GPU suite's odd-width fuzz (haploid stretches, GT:DP:GQ stretches, multi-digit alleles, literals of
+    kilobytes, runs at the chunk limits) through the unmodified reference binary: the oracle writes the same bytes both ways, so the
+    CUDA path is compared with something the reference itself confirms on this class of input."""
+    import random
+    for seed in range(8):
+        rng = random.Random(500 + seed)
+        n_samples = rng.choice((1, 2, 7, 31, 64, 500, 1000, 2504))
+        lines = vcfgen.odd_mix_lines(rng, n_samples, rng.choice((1, 3, 20)))
+        vcf = vcfgen.header(n_samples) + b"".join(lines)
+        if rng.random() < 0.3:
+            vcf = vcf[:-1]                                       # the last line ends with the file
+        ip, op, rp = (str(tmp_path / x) for x in ("a.vcf", "a.vcfc", "a.rt"))
+        open(ip, "wb").write(vcf)
+        assert subprocess.run([O.REF_BIN, "compress", ip, op], capture_output=True).returncode == 0, seed
+        ref = open(op, "rb").read()
+        rc, mine = O.compress_vcf(vcf)
+        assert rc == 0 and mine == ref, seed
+        assert subprocess.run([O.REF_BIN, "decompress", op, rp], capture_output=True).returncode == 0, seed
+        rc, txt = O.decompress_vcfc(ref)
+        assert rc == 0 and txt == open(rp, "rb").read(), seed
+
+
 # ---- binned index (.vcfci): oracle of the next scope row (SURVEY.md 8f N1), not yet served by the CUDA library ----
 def test_binned_index_golden():
     """vcfc_oracle_build_binned_index == the .vcfci files written by `main_release create-binned-index`

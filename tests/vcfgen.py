@@ -161,3 +161,33 @@ def run_length_lines(lengths=(1, 30, 31, 32, 62, 63, 126, 127, 128, 254, 255, 30
             lines.append(b"2\t%d\t.\tC\tG\t.\t.\t.\tGT\t" % pos + b"\t".join(samples) + b"\n")
             pos += 1
     return lines
+
+
+def odd_mix_lines(rng, n_samples: int, n_lines: int):
+    """Data lines whose sample columns are a random mix, drawn per line, of coded genotypes (in runs around the 31 / 127 chunk
+    limits), 3-byte literals, haploid calls, GT:DP[:GQ] columns, multi-digit alleles and (rarely) literals of kilobytes."""
+    coded = (b"0|0", b"0|0", b"0|0", b"0|1", b"1|0", b"1|1")
+    lit3 = (b"./.", b"0/0", b"0/1", b"2|0", b"1|2", b".|.")
+
+    def term(kind):
+        if kind == 0: return rng.choice(coded)
+        if kind == 1: return rng.choice(lit3)
+        if kind == 2: return bytes(rng.choice(b"01.2") for _ in range(rng.choice((1, 1, 1, 2, 2))))       # haploid calls, "12"
+        if kind == 3: return rng.choice(coded + lit3) + b":" + b":".join(str(rng.randrange(10 ** rng.randrange(1, 4))).encode() for _ in range(rng.randrange(1, 4)))
+        if kind == 4: return rng.choice((b"10|0", b"0|10", b"0|0|0", b"11|12"))
+        return b"0|1:" + bytes(rng.choice(b"0123456789,") for _ in range(rng.choice((300, 2040, 2100, 5000))))
+
+    lines = []
+    for i in range(n_lines):
+        weights = [rng.choice((0, 1, 8, 40)), rng.choice((0, 0, 1, 5)), rng.choice((0, 0, 3, 30)), rng.choice((0, 0, 3, 30)),
+                   rng.choice((0, 0, 1)), rng.choice((0, 0, 0, 0.02))]
+        if not any(weights): weights[0] = 1
+        terms = []
+        while len(terms) < n_samples:
+            kind = rng.choices(range(6), weights)[0]
+            if kind == 0 and rng.random() < 0.5:
+                terms += [rng.choice(coded)] * rng.choice((1, 2, 30, 31, 32, 126, 127, 128, 300))      # runs at the chunk limits
+            else:
+                terms += [term(kind) for _ in range(rng.choice((1, 1, 3, 9, 40)))]
+        lines.append(b"%d\t%d\t.\tA\tC\t.\tPASS\tDP=%d\tGT\t" % (rng.randrange(1, 23), 100 + i, i) + b"\t".join(terms[:n_samples]) + b"\n")
+    return lines
